@@ -1,0 +1,139 @@
+// C-ABI plumbing (version, thread-local error, launch counter) + optimizer / cast / fill kernels.
+//   Adam : Keras 2.2.4 optimizers.Adam as configured at segmentation.ipynb cell "compile" (ipynb:107):
+//          Adam(lr=7e-4, epsilon=1e-8, decay=1e-6)
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace dlb {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return DLB_ERR_CUDA;
+  }
+  return DLB_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+__global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
+                            float eps, float decay, float gmult) {
+  const long long it = *step;                 // iterations before this update
+  const float t = static_cast<float>(it) + 1.f;
+  float lr_t = lr;
+  if (decay > 0.f) lr_t = lr_t * (1.f / (1.f + decay * static_cast<float>(it)));
+  lr_t = lr_t * (sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t)));
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gmult;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void step_inc_kernel(long long* step) { *step += 1; }
+
+template <typename T>
+__global__ void cast_weight_kernel(int K, int N, const float* __restrict__ w, T* __restrict__ w_kn, T* __restrict__ w_nk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int k = i / N, n = i - k * N;
+  const float v = w[i];
+  if (w_kn) Act<T>::st(&w_kn[i], v);
+  if (w_nk) Act<T>::st(&w_nk[static_cast<size_t>(n) * K + k], v);
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(long long n, const S* __restrict__ s, D* __restrict__ d) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    Act<D>::st(&d[i], Act<S>::ld(&s[i]));
+}
+
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int dlb_version(void) { return DLB_ABI_VERSION; }
+extern "C" const char* dlb_last_error(void) { return g_err; }
+extern "C" int64_t dlb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int dlb_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int dlb_adam_step(int64_t n, float* param, const float* grad, float* m, float* v, int64_t* step_dev,
+                             float lr, float beta1, float beta2, float eps, float decay, float grad_mult,
+                             void* stream) {
+  DLB_REQUIRE(n > 0 && param && grad && m && v && step_dev, "adam_step: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  adam_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(
+      n, param, grad, m, v, reinterpret_cast<const long long*>(step_dev), lr, beta1, beta2, eps, decay, grad_mult);
+  step_inc_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_dev));
+  g_launches += 2;
+  return check_launch("adam_kernel");
+}
+
+extern "C" int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_kn, void* w_nk, void* stream) {
+  DLB_REQUIRE(w && (w_kn || w_nk) && K > 0 && N > 0, "cast_weight: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (K * N + 255) / 256;
+  if (dtype == DLB_F16) cast_weight_kernel<__half><<<grid, 256, 0, st>>>(K, N, w, (__half*)w_kn, (__half*)w_nk);
+  else if (dtype == DLB_BF16) cast_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(K, N, w, (__nv_bfloat16*)w_kn, (__nv_bfloat16*)w_nk);
+  else cast_weight_kernel<float><<<grid, 256, 0, st>>>(K, N, w, (float*)w_kn, (float*)w_nk);
+  g_launches++;
+  return check_launch("cast_weight_kernel");
+}
+
+extern "C" int dlb_cast(int64_t n, int src_dtype, const void* src, int dst_dtype, void* dst, void* stream) {
+  DLB_REQUIRE(n > 0 && src && dst, "cast: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+#define GO(S, D) cast_kernel<S, D><<<grid, 256, 0, st>>>(n, (const S*)src, (D*)dst)
+  if (src_dtype == DLB_F32 && dst_dtype == DLB_F16) GO(float, __half);
+  else if (src_dtype == DLB_F32 && dst_dtype == DLB_BF16) GO(float, __nv_bfloat16);
+  else if (src_dtype == DLB_F16 && dst_dtype == DLB_F32) GO(__half, float);
+  else if (src_dtype == DLB_BF16 && dst_dtype == DLB_F32) GO(__nv_bfloat16, float);
+  else if (src_dtype == DLB_F32 && dst_dtype == DLB_F32) GO(float, float);
+  else { set_last_error("cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype); return DLB_ERR_UNSUPPORTED; }
+#undef GO
+  g_launches++;
+  return check_launch("cast_kernel");
+}
+
+extern "C" int dlb_fill_zero(void* p, int64_t bytes, void* stream) {
+  DLB_REQUIRE(p && bytes >= 0, "fill_zero: bad arguments");
+  DLB_CUDA(cudaMemsetAsync(p, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return DLB_OK;
+}

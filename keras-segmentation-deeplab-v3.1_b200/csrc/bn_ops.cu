@@ -1,0 +1,372 @@
+// BatchNormalization (training-mode batch statistics + inference fold), activation/residual/dropout apply,
+// BN backward (two passes), ASPP global average pooling, and a tiny fp32 GEMM for the [B, C] pooled branch.
+// Reference sites: BatchNormalization deeplabv3p.py:76,80,178,189,197,322,379,386,408 ; relu6 Lambda :181,192,325 ;
+// Add :202 ; Dropout :410 ; AveragePooling2D :375.
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dlb {
+
+extern std::atomic<long long> g_launches;
+
+__global__ void bn_finalize_kernel(int C, double count, double* sum, double* sqs, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* moving_mean,
+                                   float* moving_var, float* scale, float* shift, float* mean_out, float* rstd_out,
+                                   int reset) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sum[c] / count;
+  double var = sqs[c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  if (mean_out) mean_out[c] = static_cast<float>(mean);
+  if (rstd_out) rstd_out[c] = rstd;
+  if (moving_mean) {
+    // Keras 2.2.4 / TF backend: moving average is fed the Bessel-corrected variance
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    moving_mean[c] = moving_mean[c] * momentum + (1.f - momentum) * static_cast<float>(mean);
+    moving_var[c] = moving_var[c] * momentum + (1.f - momentum) * static_cast<float>(unbiased);
+  }
+  if (reset) { sum[c] = 0.0; sqs[c] = 0.0; }
+}
+
+__global__ void bn_fold_kernel(int C, const float* gamma, const float* beta, const float* mm, const float* mv,
+                               float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(mv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - mm[c] * sc;
+}
+
+// counter-based uniform in [0,1): splitmix64 finaliser on (seed, index)
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+
+struct ApplyArgs {
+  long long nvec; int C; const void* x; void* y; const void* res;
+  const float* scale; const float* shift; int act; float drop_rate; uint64_t seed;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const T* res = reinterpret_cast<const T*>(a.res);
+  T* y = reinterpret_cast<T*>(a.y);
+  const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e0 = i * 8;
+    const int c0 = static_cast<int>(e0 % a.C);
+    float v[8];
+    Vec8<T>::ld(x + e0, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = a.scale ? fmaf(v[k], a.scale[c0 + k], a.shift[c0 + k]) : v[k];
+      z = apply_act(z, a.act);
+      if (a.drop_rate > 0.f) z = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? z * keep_inv : 0.f;
+      v[k] = z;
+    }
+    if (res) {
+      float r[8];
+      Vec8<T>::ld(res + e0, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    Vec8<T>::st(y + e0, v);
+  }
+}
+
+struct BwdArgs {
+  long long M; int C; const void* x; const void* da; void* dx;
+  const float* scale; const float* shift; const float* mean; const float* rstd; int act;
+  double* red; float* dgamma; float* dbeta; float drop_rate; uint64_t seed; int frozen;
+  int cv, rpb;   // channel vectors, rows per block
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
+  extern __shared__ float s_red[];   // [2*C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  if (tid < a.rpb * a.cv) {
+    const int r_in = tid / a.cv;
+    const int c0 = (tid - r_in * a.cv) * 8;
+    float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = a.scale[c0 + k]; sh[k] = a.shift[c0 + k]; mu[k] = a.mean[c0 + k]; rs[k] = a.rstd[c0 + k]; }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const T* x = reinterpret_cast<const T*>(a.x);
+    const T* da = reinterpret_cast<const T*>(a.da);
+    const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+    for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
+         r += static_cast<long long>(gridDim.x) * a.rpb) {
+      const long long e0 = r * a.C + c0;
+      float xv[8], gv[8];
+      Vec8<T>::ld(x + e0, xv);
+      Vec8<T>::ld(da + e0, gv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(xv[k], sc[k], sh[k]);
+        float dz = gv[k] * act_mask(z, a.act);
+        if (a.drop_rate > 0.f) dz = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+        s1[k] += dz;
+        s2[k] += dz * (xv[k] - mu[k]) * rs[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_red[c0 + k], s1[k]); atomicAdd(&s_red[a.C + c0 + k], s2[k]); }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.red[i], static_cast<double>(s_red[i]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0) {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      if (a.dbeta) a.dbeta[c] = static_cast<float>(a.red[c]);
+      // d gamma = sum dz * xhat
+      if (a.dgamma) a.dgamma[c] = static_cast<float>(a.red[a.C + c]);
+    }
+  }
+  if (tid >= a.rpb * a.cv) return;
+  const int r_in = tid / a.cv;
+  const int c0 = (tid - r_in * a.cv) * 8;
+  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+  const float invM = 1.f / static_cast<float>(a.M);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = a.scale[c0 + k]; sh[k] = a.shift[c0 + k]; mu[k] = a.mean[c0 + k]; rs[k] = a.rstd[c0 + k];
+    k1[k] = a.frozen ? 0.f : static_cast<float>(a.red[c0 + k]) * invM;
+    k2[k] = a.frozen ? 0.f : static_cast<float>(a.red[a.C + c0 + k]) * invM;
+  }
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const T* da = reinterpret_cast<const T*>(a.da);
+  T* dx = reinterpret_cast<T*>(a.dx);
+  const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+  for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
+       r += static_cast<long long>(gridDim.x) * a.rpb) {
+    const long long e0 = r * a.C + c0;
+    float xv[8], gv[8], o[8];
+    Vec8<T>::ld(x + e0, xv);
+    Vec8<T>::ld(da + e0, gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float z = fmaf(xv[k], sc[k], sh[k]);
+      float dz = gv[k] * act_mask(z, a.act);
+      if (a.drop_rate > 0.f) dz = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+      const float xhat = (xv[k] - mu[k]) * rs[k];
+      o[k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
+    }
+    Vec8<T>::st(dx + e0, o);
+  }
+}
+
+// global average pool over HW of act(x*scale+shift): out[b, c] (+)= partial means (out pre-zeroed)
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(int HW, int C, int cv, int rpb, int splits, const T* x,
+                                                          const float* in_scale, const float* in_shift, int in_act,
+                                                          float* out) {
+  extern __shared__ float s_acc[];   // [C]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / splits, sp = blockIdx.x - b * splits;
+  for (int i = tid; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  if (tid < rpb * cv) {
+    const int r_in = tid / cv;
+    const int c0 = (tid - r_in * cv) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = sp * rpb + r_in; r < HW; r += splits * rpb) {
+      float v[8];
+      Vec8<T>::ld(x + (static_cast<size_t>(b) * HW + r) * C + c0, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = in_scale ? fmaf(v[k], in_scale[c0 + k], in_shift[c0 + k]) : v[k];
+        acc[k] += apply_act(z, in_act);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[c0 + k], acc[k]);
+  }
+  __syncthreads();
+  const float inv = 1.f / static_cast<float>(HW);
+  for (int i = tid; i < C; i += blockDim.x) atomicAdd(&out[static_cast<size_t>(b) * C + i], s_acc[i] * inv);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(long long nvec, int HW, int C, const float* dout, T* dx,
+                                                          int accumulate) {
+  const float inv = 1.f / static_cast<float>(HW);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e0 = i * 8;
+    const int c0 = static_cast<int>(e0 % C);
+    const long long b = e0 / (static_cast<long long>(HW) * C);
+    float v[8];
+    if (accumulate) Vec8<T>::ld(dx + e0, v);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += dout[b * C + c0 + k] * inv;
+    Vec8<T>::st(dx + e0, v);
+  }
+}
+
+// tiny fp32 GEMM, one thread per output element (M, N <= a few hundred)
+__global__ void small_gemm_kernel(int M, int N, int K, const float* A, int lda, int tA, const float* B, int ldb,
+                                  int tB, float* C, int ldc, float alpha, float beta) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float a = tA ? A[static_cast<size_t>(k) * lda + m] : A[static_cast<size_t>(m) * lda + k];
+    const float b = tB ? B[static_cast<size_t>(n) * ldb + k] : B[static_cast<size_t>(k) * ldb + n];
+    acc = fmaf(a, b, acc);
+  }
+  float* c = C + static_cast<size_t>(m) * ldc + n;
+  *c = alpha * acc + (beta != 0.f ? beta * *c : 0.f);
+}
+
+static int grid_for(long long n, int threads, int per_sm) {
+  long long blocks = (n + threads - 1) / threads;
+  long long cap = static_cast<long long>(num_sms()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int dlb_bn_finalize(int C, double count, double* sum, double* sqs, const float* gamma, const float* beta,
+                               float eps, float momentum, float* moving_mean, float* moving_var, float* scale,
+                               float* shift, float* mean, float* rstd, int reset, void* stream) {
+  DLB_REQUIRE(C > 0 && sum && sqs && gamma && beta && scale && shift, "bn_finalize: null pointer");
+  DLB_REQUIRE(count > 0, "bn_finalize: count must be positive");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      C, count, sum, sqs, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, mean, rstd, reset);
+  g_launches++;
+  return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int dlb_bn_fold(int C, const float* gamma, const float* beta, const float* moving_mean,
+                           const float* moving_var, float eps, float* scale, float* shift, void* stream) {
+  DLB_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && shift, "bn_fold: null pointer");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(C, gamma, beta, moving_mean,
+                                                                                 moving_var, eps, scale, shift);
+  g_launches++;
+  return check_launch("bn_fold_kernel");
+}
+
+extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
+  DLB_REQUIRE(p && p->x && p->y, "bn_act_apply: null pointer");
+  DLB_REQUIRE(p->C % 8 == 0, "bn_act_apply: C must be a multiple of 8 (C=%d)", p->C);
+  ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed};
+  const int grid = grid_for(a.nvec, 256, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F16) bn_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else if (p->dtype == DLB_BF16) bn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  else bn_apply_kernel<float><<<grid, 256, 0, st>>>(a);
+  g_launches++;
+  return check_launch("bn_apply_kernel");
+}
+
+static int fill_bwd(const dlb_bn_bwd_params* p, BwdArgs* a) {
+  DLB_REQUIRE(p && p->x && p->da && p->scale && p->shift && p->mean && p->rstd && p->red, "bn_bwd: null pointer");
+  DLB_REQUIRE(p->C % 8 == 0 && p->C / 8 <= 256, "bn_bwd: C must be a multiple of 8 and <= 2048 (C=%d)", p->C);
+  a->M = p->M; a->C = p->C; a->x = p->x; a->da = p->da; a->dx = p->dx;
+  a->scale = p->scale; a->shift = p->shift; a->mean = p->mean; a->rstd = p->rstd; a->act = p->act;
+  a->red = p->red; a->dgamma = p->dgamma; a->dbeta = p->dbeta; a->drop_rate = p->drop_rate; a->seed = p->drop_seed;
+  a->frozen = p->frozen_stats; a->cv = p->C / 8; a->rpb = 256 / a->cv;
+  return DLB_OK;
+}
+
+extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
+  BwdArgs a{};
+  int rc = fill_bwd(p, &a);
+  if (rc) return rc;
+  long long blocks = (a.M + a.rpb - 1) / a.rpb;
+  long long cap = static_cast<long long>(num_sms()) * 4;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  const size_t smem = 2 * p->C * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
+  else if (p->dtype == DLB_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
+  else bn_bwd_reduce_kernel<float><<<grid, 256, smem, st>>>(a);
+  g_launches++;
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
+  BwdArgs a{};
+  int rc = fill_bwd(p, &a);
+  if (rc) return rc;
+  DLB_REQUIRE(p->dx, "bn_bwd_apply: dx is null");
+  long long blocks = (a.M + a.rpb - 1) / a.rpb;
+  long long cap = static_cast<long long>(num_sms()) * 8;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else if (p->dtype == DLB_BF16) bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  else bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(a);
+  g_launches++;
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int dlb_global_avgpool_fwd(int B, int HW, int C, int dtype, const void* x, const float* in_scale,
+                                      const float* in_shift, int in_act, float* out, void* stream) {
+  DLB_REQUIRE(x && out && B > 0 && HW > 0, "global_avgpool_fwd: bad arguments");
+  DLB_REQUIRE(C % 8 == 0 && C / 8 <= 256, "global_avgpool_fwd: C must be a multiple of 8 and <= 2048");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DLB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * B * C, st));
+  const int cv = C / 8, rpb = 256 / cv;
+  int splits = (2 * num_sms() + B - 1) / B;
+  const int max_splits = (HW + rpb - 1) / rpb;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const size_t smem = C * sizeof(float);
+  if (dtype == DLB_F16) avgpool_fwd_kernel<__half><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const __half*)x, in_scale, in_shift, in_act, out);
+  else if (dtype == DLB_BF16) avgpool_fwd_kernel<__nv_bfloat16><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const __nv_bfloat16*)x, in_scale, in_shift, in_act, out);
+  else avgpool_fwd_kernel<float><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const float*)x, in_scale, in_shift, in_act, out);
+  g_launches++;
+  return check_launch("avgpool_fwd_kernel");
+}
+
+extern "C" int dlb_global_avgpool_bwd(int B, int HW, int C, int dtype, const float* dout, void* dx, int accumulate,
+                                      void* stream) {
+  DLB_REQUIRE(dout && dx && C % 8 == 0, "global_avgpool_bwd: bad arguments");
+  const long long nvec = static_cast<long long>(B) * HW * C / 8;
+  const int grid = grid_for(nvec, 256, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLB_F16) avgpool_bwd_kernel<__half><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (__half*)dx, accumulate);
+  else if (dtype == DLB_BF16) avgpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (__nv_bfloat16*)dx, accumulate);
+  else avgpool_bwd_kernel<float><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (float*)dx, accumulate);
+  g_launches++;
+  return check_launch("avgpool_bwd_kernel");
+}
+
+extern "C" int dlb_small_gemm(int M, int N, int K, const float* A, int lda, int transA, const float* B, int ldb,
+                              int transB, float* C, int ldc, float alpha, float beta, void* stream) {
+  DLB_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "small_gemm: bad arguments");
+  dim3 grid((N + 127) / 128, M);
+  small_gemm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(M, N, K, A, lda, transA, B, ldb, transB, C,
+                                                                        ldc, alpha, beta);
+  g_launches++;
+  return check_launch("small_gemm_kernel");
+}

@@ -1,0 +1,460 @@
+// Direct (im2col-free) convolutions of the DeepLabV3+ graph that are not GEMMs:
+//   * stem 3x3 stride-2 conv on the 3-channel image with the x/127.5-1 preprocessing fused
+//     (deeplabv3p.py:270, :317-321 / :283-284)
+//   * depthwise / atrous depthwise 3x3, stride 1|2, any dilation, TF-SAME or explicit padding
+//     (deeplabv3p.py:73-74, :186-188, :61-69), forward, backward-data and backward-weight.
+// NHWC, 8-channel (16 B) vector accesses, fp32 math, consumer-side BatchNorm+activation prologue so the
+// normalised tensor of the previous layer never round-trips through HBM, BatchNorm batch statistics of the
+// output accumulated in the same pass (fp32 per thread -> smem -> one fp64 atomic per CTA and channel).
+//
+// These kernels are HBM/L2-bandwidth bound: per output element 2 B read + 2 B write algorithmic traffic at
+// 16 bit for 18 flop.  Grids are sized as a multiple of the SM count and loop (persistent style).
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dlb {
+
+extern std::atomic<long long> g_launches;
+
+// ---------------------------------------------------------------------------------------------
+// depthwise forward
+// ---------------------------------------------------------------------------------------------
+struct DwArgs {
+  int B, H, W, C, Ho, Wo, stride, dil, pad_t, pad_l;
+  const void* x; void* y; const float* w;
+  const float* in_scale; const float* in_shift; int in_act;
+  const float* out_scale; const float* out_shift; int out_act;
+  double* stat_sum; double* stat_sqs;
+  int cv;        // C / 8
+  int ppb;       // pixels per block
+  long long npix;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) dw_fwd_kernel(const DwArgs a) {
+  extern __shared__ float s_stats[];   // [2*C] when stats are requested
+  const int tid = threadIdx.x;
+  const bool active = tid < a.ppb * a.cv;
+  const int p_in_blk = tid / a.cv;
+  const int cvi = tid - p_in_blk * a.cv;
+  const int c0 = cvi * 8;
+  const bool stats = a.stat_sum != nullptr;
+  if (stats) {
+    for (int i = tid; i < 2 * a.C; i += blockDim.x) s_stats[i] = 0.f;
+    __syncthreads();
+  }
+  float wreg[9][8];
+  float isc[8], ish[8], osc[8], osh[8];
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wreg[t][i] = a.w[t * a.C + c0 + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      isc[i] = a.in_scale ? a.in_scale[c0 + i] : 1.f;
+      ish[i] = a.in_scale ? a.in_shift[c0 + i] : 0.f;
+      osc[i] = a.out_scale ? a.out_scale[c0 + i] : 1.f;
+      osh[i] = a.out_scale ? a.out_shift[c0 + i] : 0.f;
+    }
+  }
+  float ssum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ssqs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const T* x = reinterpret_cast<const T*>(a.x);
+  T* y = reinterpret_cast<T*>(a.y);
+  if (active) {
+    for (long long pix = static_cast<long long>(blockIdx.x) * a.ppb + p_in_blk; pix < a.npix;
+         pix += static_cast<long long>(gridDim.x) * a.ppb) {
+      const int wo = static_cast<int>(pix % a.Wo);
+      const long long t1 = pix / a.Wo;
+      const int ho = static_cast<int>(t1 % a.Ho);
+      const int b = static_cast<int>(t1 / a.Ho);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int h = ho * a.stride - a.pad_t + ky * a.dil;
+        if (h < 0 || h >= a.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int w = wo * a.stride - a.pad_l + kx * a.dil;
+          if (w < 0 || w >= a.W) continue;
+          float v[8];
+          Vec8<T>::ld(x + ((static_cast<size_t>(b) * a.H + h) * a.W + w) * a.C + c0, v);
+          if (a.in_scale) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = apply_act(fmaf(v[i], isc[i], ish[i]), a.in_act);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], wreg[ky * 3 + kx][i], acc[i]);
+        }
+      }
+      if (a.out_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], osc[i], osh[i]), a.out_act);
+      }
+      if (stats) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float q = Act<T>::rnd(acc[i]); ssum[i] += q; ssqs[i] += q * q; }
+      }
+      Vec8<T>::st(y + static_cast<size_t>(pix) * a.C + c0, acc);
+    }
+  }
+  if (stats) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[c0 + i], ssum[i]); atomicAdd(&s_stats[a.C + c0 + i], ssqs[i]); }
+    }
+    __syncthreads();
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      atomicAdd(&a.stat_sum[c], static_cast<double>(s_stats[c]));
+      atomicAdd(&a.stat_sqs[c], static_cast<double>(s_stats[a.C + c]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise backward-data: da[b,h,w,c] = sum_taps w[ky,kx,c] * dy[b,ho,wo,c]
+// ---------------------------------------------------------------------------------------------
+struct DwBwdArgs {
+  int B, H, W, C, Ho, Wo, stride, dil, pad_t, pad_l;
+  const void* x; const void* dy; void* dx; const float* w; float* dw;
+  const float* in_scale; const float* in_shift; int in_act;
+  int cv, ppb; long long npix;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) dw_bwd_data_kernel(const DwBwdArgs a) {
+  const int tid = threadIdx.x;
+  if (tid >= a.ppb * a.cv) return;
+  const int p_in_blk = tid / a.cv;
+  const int c0 = (tid - p_in_blk * a.cv) * 8;
+  float wreg[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wreg[t][i] = a.w[t * a.C + c0 + i];
+  const T* dy = reinterpret_cast<const T*>(a.dy);
+  T* dx = reinterpret_cast<T*>(a.dx);
+  for (long long pix = static_cast<long long>(blockIdx.x) * a.ppb + p_in_blk; pix < a.npix;
+       pix += static_cast<long long>(gridDim.x) * a.ppb) {
+    const int w = static_cast<int>(pix % a.W);
+    const long long t1 = pix / a.W;
+    const int h = static_cast<int>(t1 % a.H);
+    const int b = static_cast<int>(t1 / a.H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hn = h + a.pad_t - ky * a.dil;
+      if (hn < 0 || (hn % a.stride) != 0) continue;
+      const int ho = hn / a.stride;
+      if (ho >= a.Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int wn = w + a.pad_l - kx * a.dil;
+        if (wn < 0 || (wn % a.stride) != 0) continue;
+        const int wo = wn / a.stride;
+        if (wo >= a.Wo) continue;
+        float v[8];
+        Vec8<T>::ld(dy + ((static_cast<size_t>(b) * a.Ho + ho) * a.Wo + wo) * a.C + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], wreg[ky * 3 + kx][i], acc[i]);
+      }
+    }
+    Vec8<T>::st(dx + static_cast<size_t>(pix) * a.C + c0, acc);
+  }
+}
+
+// depthwise backward-weight: dw[ky,kx,c] += sum a[b, ho*s - pad + ky*d, wo*s - pad + kx*d, c] * dy[b,ho,wo,c]
+template <typename T>
+__global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const DwBwdArgs a) {
+  extern __shared__ float s_dw[];   // [9*C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * a.C; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const bool active = tid < a.ppb * a.cv;
+  if (active) {
+    const int p_in_blk = tid / a.cv;
+    const int c0 = (tid - p_in_blk * a.cv) * 8;
+    float isc[8], ish[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      isc[i] = a.in_scale ? a.in_scale[c0 + i] : 1.f;
+      ish[i] = a.in_scale ? a.in_shift[c0 + i] : 0.f;
+    }
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    const T* x = reinterpret_cast<const T*>(a.x);
+    const T* dy = reinterpret_cast<const T*>(a.dy);
+    for (long long pix = static_cast<long long>(blockIdx.x) * a.ppb + p_in_blk; pix < a.npix;
+         pix += static_cast<long long>(gridDim.x) * a.ppb) {
+      const int wo = static_cast<int>(pix % a.Wo);
+      const long long t1 = pix / a.Wo;
+      const int ho = static_cast<int>(t1 % a.Ho);
+      const int b = static_cast<int>(t1 / a.Ho);
+      float g[8];
+      Vec8<T>::ld(dy + static_cast<size_t>(pix) * a.C + c0, g);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int h = ho * a.stride - a.pad_t + ky * a.dil;
+        if (h < 0 || h >= a.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int w = wo * a.stride - a.pad_l + kx * a.dil;
+          if (w < 0 || w >= a.W) continue;
+          float v[8];
+          Vec8<T>::ld(x + ((static_cast<size_t>(b) * a.H + h) * a.W + w) * a.C + c0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float av = a.in_scale ? apply_act(fmaf(v[i], isc[i], ish[i]), a.in_act) : v[i];
+            acc[ky * 3 + kx][i] = fmaf(av, g[i], acc[ky * 3 + kx][i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * a.C + c0 + i], acc[t][i]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * a.C; i += blockDim.x) atomicAdd(&a.dw[i], s_dw[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem conv: 3x3 stride 2, Cin = 3, TF-SAME ((0,1) padding for even sizes), preprocessing fused
+// ---------------------------------------------------------------------------------------------
+struct StemArgs {
+  int B, H, W, Cout, Ho, Wo, pad_t, pad_l;
+  const float* x; void* y; const float* w;
+  const float* out_scale; const float* out_shift; int out_act;
+  double* stat_sum; double* stat_sqs;
+  long long npix;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) stem_fwd_kernel(const StemArgs a) {
+  __shared__ float s_w[27 * 32];
+  __shared__ float s_stat[64];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 32; i += blockDim.x) s_w[i] = a.w[i];
+  if (tid < 64) s_stat[tid] = 0.f;
+  __syncthreads();
+  const bool stats = a.stat_sum != nullptr;
+  float ssum[32], ssqs[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
+  T* y = reinterpret_cast<T*>(a.y);
+  for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + tid; pix < a.npix;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(pix % a.Wo);
+    const long long t1 = pix / a.Wo;
+    const int ho = static_cast<int>(t1 % a.Ho);
+    const int b = static_cast<int>(t1 / a.Ho);
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int h = ho * 2 - a.pad_t + ky;
+      if (h < 0 || h >= a.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int w = wo * 2 - a.pad_l + kx;
+        if (w < 0 || w >= a.W) continue;
+        const float* px = a.x + ((static_cast<size_t>(b) * a.H + h) * a.W + w) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float v = px[ci] / 127.5f - 1.f;
+          const float* wr = &s_w[((ky * 3 + kx) * 3 + ci) * 32];
+#pragma unroll
+          for (int co = 0; co < 32; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+        }
+      }
+    }
+    if (a.out_scale) {
+#pragma unroll
+      for (int co = 0; co < 32; ++co) acc[co] = apply_act(fmaf(acc[co], a.out_scale[co], a.out_shift[co]), a.out_act);
+    }
+    if (stats) {
+#pragma unroll
+      for (int co = 0; co < 32; ++co) { const float q = Act<T>::rnd(acc[co]); ssum[co] += q; ssqs[co] += q * q; }
+    }
+#pragma unroll
+    for (int v8 = 0; v8 < 4; ++v8) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = acc[v8 * 8 + i];
+      Vec8<T>::st(y + static_cast<size_t>(pix) * 32 + v8 * 8, o);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int co = 0; co < 32; ++co) {
+      float s = ssum[co], q = ssqs[co];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+      if ((tid & 31) == 0) { atomicAdd(&s_stat[co], s); atomicAdd(&s_stat[32 + co], q); }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      atomicAdd(&a.stat_sum[tid], static_cast<double>(s_stat[tid]));
+      atomicAdd(&a.stat_sqs[tid], static_cast<double>(s_stat[32 + tid]));
+    }
+  }
+}
+
+// stem weight gradient: one thread per (tap*ci, co) pair, CTA loops over a slab of output pixels staged in smem
+template <typename T>
+__global__ void __launch_bounds__(864) stem_wgrad_kernel(int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+                                                         const float* __restrict__ x, const T* __restrict__ dy,
+                                                         float* __restrict__ dw, long long npix) {
+  constexpr int PIX = 64;
+  __shared__ float s_x[PIX][28];
+  __shared__ float s_dy[PIX][32];
+  const int tid = threadIdx.x;
+  const int tap = tid >> 5, co = tid & 31;   // tap in 0..26 = (ky*3+kx)*3+ci
+  float acc = 0.f;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * PIX; p0 < npix; p0 += static_cast<long long>(gridDim.x) * PIX) {
+    __syncthreads();
+    for (int i = tid; i < PIX * 27; i += blockDim.x) {
+      const int p = i / 27, t = i - p * 27;
+      const long long pix = p0 + p;
+      float v = 0.f;
+      if (pix < npix) {
+        const int wo = static_cast<int>(pix % Wo);
+        const long long t1 = pix / Wo;
+        const int ho = static_cast<int>(t1 % Ho);
+        const int b = static_cast<int>(t1 / Ho);
+        const int kk = t / 3, ci = t - kk * 3, ky = kk / 3, kx = kk - ky * 3;
+        const int h = ho * 2 - pad_t + ky, w = wo * 2 - pad_l + kx;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = x[((static_cast<size_t>(b) * H + h) * W + w) * 3 + ci] / 127.5f - 1.f;
+      }
+      s_x[p][t] = v;
+    }
+    for (int i = tid; i < PIX * 32; i += blockDim.x) {
+      const int p = i >> 5, c = i & 31;
+      const long long pix = p0 + p;
+      s_dy[p][c] = pix < npix ? Act<T>::ld(dy + static_cast<size_t>(pix) * 32 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int p = 0; p < PIX; ++p) acc = fmaf(s_x[p][tap], s_dy[p][co], acc);
+  }
+  atomicAdd(&dw[tap * 32 + co], acc);
+}
+
+static int pick_grid(long long work_blocks, int per_sm) {
+  long long cap = static_cast<long long>(num_sms()) * per_sm;
+  return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
+}
+
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream) {
+  DLB_REQUIRE(p && p->x && p->y && p->w, "dw_conv_fwd: null pointer");
+  DLB_REQUIRE(p->C % 8 == 0 && p->C / 8 <= 256, "dw_conv_fwd: C must be a multiple of 8 and <= 2048 (C=%d)", p->C);
+  DLB_REQUIRE(p->stride == 1 || p->stride == 2, "dw_conv_fwd: stride %d", p->stride);
+  DwArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+  a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
+  a.x = p->x; a.y = p->y; a.w = p->w;
+  a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
+  a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
+  a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
+  a.cv = p->C / 8; a.ppb = 256 / a.cv; a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
+  const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
+  const size_t smem = p->stat_sum ? 2 * p->C * sizeof(float) : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F16) dw_fwd_kernel<__half><<<grid, 256, smem, st>>>(a);
+  else if (p->dtype == DLB_BF16) dw_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
+  else dw_fwd_kernel<float><<<grid, 256, smem, st>>>(a);
+  g_launches++;
+  return check_launch("dw_fwd_kernel");
+}
+
+extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
+  DLB_REQUIRE(p && p->dy && p->w, "dw_conv_bwd: null pointer");
+  DLB_REQUIRE(p->C % 8 == 0 && p->C / 8 <= 256, "dw_conv_bwd: C must be a multiple of 8 and <= 2048 (C=%d)", p->C);
+  DwBwdArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+  a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
+  a.x = p->x; a.dy = p->dy; a.dx = p->dx; a.w = p->w; a.dw = p->dw;
+  a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
+  a.cv = p->C / 8; a.ppb = 256 / a.cv;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dx) {
+    a.npix = static_cast<long long>(p->B) * p->H * p->W;
+    const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
+    if (p->dtype == DLB_F16) dw_bwd_data_kernel<__half><<<grid, 256, 0, st>>>(a);
+    else if (p->dtype == DLB_BF16) dw_bwd_data_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+    else dw_bwd_data_kernel<float><<<grid, 256, 0, st>>>(a);
+    g_launches++;
+    int rc = check_launch("dw_bwd_data_kernel");
+    if (rc) return rc;
+  }
+  if (p->dw) {
+    DLB_REQUIRE(p->x, "dw_conv_bwd: x required for the weight gradient");
+    a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
+    const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 2);
+    const size_t smem = 9 * p->C * sizeof(float);
+#define L(TT)                                                                                                  \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_weight_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dw_bwd_weight_kernel<TT><<<grid, 256, smem, st>>>(a);                                                      \
+  } while (0)
+    if (p->dtype == DLB_F16) L(__half);
+    else if (p->dtype == DLB_BF16) L(__nv_bfloat16);
+    else L(float);
+#undef L
+    g_launches++;
+    return check_launch("dw_bwd_weight_kernel");
+  }
+  return DLB_OK;
+}
+
+extern "C" int dlb_stem_conv_fwd(const dlb_stem_conv_params* p, void* stream) {
+  DLB_REQUIRE(p && p->x && p->y && p->w, "stem_conv_fwd: null pointer");
+  DLB_REQUIRE(p->Cout == 32, "stem_conv_fwd: Cout must be 32 (got %d)", p->Cout);
+  StemArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.Ho = p->Ho; a.Wo = p->Wo;
+  // TF SAME for k=3, s=2: pad_total = max((Ho-1)*2 + 3 - H, 0); before = total // 2
+  const int pt = (p->Ho - 1) * 2 + 3 - p->H, pl = (p->Wo - 1) * 2 + 3 - p->W;
+  a.pad_t = (pt > 0 ? pt : 0) / 2; a.pad_l = (pl > 0 ? pl : 0) / 2;
+  a.x = p->x; a.y = p->y; a.w = p->w;
+  a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
+  a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
+  a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
+  const int grid = pick_grid((a.npix + 127) / 128, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F16) stem_fwd_kernel<__half><<<grid, 128, 0, st>>>(a);
+  else if (p->dtype == DLB_BF16) stem_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
+  else stem_fwd_kernel<float><<<grid, 128, 0, st>>>(a);
+  g_launches++;
+  return check_launch("stem_fwd_kernel");
+}
+
+extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, const float* x, const void* dy,
+                                   float* dw, void* stream) {
+  DLB_REQUIRE(x && dy && dw, "stem_conv_wgrad: null pointer");
+  DLB_REQUIRE(Cout == 32, "stem_conv_wgrad: Cout must be 32");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int pt = (Ho - 1) * 2 + 3 - H, pl = (Wo - 1) * 2 + 3 - W;
+  const int pad_t = (pt > 0 ? pt : 0) / 2, pad_l = (pl > 0 ? pl : 0) / 2;
+  const long long npix = static_cast<long long>(B) * Ho * Wo;
+  const int grid = pick_grid((npix + 63) / 64, 2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLB_F16)
+    stem_wgrad_kernel<__half><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
+  else if (dtype == DLB_BF16)
+    stem_wgrad_kernel<__nv_bfloat16><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __nv_bfloat16*)dy, dw, npix);
+  else
+    stem_wgrad_kernel<float><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
+  g_launches++;
+  return check_launch("stem_wgrad_kernel");
+}

@@ -1,0 +1,413 @@
+// Segmentation head: legacy TF1 bilinear resize + softmax (+ void-ignoring sparse cross-entropy and its
+// gradient), Subpixel phase shift, confusion counts.
+//   resize   : K.tf.image.resize_bilinear(x, size)   deeplabv3p.py:382,:418,:439 ; utils.py:190
+//              (align_corners=False, no half-pixel centres: src = dst * in/out, hi = min(lo+1, in-1))
+//   softmax  : Activation('softmax')                 deeplabv3p.py:440-444 ; utils.py:192,197
+//   loss     : sparse_crossentropy_ignoring_last_label utils.py:127-130 (+ Keras categorical_crossentropy clip
+//              1e-7 and the temporal sample-weight normalisation of weighted_masked_objective)
+//   shuffle  : Subpixel._phase_shift                 subpixel.py:77-88
+//   metrics  : utils.py:132-157 work from an argmax map + confusion counts
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dlb {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int kMaxC = 32;   // classes held in registers
+
+__device__ __forceinline__ void bilinear_coeffs(int dst, int in_size, float scale, int& lo, int& hi, float& f) {
+  const float src = static_cast<float>(dst) * scale;
+  lo = static_cast<int>(floorf(src));
+  hi = min(lo + 1, in_size - 1);
+  f = src - static_cast<float>(lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inference: probs [B, H*W, C] fp32 and/or argmax
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) resize_softmax_fwd_kernel(int B, int h, int w, int ldl, int H, int W,
+                                                                 const float* __restrict__ logits,
+                                                                 float* __restrict__ probs,
+                                                                 uint8_t* __restrict__ argmax_out) {
+  __shared__ float s_out[128 * C];
+  const long long npix = static_cast<long long>(B) * H * W;
+  const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
+  for (long long p0 = static_cast<long long>(blockIdx.x) * 128; p0 < npix; p0 += static_cast<long long>(gridDim.x) * 128) {
+    const long long pix = p0 + threadIdx.x;
+    if (pix < npix) {
+      const int X = static_cast<int>(pix % W);
+      const long long t = pix / W;
+      const int Y = static_cast<int>(t % H);
+      const int b = static_cast<int>(t / H);
+      int y0, y1, x0, x1; float fy, fx;
+      bilinear_coeffs(Y, h, sy, y0, y1, fy);
+      bilinear_coeffs(X, w, sx, x0, x1, fx);
+      const float* base = logits + static_cast<size_t>(b) * h * w * ldl;
+      const float* tl = base + (static_cast<size_t>(y0) * w + x0) * ldl;
+      const float* tr = base + (static_cast<size_t>(y0) * w + x1) * ldl;
+      const float* bl = base + (static_cast<size_t>(y1) * w + x0) * ldl;
+      const float* br = base + (static_cast<size_t>(y1) * w + x1) * ldl;
+      float v[C];
+      float mx = -INFINITY; int am = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float top = tl[c] + (tr[c] - tl[c]) * fx;
+        const float bot = bl[c] + (br[c] - bl[c]) * fx;
+        v[c] = top + (bot - top) * fy;
+        if (v[c] > mx) { mx = v[c]; am = c; }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_out[threadIdx.x * C + c] = v[c] * inv;
+      if (argmax_out) argmax_out[pix] = static_cast<uint8_t>(am);
+    }
+    if (probs) {
+      __syncthreads();
+      const long long n_here = min(static_cast<long long>(128), npix - p0) * C;
+      float* dst = probs + p0 * C;
+      for (int i = threadIdx.x; i < n_here; i += 128) dst[i] = s_out[i];
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// training: fused resize + softmax + CE loss + gradient w.r.t. the low-resolution logits.
+// One CTA owns a TILE x TILE block of low-res cells = (TILE*S)^2 output pixels; the transposed resize is
+// accumulated in shared memory (the S pixels that share a pair of source columns are first reduced with
+// warp shuffles), then flushed with one global atomic per low-res logit of the (TILE+1)^2 halo tile.
+// ---------------------------------------------------------------------------------------------
+struct CeArgs {
+  int B, h, w, ldl, H, W, S;
+  const float* logits; const float* labels; const float* sample_w; const float* grad_scale;
+  float* dlogits; double* loss_sum; uint8_t* argmax;
+};
+
+template <int C, int S>
+__global__ void __launch_bounds__(256) resize_softmax_ce_kernel(const CeArgs a) {
+  constexpr int TILE = 64 / S >= 8 ? 8 : 64 / S;      // low-res cells per tile side (8 for S=8, 8 for S=4 -> 32px)
+  constexpr int TP = TILE + 1;
+  constexpr int PX = TILE * S;                        // output pixels per tile side
+  __shared__ float s_log[TP * TP * C];
+  __shared__ float s_grad[TP * TP * C];
+  __shared__ float s_loss[8];
+  const int tiles_x = (a.w + TILE - 1) / TILE, tiles_y = (a.h + TILE - 1) / TILE;
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int ty0 = (tile / tiles_x) * TILE, tx0 = (tile % tiles_x) * TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < TP * TP * C; i += 256) {
+    const int c = i % C, cell = i / C;
+    const int cy = min(ty0 + cell / TP, a.h - 1), cx = min(tx0 + cell % TP, a.w - 1);
+    s_log[i] = a.logits[((static_cast<size_t>(b) * a.h + cy) * a.w + cx) * a.ldl + c];
+    s_grad[i] = 0.f;
+  }
+  __syncthreads();
+  const float gs = *a.grad_scale;
+  float loss_acc = 0.f;
+  // each warp walks rows of the tile; a lane owns one output pixel of a 32-pixel row segment
+  constexpr int SEGS = (PX + 31) / 32;
+  for (int rs = warp; rs < PX * SEGS; rs += 8) {
+    const int ry = rs / SEGS, seg = rs - ry * SEGS;
+    const int lx = seg * 32 + lane;                 // pixel x inside the tile
+    const int Y = ty0 * S + ry, X = tx0 * S + lx;
+    const bool ok = lx < PX && Y < a.H && X < a.W;
+    // local (tile) source coordinates; src = dst / S exactly, hi clamps at the image edge
+    const int cy0 = ry / S; const float fy = static_cast<float>(ry % S) / static_cast<float>(S);
+    const int cx0 = lx / S; const float fx = static_cast<float>(lx % S) / static_cast<float>(S);
+    const int cy1 = (ty0 + cy0 + 1 <= a.h - 1) ? cy0 + 1 : cy0;
+    const int cx1 = (tx0 + cx0 + 1 <= a.w - 1) ? cx0 + 1 : cx0;
+    float g[C];
+    const float wy0 = 1.f - fy, wy1 = fy;   // identical for all lanes of the row
+    if (ok) {
+      const float* tl = &s_log[(cy0 * TP + cx0) * C];
+      const float* tr = &s_log[(cy0 * TP + cx1) * C];
+      const float* bl = &s_log[(cy1 * TP + cx0) * C];
+      const float* br = &s_log[(cy1 * TP + cx1) * C];
+      float mx = -INFINITY; int am = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float top = tl[c] + (tr[c] - tl[c]) * fx;
+        const float bot = bl[c] + (br[c] - bl[c]) * fx;
+        g[c] = top + (bot - top) * fy;
+        if (g[c] > mx) { mx = g[c]; am = c; }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { g[c] = expf(g[c] - mx); sum += g[c]; }
+      const float inv = 1.f / sum;
+      const size_t pix = (static_cast<size_t>(b) * a.H + Y) * a.W + X;
+      if (a.argmax) a.argmax[pix] = static_cast<uint8_t>(am);
+      const int label = static_cast<int>(a.labels[pix]);
+      const float sw = a.sample_w ? a.sample_w[pix] : 1.f;
+      float py = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { g[c] *= inv; if (c == label) py = g[c]; }
+      const bool valid = label >= 0 && label < C;
+      // Keras: p = clip(p, 1e-7, 1 - 1e-7); loss = -log p[y]; the clip has zero gradient outside its range
+      const bool in_range = valid && py >= 1e-7f && py <= 1.f - 1e-7f;
+      if (valid) loss_acc += sw * -logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f));
+      const float k = in_range ? sw * gs : 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) g[c] = k * (g[c] - (c == label ? 1.f : 0.f));
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) g[c] = 0.f;
+    }
+    // transposed resize: pixel contributes (1-fx) to column cx0 and fx to cx1; the S lanes of a group share them
+    const bool leader = (lane % S) == 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float ga = g[c] * (1.f - fx), gb = g[c] * fx;
+#pragma unroll
+      for (int o = S / 2; o > 0; o >>= 1) {
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        gb += __shfl_xor_sync(0xffffffffu, gb, o);
+      }
+      if (leader && lx < PX) {
+        const float w0 = wy0, w1 = wy1;
+        if (ga != 0.f) {
+          atomicAdd(&s_grad[(cy0 * TP + cx0) * C + c], ga * w0);
+          if (w1 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx0) * C + c], ga * w1);
+        }
+        if (gb != 0.f) {
+          atomicAdd(&s_grad[(cy0 * TP + cx1) * C + c], gb * w0);
+          if (w1 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx1) * C + c], gb * w1);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+  if (lane == 0) s_loss[warp] = loss_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_loss[i];
+    atomicAdd(a.loss_sum, static_cast<double>(t));
+  }
+  for (int i = tid; i < TP * TP * C; i += 256) {
+    const float v = s_grad[i];
+    if (v == 0.f) continue;
+    const int c = i % C, cell = i / C;
+    const int cy = ty0 + cell / TP, cx = tx0 + cell % TP;
+    if (cy < a.h && cx < a.w) atomicAdd(&a.dlogits[((static_cast<size_t>(b) * a.h + cy) * a.w + cx) * a.ldl + c], v);
+  }
+}
+
+// S == 1 (Subpixel head: logits already at full resolution)
+template <int C>
+__global__ void __launch_bounds__(256) softmax_ce_full_kernel(const CeArgs a) {
+  __shared__ float s_loss[8];
+  const long long npix = static_cast<long long>(a.B) * a.H * a.W;
+  const float gs = *a.grad_scale;
+  float loss_acc = 0.f;
+  for (long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(gridDim.x) * 256) {
+    const float* l = a.logits + pix * a.ldl;
+    float g[C]; float mx = -INFINITY; int am = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { g[c] = l[c]; if (g[c] > mx) { mx = g[c]; am = c; } }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { g[c] = expf(g[c] - mx); sum += g[c]; }
+    const float inv = 1.f / sum;
+    if (a.argmax) a.argmax[pix] = static_cast<uint8_t>(am);
+    const int label = static_cast<int>(a.labels[pix]);
+    const float sw = a.sample_w ? a.sample_w[pix] : 1.f;
+    float py = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { g[c] *= inv; if (c == label) py = g[c]; }
+    const bool valid = label >= 0 && label < C;
+    const bool in_range = valid && py >= 1e-7f && py <= 1.f - 1e-7f;
+    if (valid) loss_acc += sw * -logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f));
+    const float k = in_range ? sw * gs : 0.f;
+    float* d = a.dlogits + pix * a.ldl;
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = k * (g[c] - (c == label ? 1.f : 0.f));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+  if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_loss[i];
+    atomicAdd(a.loss_sum, static_cast<double>(t));
+  }
+}
+
+__global__ void count_nonzero_kernel(long long n, const float* sw, double* count) {
+  __shared__ unsigned int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned int c = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    c += sw[i] != 0.f ? 1u : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(count, static_cast<double>(s_cnt));
+}
+__global__ void grad_scale_kernel(long long n, int has_sw, double* count, float* grad_scale) {
+  if (!has_sw) *count = static_cast<double>(n);
+  const double c = *count;
+  *grad_scale = c > 0.0 ? static_cast<float>(1.0 / c) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Subpixel phase shift, standalone:  out[n, a*r+j, b*r+i, k] = in[n, a, b, k*r*r + i*r + j]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void phase_shift_kernel(long long total, int h, int w, int Cs, int r, const T* in, T* out, int inverse) {
+  for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < total;
+       o += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // o indexes the high-res tensor [n, h*r, w*r, Cs]
+    const int k = static_cast<int>(o % Cs);
+    long long t = o / Cs;
+    const int X = static_cast<int>(t % (w * r)); t /= (w * r);
+    const int Y = static_cast<int>(t % (h * r));
+    const long long n = t / (h * r);
+    const int a = Y / r, j = Y % r, b = X / r, i = X % r;
+    const long long src = ((n * h + a) * w + b) * (static_cast<long long>(Cs) * r * r) + static_cast<long long>(k) * r * r + i * r + j;
+    if (inverse) out[src] = in[o];
+    else out[o] = in[src];
+  }
+}
+
+__global__ void __launch_bounds__(256) confusion_kernel(long long npix, int C, const float* labels,
+                                                        const uint8_t* argmax, unsigned long long* conf) {
+  extern __shared__ unsigned int s_conf[];   // [(C+1)*C]
+  const int b = blockIdx.y;
+  const int nb = (C + 1) * C;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_conf[i] = 0;
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>(labels[b * npix + i]);
+    const int p = argmax[b * npix + i];
+    if (l >= 0 && l <= C && p < C) atomicAdd(&s_conf[l * C + p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (s_conf[i]) atomicAdd(&conf[static_cast<size_t>(b) * nb + i], static_cast<unsigned long long>(s_conf[i]));
+}
+
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int dlb_resize_softmax_fwd(int B, int h, int w, int C, int ldl, int H, int W, const float* logits,
+                                      float* probs, uint8_t* argmax, void* stream) {
+  DLB_REQUIRE(logits && (probs || argmax), "resize_softmax_fwd: null pointer");
+  DLB_REQUIRE(C >= 1 && C <= ldl, "resize_softmax_fwd: C=%d ldl=%d", C, ldl);
+  const long long npix = static_cast<long long>(B) * H * W;
+  long long blocks = (npix + 127) / 128;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (C) {
+#define CASE(CC) case CC: resize_softmax_fwd_kernel<CC><<<grid, 128, 0, st>>>(B, h, w, ldl, H, W, logits, probs, argmax); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+    CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
+#undef CASE
+    default:
+      set_last_error("resize_softmax_fwd: classes=%d unsupported (2..24)", C);
+      return DLB_ERR_UNSUPPORTED;
+  }
+  g_launches++;
+  return check_launch("resize_softmax_fwd_kernel");
+}
+
+template <int C>
+static int launch_ce(const CeArgs& a, cudaStream_t st) {
+  if (a.S == 1) {
+    const long long npix = static_cast<long long>(a.B) * a.H * a.W;
+    long long blocks = (npix + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    softmax_ce_full_kernel<C><<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(a);
+  } else if (a.S == 8) {
+    const int tiles = ((a.w + 7) / 8) * ((a.h + 7) / 8);
+    resize_softmax_ce_kernel<C, 8><<<a.B * tiles, 256, 0, st>>>(a);
+  } else if (a.S == 4) {
+    const int tiles = ((a.w + 7) / 8) * ((a.h + 7) / 8);
+    resize_softmax_ce_kernel<C, 4><<<a.B * tiles, 256, 0, st>>>(a);
+  } else {
+    set_last_error("resize_softmax_ce: scale %d unsupported (1, 4, 8)", a.S);
+    return DLB_ERR_UNSUPPORTED;
+  }
+  g_launches++;
+  return check_launch("resize_softmax_ce_kernel");
+}
+
+extern "C" int dlb_resize_softmax_ce(const dlb_softmax_ce_params* p, void* stream) {
+  DLB_REQUIRE(p && p->logits && p->labels && p->grad_scale_dev && p->dlogits && p->loss_sum,
+              "resize_softmax_ce: null pointer");
+  DLB_REQUIRE(p->H % p->h == 0 && p->W % p->w == 0 && p->H / p->h == p->W / p->w,
+              "resize_softmax_ce: integer isotropic scale required (h=%d H=%d w=%d W=%d)", p->h, p->H, p->w, p->W);
+  CeArgs a{p->B, p->h, p->w, p->ldl, p->H, p->W, p->H / p->h, p->logits, p->labels, p->sample_w,
+           p->grad_scale_dev, p->dlogits, p->loss_sum, p->argmax};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (p->C) {
+    case 21: return launch_ce<21>(a, st);
+    case 2: return launch_ce<2>(a, st);
+    case 3: return launch_ce<3>(a, st);
+    case 4: return launch_ce<4>(a, st);
+    case 5: return launch_ce<5>(a, st);
+    case 8: return launch_ce<8>(a, st);
+    case 19: return launch_ce<19>(a, st);
+    default:
+      set_last_error("resize_softmax_ce: classes=%d not instantiated", p->C);
+      return DLB_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_scale_dev, double* wcount,
+                                 void* stream) {
+  DLB_REQUIRE(grad_scale_dev && wcount && n > 0, "ce_grad_scale: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DLB_CUDA(cudaMemsetAsync(wcount, 0, sizeof(double), st));
+  if (sample_w) {
+    long long blocks = (n + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    count_nonzero_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(n, sample_w, wcount);
+    g_launches++;
+  }
+  grad_scale_kernel<<<1, 1, 0, st>>>(n, sample_w != nullptr, wcount, grad_scale_dev);
+  g_launches++;
+  return check_launch("grad_scale_kernel");
+}
+
+extern "C" int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, const void* in, void* out, int inverse,
+                               void* stream) {
+  DLB_REQUIRE(in && out && r >= 1, "phase_shift: bad arguments");
+  const long long total = static_cast<long long>(B) * h * r * w * r * Cs;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLB_F32) phase_shift_kernel<float><<<grid, 256, 0, st>>>(total, h, w, Cs, r, (const float*)in, (float*)out, inverse);
+  else phase_shift_kernel<uint16_t><<<grid, 256, 0, st>>>(total, h, w, Cs, r, (const uint16_t*)in, (uint16_t*)out, inverse);
+  g_launches++;
+  return check_launch("phase_shift_kernel");
+}
+
+extern "C" int dlb_confusion(int B, int64_t npix, int C, const float* labels, const uint8_t* argmax,
+                             unsigned long long* conf, void* stream) {
+  DLB_REQUIRE(labels && argmax && conf && C >= 1 && C <= 255, "confusion: bad arguments");
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  dim3 grid(static_cast<unsigned>(blocks), B);
+  confusion_kernel<<<grid, 256, (C + 1) * C * sizeof(unsigned int), static_cast<cudaStream_t>(stream)>>>(
+      npix, C, labels, argmax, conf);
+  g_launches++;
+  return check_launch("confusion_kernel");
+}

@@ -1,0 +1,503 @@
+// Pointwise (1x1) convolution as a GEMM on the Blackwell tensor cores.
+//
+//   C[M, N] = epilogue(A[M, K] * Bt[N, K]^T)       M = B*H*W (large), K, N = channel counts (16..1344)
+//
+// Replaces every Conv2D(filters, (1,1)) of the reference graph (deeplabv3p.py:78-82, :175-177, :194-196,
+// :385, :406, :420, :438; utils.py:189; subpixel.py:90-91) together with the BatchNorm / ReLU6 / Add /
+// bias / phase-shift that follow it, which live in the epilogue.
+//
+// All of these GEMMs are HBM-bound (arithmetic intensity K*N/(K+N) <= 137 flop/B at 16 bit vs a ridge of
+// ~250 flop/B), so the design goal is: stream A exactly once from HBM, keep the (tiny) weights L2-resident,
+// and never let the tensor pipe or the epilogue stall the stream.
+//
+//   * persistent CTAs (one per SM), static tile striding over M tiles of 128 rows
+//   * warp 0   : TMA producer  (cp.async.bulk.tensor 2D, 128-byte swizzle, OOB zero fill pads K and N)
+//   * warp 1   : tcgen05.mma issuer (one thread), accumulators in TMEM (up to 512 fp32 columns,
+//                double-buffered when a column group is <= 256 wide), tcgen05.commit -> mbarriers
+//   * warps 2-5: epilogue, tcgen05.ld 32x32b -> registers -> fused BN-affine / bias / per-image bias /
+//                activation / residual / BatchNorm batch statistics / Subpixel phase-shift store
+//   * N > 512 (expand convs, Subpixel) is processed in column groups; A tiles are re-fetched through L2.
+//
+// DLB_F32 inputs take an exact-fp32 SIMT path (the 1e-3 parity mode of BASELINE.json; tf32 would not hold it).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dlb {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int kBlockM = 128;
+constexpr int kSwzBytes = 128;
+constexpr int kABytes = kBlockM * kSwzBytes;   // 16 KB per A stage
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  int n_store, ldc, ldr;
+  void* C;
+  const void* R;
+  const float* col_scale;
+  const float* col_shift;
+  const float* row_bias;
+  int rows_per_img, ld_row_bias;
+  int act;
+  double* stat_sum;
+  double* stat_sqs;
+  int shuffle_r, shuffle_h, shuffle_w, shuffle_cs;
+  int chunk_n, chunks_per_group, n_groups, n_chunks;
+  int num_k_blocks, num_m_tiles, num_stages, acc_stages, acc_cols;
+  int k_elems_per_block, umma_k;   // 64/16 for 16-bit inputs
+  uint32_t idesc;
+  uint32_t stage_bytes;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmArgs g) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* tail = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  const int npad = g.n_chunks * g.chunk_n;
+  float* s_shift = s_scale + npad;
+  float* s_sum = s_shift + npad;
+  float* s_sqs = s_sum + npad;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < npad; i += kGemmThreads) {
+    s_scale[i] = (g.col_scale && i < g.N) ? g.col_scale[i] : 1.f;
+    s_shift[i] = (g.col_shift && i < g.N) ? g.col_shift[i] : 0.f;
+    s_sum[i] = 0.f;
+    s_sqs[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int group_rows = g.chunks_per_group * g.chunk_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
+        const int m0 = tile * kBlockM;
+        for (int grp = 0; grp < g.n_groups; ++grp) {
+          const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
+          for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[stage], kABytes + chunks * g.chunk_n * kSwzBytes);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * g.k_elems_per_block, m0);
+            for (int c = 0; c < chunks; ++c)
+              tma_load_2d(sb + c * g.chunk_n * kSwzBytes, &tmap_b, &full_bar[stage], kb * g.k_elems_per_block,
+                          (grp * g.chunks_per_group + c) * g.chunk_n);
+            if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
+        for (int grp = 0; grp < g.n_groups; ++grp, ++it) {
+          const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
+          const int as = it % g.acc_stages;
+          const uint32_t aphase = (it / g.acc_stages) & 1;
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+            const uint32_t sb = sa + kABytes;
+            const int k_left = g.K - kb * g.k_elems_per_block;
+            const int ksteps = min(g.k_elems_per_block / g.umma_k, (k_left + g.umma_k - 1) / g.umma_k);
+            for (int c = 0; c < chunks; ++c) {
+              const uint32_t d_tmem = tmem_base + as * g.acc_cols + c * g.chunk_n;
+              for (int k = 0; k < ksteps; ++k) {
+                // +32 B per UMMA_K step inside the 128-byte swizzle atom
+                const uint64_t adesc = make_sw128_desc(sa + k * 32, 16, 1024);
+                const uint64_t bdesc = make_sw128_desc(sb + c * g.chunk_n * kSwzBytes + k * 32, 16, 1024);
+                umma_f16(d_tmem, adesc, bdesc, g.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs retire
+            if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[as]);          // accumulator group complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;                  // TMEM lane quarter this warp may access
+    const bool do_stats = g.stat_sum != nullptr;
+    const int red_col = reduce16_col_of_lane(lane);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
+      const int m = tile * kBlockM + quad * 32 + lane;
+      const bool row_ok = m < g.M;
+      const float* rb = nullptr;
+      if (g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
+      // Subpixel store geometry
+      size_t shuf_row_base = 0;
+      if (g.shuffle_r > 0 && row_ok) {
+        const int hw = g.shuffle_h * g.shuffle_w;
+        const int b = m / hw, rem = m - b * hw;
+        const int a = rem / g.shuffle_w, bb = rem - a * g.shuffle_w;
+        // element offset of out[b, a*r + 0, bb*r + 0, 0]
+        shuf_row_base = ((static_cast<size_t>(b) * g.shuffle_h * g.shuffle_r + static_cast<size_t>(a) * g.shuffle_r) *
+                             (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) +
+                         static_cast<size_t>(bb) * g.shuffle_r) *
+                        g.shuffle_cs;
+      }
+      for (int grp = 0; grp < g.n_groups; ++grp, ++it) {
+        const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
+        const int as = it % g.acc_stages;
+        const uint32_t aphase = (it / g.acc_stages) & 1;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const int gcols = chunks * g.chunk_n;
+        const int col_base = grp * group_rows;
+        for (int j = 0; j < gcols; j += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j, r);
+          tmem_ld_wait();
+          const int n0 = col_base + j;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = __uint_as_float(r[i]) * s_scale[n0 + i] + s_shift[n0 + i];
+            if (rb && n0 + i < g.N) x += rb[n0 + i];
+            v[i] = x;
+          }
+          if (do_stats) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float q = row_ok ? Act<OutT>::rnd(v[i]) : 0.f;
+              s1[i] = q; s2[i] = q * q;
+            }
+            const float t1 = warp_reduce16(s1, lane);
+            const float t2 = warp_reduce16(s2, lane);
+            if ((lane & 1) == 0) {
+              atomicAdd(&s_sum[n0 + red_col], t1);
+              atomicAdd(&s_sqs[n0 + red_col], t2);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], g.act);
+          if (row_ok) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int n = n0 + h8 * 8;
+              if (n >= g.n_store) continue;
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = v[h8 * 8 + i];
+              if (g.R) {
+                float rr[8];
+                Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += rr[i];
+              }
+              OutT* dst;
+              if (g.shuffle_r > 0) {
+                const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
+                const int jj = n / rowlen, rem = n - jj * rowlen;
+                dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
+                      static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
+              } else {
+                dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
+              }
+              if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
+                // fp32 outputs may end on a multiple of 4
+                float4 lo4 = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst) = lo4;
+              } else {
+                Vec8<OutT>::st(dst, o);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+    }
+    if (do_stats) {
+      named_bar_sync(1, 128);
+      for (int n = threadIdx.x - 64; n < g.N; n += 128) {
+        atomicAdd(&g.stat_sum[n], static_cast<double>(s_sum[n]));
+        atomicAdd(&g.stat_sqs[n], static_cast<double>(s_sqs[n]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact fp32 SIMT path (parity mode)
+// ---------------------------------------------------------------------------------------------
+struct SimtArgs {
+  int M, N, K, lda, ldb, ldc, ldr, n_store;
+  const float* A; const float* Bt; float* C; const float* R;
+  const float* col_scale; const float* col_shift; const float* row_bias;
+  int rows_per_img, ld_row_bias, act;
+  double* stat_sum; double* stat_sqs;
+  int shuffle_r, shuffle_h, shuffle_w, shuffle_cs;
+};
+
+__global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const SimtArgs g) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float sA[TK][TM + 4];
+  __shared__ float sB[TK][TN + 4];
+  __shared__ float s_sum[TN], s_sqs[TN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int tx = tid & 15, ty = tid >> 4;   // thread computes rows ty*4.., cols tx*4..
+  if (tid < TN) { s_sum[tid] = 0.f; s_sqs[tid] = 0.f; }
+  float acc[4][4] = {};
+  const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row lr (0..63), k offset lk
+  for (int k0 = 0; k0 < g.K; k0 += TK) {
+    {
+      float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+      const int m = m0 + lr, n = n0 + lr, k = k0 + lk;
+      if (m < g.M && k < g.K) a = *reinterpret_cast<const float4*>(g.A + static_cast<size_t>(m) * g.lda + k);
+      if (n < g.N && k < g.K) b = *reinterpret_cast<const float4*>(g.Bt + static_cast<size_t>(n) * g.ldb + k);
+      sA[lk + 0][lr] = a.x; sA[lk + 1][lr] = a.y; sA[lk + 2][lr] = a.z; sA[lk + 3][lr] = a.w;
+      sB[lk + 0][lr] = b.x; sB[lk + 1][lr] = b.y; sB[lk + 2][lr] = b.z; sB[lk + 3][lr] = b.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float cs[4] = {0, 0, 0, 0}, cq[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N && n >= g.n_store) continue;
+      float v = acc[i][j];
+      if (n < g.N) {
+        if (g.col_scale) v *= g.col_scale[n];
+        if (g.col_shift) v += g.col_shift[n];
+        if (g.row_bias) v += g.row_bias[static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias + n];
+        cs[j] += v; cq[j] += v * v;
+      } else {
+        v = 0.f;
+      }
+      v = apply_act(v, g.act);
+      if (n < g.n_store) {
+        if (g.R) v += g.R[static_cast<size_t>(m) * g.ldr + n];
+        size_t off;
+        if (g.shuffle_r > 0) {
+          const int hw = g.shuffle_h * g.shuffle_w;
+          const int b = m / hw, rem = m - b * hw;
+          const int a = rem / g.shuffle_w, bb = rem - a * g.shuffle_w;
+          const int rowlen = g.shuffle_r * g.shuffle_cs;
+          const int jj = n / rowlen, r2 = n - jj * rowlen;
+          off = ((static_cast<size_t>(b) * g.shuffle_h * g.shuffle_r + static_cast<size_t>(a) * g.shuffle_r + jj) *
+                     (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) +
+                 static_cast<size_t>(bb) * g.shuffle_r) * g.shuffle_cs + r2;
+        } else {
+          off = static_cast<size_t>(m) * g.ldc + n;
+        }
+        g.C[off] = v;
+      }
+    }
+  }
+  if (g.stat_sum) {
+    for (int j = 0; j < 4; ++j) { atomicAdd(&s_sum[tx * 4 + j], cs[j]); atomicAdd(&s_sqs[tx * 4 + j], cq[j]); }
+    __syncthreads();
+    if (tid < TN && n0 + tid < g.N) {
+      atomicAdd(&g.stat_sum[n0 + tid], static_cast<double>(s_sum[tid]));
+      atomicAdd(&g.stat_sqs[n0 + tid], static_cast<double>(s_sqs[tid]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols], 128 B swizzle
+int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled driver entry point unavailable"); return DLB_ERR_CUDA; }
+  const int es = dtype_size(dtype);
+  CUtensorMapDataType dt = dtype == DLB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                         : dtype == DLB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * es};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u ptr=%p", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, ptr);
+    return DLB_ERR_CUDA;
+  }
+  return DLB_OK;
+}
+
+static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
+  GemmArgs g{};
+  g.M = p->M; g.N = p->N; g.K = p->K;
+  g.n_store = p->n_store; g.ldc = p->ldc; g.ldr = p->ldr;
+  g.C = p->C; g.R = p->R;
+  g.col_scale = p->col_scale; g.col_shift = p->col_shift; g.row_bias = p->row_bias;
+  g.rows_per_img = p->rows_per_img > 0 ? p->rows_per_img : 1; g.ld_row_bias = p->ld_row_bias;
+  g.act = p->act; g.stat_sum = p->stat_sum; g.stat_sqs = p->stat_sqs;
+  g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
+  g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
+
+  const int npad = (p->N + 15) / 16 * 16;
+  g.n_chunks = (npad + 255) / 256;
+  g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
+  g.chunks_per_group = g.n_chunks >= 2 ? 2 : 1;
+  if (g.chunks_per_group * g.chunk_n > 512) g.chunks_per_group = 1;
+  g.n_groups = (g.n_chunks + g.chunks_per_group - 1) / g.chunks_per_group;
+  g.acc_cols = g.chunks_per_group * g.chunk_n;
+  g.acc_stages = g.acc_cols <= 256 ? 2 : 1;
+  g.k_elems_per_block = 64; g.umma_k = 16;
+  g.num_k_blocks = (p->K + 63) / 64;
+  g.num_m_tiles = (p->M + kBlockM - 1) / kBlockM;
+  g.stage_bytes = kABytes + g.acc_cols * kSwzBytes;
+  const int smem_budget = 200 * 1024;
+  g.num_stages = smem_budget / g.stage_bytes;
+  if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+  if (g.num_stages < 2) g.num_stages = 2;
+  g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 0, 0);
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, kBlockM, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, 64);
+  if (rc) return rc;
+
+  const size_t tail = (2 * kMaxStages + 4) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
+  const int grid = g.num_m_tiles < num_sms() ? g.num_m_tiles : num_sms();
+
+#define LAUNCH(OT)                                                                                             \
+  do {                                                                                                         \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                  (int)smem_bytes));                                                           \
+    pw_gemm_tc_kernel<OT><<<grid, kGemmThreads, smem_bytes, st>>>(ta, tb, g);                                  \
+  } while (0)
+  if (p->out_dtype == DLB_F16) LAUNCH(__half);
+  else if (p->out_dtype == DLB_BF16) LAUNCH(__nv_bfloat16);
+  else LAUNCH(float);
+#undef LAUNCH
+  g_launches++;
+  return check_launch("pw_gemm_tc_kernel");
+}
+
+static int launch_simt(const dlb_pw_gemm_params* p, cudaStream_t st) {
+  DLB_REQUIRE(p->out_dtype == DLB_F32, "pw_gemm: f32 inputs require f32 output");
+  DLB_REQUIRE(p->K % 4 == 0 && p->lda % 4 == 0 && p->ldb % 4 == 0, "pw_gemm(f32): K, lda, ldb must be multiples of 4");
+  SimtArgs g{};
+  g.M = p->M; g.N = p->N; g.K = p->K; g.lda = p->lda; g.ldb = p->ldb; g.ldc = p->ldc; g.ldr = p->ldr;
+  g.n_store = p->n_store;
+  g.A = (const float*)p->A; g.Bt = (const float*)p->Bt; g.C = (float*)p->C; g.R = (const float*)p->R;
+  g.col_scale = p->col_scale; g.col_shift = p->col_shift; g.row_bias = p->row_bias;
+  g.rows_per_img = p->rows_per_img > 0 ? p->rows_per_img : 1; g.ld_row_bias = p->ld_row_bias; g.act = p->act;
+  g.stat_sum = p->stat_sum; g.stat_sqs = p->stat_sqs;
+  g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
+  g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
+  const int ncols = p->n_store > p->N ? p->n_store : p->N;
+  dim3 grid((p->M + 63) / 64, (ncols + 63) / 64);
+  pw_gemm_simt_kernel<<<grid, 256, 0, st>>>(g);
+  g_launches++;
+  return check_launch("pw_gemm_simt_kernel");
+}
+
+}  // namespace dlb
+
+extern "C" int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream) {
+  using namespace dlb;
+  DLB_REQUIRE(p && p->A && p->Bt && p->C, "pw_gemm: null pointer");
+  DLB_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "pw_gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
+  DLB_REQUIRE(p->n_store > 0 && (p->shuffle_r > 0 || p->n_store <= p->ldc), "pw_gemm: n_store %d > ldc %d",
+              p->n_store, p->ldc);
+  if (p->shuffle_r > 0) {
+    const int r = p->shuffle_r;
+    DLB_REQUIRE(p->N % (r * r) == 0 && p->n_store == p->N, "pw_gemm: shuffle needs N %% r^2 == 0 and n_store == N");
+    DLB_REQUIRE((r * (p->N / (r * r))) % 8 == 0, "pw_gemm: shuffle needs r*Cs %% 8 == 0");
+    DLB_REQUIRE(p->M % (p->shuffle_h * p->shuffle_w) == 0, "pw_gemm: shuffle geometry does not divide M");
+    DLB_REQUIRE(p->R == nullptr, "pw_gemm: residual with shuffle store unsupported");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype == DLB_F32) return launch_simt(p, st);
+  const int es = 2;
+  DLB_REQUIRE((p->lda * es) % 16 == 0 && (p->ldb * es) % 16 == 0, "pw_gemm: lda/ldb must be 16-byte multiples");
+  DLB_REQUIRE((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->Bt) & 15) == 0,
+              "pw_gemm: A/Bt must be 16-byte aligned");
+  const int vec = p->out_dtype == DLB_F32 ? 4 : 8;
+  DLB_REQUIRE(p->n_store % vec == 0 && (p->shuffle_r > 0 || p->ldc % vec == 0), "pw_gemm: n_store/ldc must be multiples of %d", vec);
+  DLB_REQUIRE(p->R == nullptr || p->ldr % 8 == 0, "pw_gemm: ldr must be a multiple of 8");
+  DLB_REQUIRE(p->N <= 2048, "pw_gemm: N > 2048 unsupported");
+  return launch_tc(p, st);
+}

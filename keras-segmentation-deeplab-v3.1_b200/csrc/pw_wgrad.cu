@@ -1,0 +1,305 @@
+// Weight gradient of the pointwise convolutions:  dW[K, N] = A[M, K]^T * dY[M, N]   (reduction over M = B*H*W)
+//
+// This is the backward counterpart of pw_gemm.cu (TF autodiff of Conv2D 1x1 in the reference's fit_generator
+// step, utils.py:231-241).  The reduction dimension (pixels) is the *non*-contiguous one of both operands, so
+// the natural NHWC tiles [rows, 64 channels] are fed to tcgen05.mma as MN-major operands (same TMA box, same
+// 128-byte swizzle as the forward GEMM, only the descriptor's major bit and LBO change).
+//
+//   * output tile  : 128 (K channels) x up to 512 (N channels) fp32 accumulators in TMEM
+//   * split-M      : each output tile's pixel range is split over S CTAs so that tiles*S ~ #SMs; partial
+//                    results go to a workspace [S, K, N] with plain vector stores and are reduced by a second
+//                    tiny kernel (deterministic; ~10x less L2 traffic than fp32 atomics)
+//   * pipeline     : warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 TMEM -> global epilogue
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dlb {
+
+extern std::atomic<long long> g_launches;
+int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
+
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxStages = 8;
+
+struct WgArgs {
+  int M, N, K;
+  int rows_per_stage;          // R: reduction rows per pipeline stage (32 or 64)
+  int n_boxes;                 // 64-wide dY boxes per stage (N group / 64)
+  int n_chunks, chunk_n;       // UMMA N chunks per group
+  int k_tiles, n_groups, splits;
+  int rows_per_split;          // multiple of R
+  int num_stages;
+  uint32_t stage_bytes, a_bytes;
+  uint32_t idesc;
+  float* part;                 // [splits, K, N]
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
+                   const WgArgs g) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* tail = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kWgMaxStages;
+  uint64_t* done_bar = empty_bar + kWgMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_y);
+    for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item of this CTA
+  int wi = blockIdx.x;
+  const int split = wi % g.splits; wi /= g.splits;
+  const int ng = wi % g.n_groups;
+  const int kt = wi / g.n_groups;
+  const int k0 = kt * 128;
+  const int n0 = ng * g.n_boxes * 64;
+  const int m_begin = split * g.rows_per_split;
+  const int m_end = min(g.M, m_begin + g.rows_per_split);
+  const int R = g.rows_per_stage;
+  const int iters = m_end > m_begin ? (m_end - m_begin + R - 1) / R : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
+        uint8_t* sy = sa + g.a_bytes;
+        const int m = m_begin + it * R;
+        mbar_expect_tx(&full_bar[stage], g.a_bytes + g.n_boxes * R * 128);
+        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m);
+        tma_load_2d(sa + R * 128, &tmap_a, &full_bar[stage], k0 + 64, m);
+        for (int bx = 0; bx < g.n_boxes; ++bx) tma_load_2d(sy + bx * R * 128, &tmap_y, &full_bar[stage], n0 + bx * 64, m);
+        if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+        const uint32_t sy = sa + g.a_bytes;
+        for (int ks = 0; ks < R / 16; ++ks) {
+          // A operand: 128 channels = two 64-wide MN blocks, LBO = one box (R*128 B); 16 reduction rows per MMA
+          const uint64_t adesc = make_sw128_desc(sa + ks * 2048, R * 128, 1024);
+          for (int c = 0; c < g.n_chunks; ++c) {
+            const uint64_t bdesc = make_sw128_desc(sy + c * (g.chunk_n / 64) * R * 128 + ks * 2048, R * 128, 1024);
+            umma_f16(tmem_base + c * g.chunk_n, adesc, bdesc, g.idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int k = k0 + quad * 32 + lane;
+    float* dst_row = g.part + (static_cast<size_t>(split) * g.K + k) * g.N;
+    const int ncols = g.n_chunks * g.chunk_n;
+    if (iters > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    for (int j = 0; j < ncols; j += 16) {
+      const int n = n0 + j;
+      if (n >= g.N) break;
+      uint32_t r[16];
+      if (iters > 0) {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + j, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0u;
+      }
+      if (k < g.K) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nn = n + q * 4;
+          if (nn + 4 <= g.N) {
+            *reinterpret_cast<float4*>(dst_row + nn) = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+          } else {
+            for (int i = 0; i < 4; ++i)
+              if (nn + i < g.N) dst_row[nn + i] = __uint_as_float(r[q * 4 + i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+__global__ void wgrad_reduce_kernel(int n, int splits, const float* __restrict__ part, float* __restrict__ dW, float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[static_cast<size_t>(s) * n + i];
+  dW[i] = beta != 0.f ? beta * dW[i] + acc : acc;
+}
+
+// exact fp32 SIMT path: blocks (k tile, n tile, split), fp32 atomics into dW
+__global__ void __launch_bounds__(256) pw_wgrad_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                            const float* __restrict__ dY, int ldy, float* __restrict__ dW,
+                                                            int ldw, int rows_per_split) {
+  constexpr int T = 64, TR = 16;
+  __shared__ float sA[TR][T + 4];
+  __shared__ float sB[TR][T + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k0 = blockIdx.x * T, n0 = blockIdx.y * T;
+  const int m_begin = blockIdx.z * rows_per_split, m_end = min(M, m_begin + rows_per_split);
+  float acc[4][4] = {};
+  const int lr = tid >> 4, lc = (tid & 15) * 4;
+  for (int m0 = m_begin; m0 < m_end; m0 += TR) {
+    const int m = m0 + lr;
+    float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+    if (m < m_end) {
+      const float* ap = A + static_cast<size_t>(m) * lda + k0 + lc;
+      const float* bp = dY + static_cast<size_t>(m) * ldy + n0 + lc;
+      if (k0 + lc + 3 < K) a = *reinterpret_cast<const float4*>(ap);
+      else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + lc + i < K) t[i] = ap[i]; a = make_float4(t[0], t[1], t[2], t[3]); }
+      if (n0 + lc + 3 < N) b = *reinterpret_cast<const float4*>(bp);
+      else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (n0 + lc + i < N) t[i] = bp[i]; b = make_float4(t[0], t[1], t[2], t[3]); }
+    }
+    *reinterpret_cast<float4*>(&sA[lr][lc]) = a;
+    *reinterpret_cast<float4*>(&sB[lr][lc]) = b;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const float4 av = *reinterpret_cast<const float4*>(&sA[r][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[r][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(&dW[static_cast<size_t>(k) * ldw + n], acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const T* __restrict__ dY, int ldy, float* __restrict__ out) {
+  // one block per 32 columns-slab; threads stride rows
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  __shared__ float s[8][33];
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + rl; m < M; m += gridDim.y * 8) acc += Act<T>::ld(dY + static_cast<size_t>(m) * ldy + n);
+  s[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x & 31];
+    atomicAdd(&out[n], t);
+  }
+}
+
+}  // namespace dlb
+
+using namespace dlb;
+
+extern "C" int64_t dlb_pw_wgrad_workspace_bytes(int M, int N, int K) {
+  // upper bound: splits <= 2 * #SMs
+  (void)M;
+  return static_cast<int64_t>(2) * 148 * static_cast<int64_t>(K) * N * 4 + 256;
+}
+
+extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
+  DLB_REQUIRE(p && p->A && p->dY && p->dW, "pw_wgrad: null pointer");
+  DLB_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0 && p->ldw >= p->N, "pw_wgrad: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dbias) {
+    DLB_CUDA(cudaMemsetAsync(p->dbias, 0, sizeof(float) * p->N, st));
+    dim3 grid((p->N + 31) / 32, 128);
+    if (p->dtype == DLB_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>(p->M, p->N, (const __half*)p->dY, p->ldy, p->dbias);
+    else if (p->dtype == DLB_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p->M, p->N, (const __nv_bfloat16*)p->dY, p->ldy, p->dbias);
+    else colsum_kernel<float><<<grid, 256, 0, st>>>(p->M, p->N, (const float*)p->dY, p->ldy, p->dbias);
+    g_launches++;
+  }
+  if (p->dtype == DLB_F32) {
+    DLB_REQUIRE(p->lda % 4 == 0 && p->ldy % 4 == 0, "pw_wgrad(f32): lda/ldy must be multiples of 4");
+    if (p->beta == 0.f) DLB_CUDA(cudaMemsetAsync(p->dW, 0, sizeof(float) * p->K * p->ldw, st));
+    const int kt = (p->K + 63) / 64, nt = (p->N + 63) / 64;
+    int splits = (2 * num_sms() + kt * nt - 1) / (kt * nt);
+    int rps = ((p->M + splits - 1) / splits + 15) / 16 * 16;
+    splits = (p->M + rps - 1) / rps;
+    dim3 grid(kt, nt, splits);
+    pw_wgrad_simt_kernel<<<grid, 256, 0, st>>>(p->M, p->N, p->K, (const float*)p->A, p->lda, (const float*)p->dY,
+                                               p->ldy, p->dW, p->ldw, rps);
+    g_launches++;
+    return check_launch("pw_wgrad_simt_kernel");
+  }
+  DLB_REQUIRE(p->ldw == p->N, "pw_wgrad: ldw must equal N on the tensor-core path");
+  DLB_REQUIRE(p->workspace != nullptr, "pw_wgrad: workspace required on the tensor-core path");
+  DLB_REQUIRE((p->lda * 2) % 16 == 0 && (p->ldy * 2) % 16 == 0, "pw_wgrad: lda/ldy must be 16-byte multiples");
+  WgArgs g{};
+  g.M = p->M; g.N = p->N; g.K = p->K;
+  const int npad64 = (p->N + 63) / 64 * 64;
+  g.n_groups = (npad64 + 511) / 512;
+  const int group_cols = ((npad64 / 64 + g.n_groups - 1) / g.n_groups) * 64;   // <= 512, multiple of 64
+  g.n_boxes = group_cols / 64;
+  g.n_chunks = (group_cols + 255) / 256;
+  g.chunk_n = group_cols / g.n_chunks;
+  if (g.chunk_n % 64 != 0) { g.n_chunks = g.n_boxes; g.chunk_n = 64; }      // fall back to 64-wide chunks
+  g.rows_per_stage = group_cols <= 256 ? 64 : 32;
+  g.k_tiles = (p->K + 127) / 128;
+  const int tiles = g.k_tiles * g.n_groups;
+  int splits = (num_sms() + tiles - 1) / tiles;
+  const int R = g.rows_per_stage;
+  int rps = ((p->M + splits - 1) / splits + R - 1) / R * R;
+  splits = (p->M + rps - 1) / rps;
+  g.splits = splits; g.rows_per_split = rps;
+  const int64_t need = static_cast<int64_t>(splits) * p->K * p->N * 4;
+  DLB_REQUIRE(p->workspace_bytes >= need, "pw_wgrad: workspace too small (%lld < %lld)", (long long)p->workspace_bytes,
+              (long long)need);
+  g.part = static_cast<float*>(p->workspace);
+  g.a_bytes = 2 * R * 128;
+  g.stage_bytes = g.a_bytes + g.n_boxes * R * 128;
+  g.num_stages = (200 * 1024) / g.stage_bytes;
+  if (g.num_stages > kWgMaxStages) g.num_stages = kWgMaxStages;
+  g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 1, 1);
+  CUtensorMap ta, ty;
+  int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, R, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(&ty, p->dtype, p->dY, p->M, p->N, p->ldy, R, 64);
+  if (rc) return rc;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + (2 * kWgMaxStages + 1) * 8 + 16;
+  DLB_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  pw_wgrad_tc_kernel<<<tiles * splits, kWgThreads, smem_bytes, st>>>(ta, ty, g);
+  g_launches++;
+  rc = check_launch("pw_wgrad_tc_kernel");
+  if (rc) return rc;
+  const int n = p->K * p->N;
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, splits, g.part, p->dW, p->beta);
+  g_launches++;
+  return check_launch("wgrad_reduce_kernel");
+}

@@ -1,0 +1,386 @@
+"""Kernel-level parity: every C-ABI op against a plain PyTorch fp32 reference of the same op (on the GPU).
+
+The network-level parity tests against the oracle live in test_model_gpu.py; these isolate one kernel each so a
+failure points at a descriptor / index bug directly.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import deeplab_b200  # noqa: F401
+    from deeplab_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+GEMM_SHAPES = [
+    # (M, K, N)  -- the MobileNetV2 / ASPP / head shapes at reduced M, plus ragged M
+    (256, 64, 64), (384, 16, 96), (1024, 96, 24), (640, 24, 144), (512, 144, 32), (1024, 192, 64),
+    (512, 384, 96), (384, 576, 160), (256, 960, 320), (512, 160, 960), (300, 320, 256), (256, 256, 1344),
+    (1000, 256, 21), (128 * 37 + 5, 32, 192), (256, 512, 256),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
+def test_pw_gemm_tc_plain(M, K, N, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + K * 3 + N)
+    A = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    Bt = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+    ldc = (N + 7) // 8 * 8
+    out = torch.full((M, ldc), float("nan"), device="cuda", dtype=dtype)
+    ops.pw_gemm(A, Bt, out)
+    ref = A.float() @ Bt.float().t()
+    torch.cuda.synchronize()
+    tol = 4e-3 if dtype == torch.float16 else 2e-2
+    assert rel_err(out[:, :N], ref) < tol
+    if ldc > N:
+        assert (out[:, N:] == 0).all()    # zero-filled pad columns (OOB weight rows)
+
+
+@pytest.mark.parametrize("M,K,N", [(512, 96, 24), (384, 576, 160), (256, 160, 960), (640, 320, 256)])
+def test_pw_gemm_tc_epilogue(M, K, N):
+    """scale/shift + per-image bias + relu6 + residual + BN statistics, fp16."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    Bt = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    sc = torch.rand(N, device="cuda", generator=g) + 0.5
+    sh = torch.randn(N, device="cuda", generator=g)
+    rows_per_img = M // 2
+    rb = torch.randn(2, N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g).half()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ssum = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ssqs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.pw_gemm(A, Bt, out, col_scale=sc, col_shift=sh, row_bias=rb, rows_per_img=rows_per_img,
+                act=ops.ACT_RELU6, residual=R, stat_sum=ssum, stat_sqs=ssqs)
+    pre = (A.float() @ Bt.float().t()) * sc + sh + rb.repeat_interleave(rows_per_img, 0)
+    ref = pre.clamp(0, 6) + R.float()
+    assert rel_err(out, ref) < 4e-3
+    pre_r = pre.half().double()
+    assert rel_err(ssum, pre_r.sum(0)) < 1e-3
+    assert rel_err(ssqs, (pre_r * pre_r).sum(0)) < 1e-3
+
+
+def test_pw_gemm_f32_out_and_f32_exact():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, K, N = 777, 256, 21
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bt = torch.randn(N, K, device="cuda", generator=g) / 16
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A @ Bt.t() + bias
+    # 16-bit inputs, fp32 logits with padded pitch 32 (the head)
+    out = torch.full((M, 32), float("nan"), device="cuda")
+    ops.pw_gemm(A.half(), Bt.half(), out, col_shift=bias, n_store=32)
+    assert rel_err(out[:, :N], A.half().float() @ Bt.half().float().t() + bias) < 1e-3
+    # exact fp32 SIMT path
+    out32 = torch.full((M, 32), float("nan"), device="cuda")
+    ops.pw_gemm(A, Bt, out32, col_shift=bias, n_store=32)
+    assert rel_err(out32[:, :N], ref) < 1e-5
+    assert (out32[:, N:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_pw_gemm_subpixel_store(dtype):
+    """phase-shift fused into the epilogue == subpixel.py:77-88 applied to the plain conv output."""
+    ops = _ops()
+    from oracle import ref_ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, h, w, K, Cs, r = 2, 8, 16, 64, 21, 8
+    N = Cs * r * r
+    A = torch.randn(B * h * w, K, device="cuda", generator=g).to(dtype)
+    W_keras = (torch.randn(K, N, device="cuda", generator=g) / 8)       # Keras column order k*r*r + i*r + j
+    bias_keras = torch.randn(N, device="cuda", generator=g)
+    perm = torch.from_numpy(ref_ops.subpixel_column_perm(Cs, r)).cuda()  # internal column j' <- keras column perm[j']
+    Wt = W_keras[:, perm].t().contiguous().to(dtype)
+    bias = bias_keras[perm].contiguous()
+    out = torch.full((B, h * r, w * r, Cs), float("nan"), device="cuda", dtype=torch.float32)
+    ops.pw_gemm(A, Wt, out, col_shift=bias, shuffle=(r, h, w))
+    conv = (A.float() @ W_keras.to(dtype).float() + bias_keras).view(B, h, w, N).cpu()
+    ref = ref_ops.phase_shift(conv, r)
+    assert rel_err(out.cpu(), ref) < (3e-3 if dtype == torch.float16 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K,N", [(4096, 96, 24), (2048, 16, 96), (1024, 960, 160), (1536, 160, 960),
+                                   (8192 + 40, 320, 256), (1000, 256, 32), (2048, 384, 64), (512, 24, 144)])
+def test_pw_wgrad(M, K, N, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    dY = torch.randn(M, N, device="cuda", generator=g).to(dtype)
+    dW = torch.full((K, N), float("nan"), device="cuda")
+    db = torch.empty(N, device="cuda")
+    ws = torch.empty(ops.pw_wgrad_workspace_bytes(M, N, K) // 4, device="cuda")
+    ops.pw_wgrad(A, dY, dW, dbias=db, workspace=ws)
+    ref = A.float().t() @ dY.float()
+    assert rel_err(dW, ref) < 1e-4
+    assert rel_err(db, dY.float().sum(0)) < 1e-4
+    ops.pw_wgrad(A, dY, dW, beta=1.0, workspace=ws)
+    assert rel_err(dW, 2 * ref) < 1e-4
+
+
+def _dw_ref(x, w, stride, dil, in_scale=None, in_shift=None, in_act=0):
+    """NHWC fp32 reference with TF-SAME padding (oracle/ref_ops.py has the CPU twin)."""
+    a = x.float()
+    if in_scale is not None:
+        a = a * in_scale + in_shift
+        a = a.clamp(0, 6) if in_act == 2 else (a.clamp_min(0) if in_act == 1 else a)
+    B, H, W, C = a.shape
+    from deeplab_b200.ops import tf_same_pad
+    Ho, pt, pb = tf_same_pad(H, 3, stride, dil)
+    Wo, pl, pr = tf_same_pad(W, 3, stride, dil)
+    a = F.pad(a.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    y = F.conv2d(a, w.permute(2, 0, 1).unsqueeze(1), stride=stride, dilation=dil, groups=C)
+    return y.permute(0, 2, 3, 1).contiguous(), (Ho, Wo, pt, pl)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("H,W,C,stride,dil", [(32, 32, 96, 1, 1), (32, 48, 144, 2, 1), (33, 31, 32, 2, 1),
+                                               (16, 16, 384, 1, 2), (16, 16, 960, 1, 4), (24, 24, 64, 1, 12),
+                                               (8, 8, 2048, 1, 36)])
+def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    B = 2
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(dtype)
+    w = torch.randn(3, 3, C, device="cuda", generator=g) / 3
+    isc = torch.rand(C, device="cuda", generator=g) + 0.5
+    ish = torch.randn(C, device="cuda", generator=g) * 0.5
+    xr = x.float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref, (Ho, Wo, pt, pl) = _dw_ref(xr, wr, stride, dil, isc, ish, 2)
+    y = torch.empty(B, Ho, Wo, C, device="cuda", dtype=dtype)
+    ssum = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ssqs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ops.dw_conv_fwd(x, w, y, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc, in_shift=ish,
+                    in_act=2, stat_sum=ssum, stat_sqs=ssqs)
+    tol = 3e-3 if dtype == torch.float16 else 1e-5
+    assert rel_err(y, ref) < tol
+    yr = y.double()
+    assert rel_err(ssum, yr.sum((0, 1, 2))) < 1e-4 + 1e-9
+    assert rel_err(ssqs, (yr * yr).sum((0, 1, 2))) < 1e-4
+    # backward: gradient w.r.t. the *activated* input a and w.r.t. the weights
+    dy = torch.randn(B, Ho, Wo, C, device="cuda", generator=g).to(dtype)
+    a = (x.float() * isc + ish).clamp(0, 6).requires_grad_(True)
+    ref2, _ = _dw_ref(a, wr, stride, dil)
+    ga, gw = torch.autograd.grad(ref2, [a, wr], dy.float())
+    dx = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=dtype)
+    dw = torch.zeros(3, 3, C, device="cuda")
+    ops.dw_conv_bwd(x, dy, w, dx=dx, dw=dw, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc,
+                    in_shift=ish, in_act=2)
+    assert rel_err(dx, ga) < tol
+    assert rel_err(dw, gw) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("H,W", [(64, 64), (33, 47)])
+def test_stem_conv(H, W, dtype):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(H)
+    B = 2
+    x = torch.randint(0, 256, (B, H, W, 3), device="cuda", generator=g).float()
+    w = torch.randn(3, 3, 3, 32, device="cuda", generator=g) / 5
+    Ho, pt, pb = ops.tf_same_pad(H, 3, 2, 1)
+    Wo, pl, pr = ops.tf_same_pad(W, 3, 2, 1)
+    xp = F.pad((x / 127.5 - 1).permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(xp, wr.permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1)
+    y = torch.empty(B, Ho, Wo, 32, device="cuda", dtype=dtype)
+    ssum = torch.zeros(32, device="cuda", dtype=torch.float64)
+    ssqs = torch.zeros(32, device="cuda", dtype=torch.float64)
+    ops.stem_conv_fwd(x, w, y, stat_sum=ssum, stat_sqs=ssqs)
+    tol = 3e-3 if dtype == torch.float16 else 1e-5
+    assert rel_err(y, ref) < tol
+    assert rel_err(ssqs, (y.double() ** 2).sum((0, 1, 2))) < 1e-4
+    dy = torch.randn(B, Ho, Wo, 32, device="cuda", generator=g).to(dtype)
+    (gw,) = torch.autograd.grad(ref, [wr], dy.float())
+    dw = torch.zeros(3, 3, 3, 32, device="cuda")
+    ops.stem_conv_wgrad(x, dy, dw)
+    assert rel_err(dw, gw) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_bn_train_fwd_bwd(dtype):
+    """finalize + apply (+residual) and the two-pass backward vs autograd through F.batch_norm."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, C = 4096, 96
+    x = (torch.randn(M, C, device="cuda", generator=g) * 2 + 0.5).to(dtype)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g)
+    res = torch.randn(M, C, device="cuda", generator=g).to(dtype)
+    xd = x.double()
+    ssum, ssqs = xd.sum(0), (xd * xd).sum(0)
+    mm, mv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    scale, shift, mean, rstd = (torch.empty(C, device="cuda") for _ in range(4))
+    eps, mom = 1e-3, 0.999
+    ops.bn_finalize(M, ssum, ssqs, gamma, beta, eps, mom, mm, mv, scale, shift, mean, rstd)
+    assert (ssum == 0).all()
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(xr, None, None, gr, br, True, 0.0, eps)
+    ref = z.clamp(0, 6) + res.float()
+    y = torch.empty_like(x)
+    ops.bn_act_apply(x, y, scale=scale, shift=shift, act=2, res=res)
+    tol = 3e-3 if dtype == torch.float16 else 2e-5
+    assert rel_err(y, ref) < tol
+    var_u = x.float().var(0, unbiased=True)
+    assert rel_err(mv, 0.999 + 0.001 * var_u) < 1e-5
+    assert rel_err(mm, 0.001 * x.float().mean(0)) < 1e-4
+    da = torch.randn(M, C, device="cuda", generator=g).to(dtype)
+    gx, gg, gb = torch.autograd.grad(ref, [xr, gr, br], da.float())
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_bwd(x, da, dx, scale=scale, shift=shift, mean=mean, rstd=rstd, act=2, red=red, dgamma=dgamma, dbeta=dbeta)
+    assert rel_err(dx, gx) < (5e-3 if dtype == torch.float16 else 1e-4)
+    assert rel_err(dgamma, gg) < 1e-3
+    assert rel_err(dbeta, gb) < 1e-3
+
+
+def test_dropout_apply_and_bwd_consistent():
+    ops = _ops()
+    M, C = 2048, 256
+    x = torch.randn(M, C, device="cuda")
+    one, zero = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    y = torch.empty_like(x)
+    ops.bn_act_apply(x, y, scale=one, shift=zero, act=1, drop_rate=0.1, drop_seed=1234)
+    kept = (y != 0) | (x <= 0)
+    frac = ((y == 0) & (x > 0)).float().sum() / (x > 0).float().sum()
+    assert abs(frac.item() - 0.1) < 0.01
+    assert rel_err(y[kept & (x > 0)], x[kept & (x > 0)] / 0.9) < 1e-6
+    # backward uses the same mask
+    red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    dx = torch.empty_like(x)
+    da = torch.ones_like(x)
+    ops.bn_bwd(x, da, dx, scale=one, shift=zero, mean=zero, rstd=one, act=1, red=red, drop_rate=0.1, drop_seed=1234,
+               frozen=True)
+    assert torch.equal(dx != 0, y != 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_global_avgpool(dtype):
+    ops = _ops()
+    B, HW, C = 3, 1024, 320
+    x = torch.randn(B, HW, C, device="cuda").to(dtype)
+    out = torch.empty(B, C, device="cuda")
+    ops.global_avgpool_fwd(x, out)
+    assert rel_err(out, x.float().mean(1)) < 1e-4
+    d = torch.randn(B, C, device="cuda")
+    dx = torch.randn(B, HW, C, device="cuda").to(dtype)
+    base = dx.float().clone()
+    ops.global_avgpool_bwd(d, dx, True)
+    assert rel_err(dx, base + d[:, None, :] / HW) < (2e-3 if dtype == torch.float16 else 1e-6)
+
+
+def test_small_gemm():
+    ops = _ops()
+    A = torch.randn(16, 320, device="cuda")
+    Bm = torch.randn(320, 256, device="cuda")
+    out = torch.empty(16, 256, device="cuda")
+    ops.small_gemm(A, Bm, out, M=16, N=256, K=320)
+    assert rel_err(out, A @ Bm) < 1e-5
+    out2 = torch.empty(320, 256, device="cuda")
+    ops.small_gemm(A, out, out2, M=320, N=256, K=16, transA=True, alpha=2.0)
+    assert rel_err(out2, 2 * A.t() @ out) < 1e-5
+
+
+@pytest.mark.parametrize("h,w,S,ldl", [(16, 16, 8, 32), (12, 20, 8, 32), (16, 24, 4, 32), (32, 32, 1, 21)])
+def test_resize_softmax_and_ce(h, w, S, ldl):
+    ops = _ops()
+    from oracle import ref_ops
+    g = torch.Generator(device="cuda").manual_seed(h * w + S)
+    B, C = 2, 21
+    H, W = h * S, w * S
+    logits = torch.zeros(B, h, w, ldl, device="cuda")
+    logits[..., :C] = torch.randn(B, h, w, C, device="cuda", generator=g) * 3
+    probs = torch.empty(B, H * W, C, device="cuda")
+    am = torch.empty(B, H * W, device="cuda", dtype=torch.uint8)
+    ops.resize_softmax_fwd(logits, C, H, W, probs, am)
+    lr = logits[..., :C].cpu().clone().requires_grad_(True)
+    up = ref_ops.resize_bilinear_tf1(lr, H, W)
+    pref = torch.softmax(up.reshape(B, H * W, C), -1)
+    assert rel_err(probs.cpu(), pref.detach()) < 1e-5
+    assert (am.cpu().long() == pref.argmax(-1)).float().mean() > 0.9999
+    labels = torch.randint(0, C + 1, (B, H * W, 1), device="cuda", generator=g).float()
+    sw = torch.rand(B, H * W, device="cuda", generator=g)
+    sw[sw < 0.2] = 0
+    loss_ref = ref_ops.keras_weighted_loss(labels.cpu(), pref, sw.cpu())
+    (gref,) = torch.autograd.grad(loss_ref, [lr])
+    gs = torch.zeros(1, device="cuda")
+    wc = torch.zeros(1, device="cuda", dtype=torch.float64)
+    ops.ce_grad_scale(B * H * W, sw, gs, wc)
+    assert wc.item() == (sw != 0).sum().item()
+    dlog = torch.zeros(B, h, w, ldl, device="cuda")
+    loss_sum = torch.zeros(1, device="cuda", dtype=torch.float64)
+    am2 = torch.empty_like(am)
+    ops.resize_softmax_ce(logits, C, H, W, labels, sw, gs, dlog, loss_sum, wc, am2)
+    loss = loss_sum.item() / wc.item()
+    assert abs(loss - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    assert rel_err(dlog[..., :C].cpu(), gref) < 1e-4
+    assert torch.equal(am, am2)
+
+
+def test_phase_shift_roundtrip():
+    ops = _ops()
+    from oracle import ref_ops
+    B, h, w, Cs, r = 2, 4, 6, 21, 8
+    x = torch.randn(B, h, w, Cs * r * r, device="cuda")
+    out = torch.empty(B, h * r, w * r, Cs, device="cuda")
+    ops.phase_shift(x, out, r)
+    assert torch.equal(out.cpu(), ref_ops.phase_shift(x.cpu(), r))
+    back = torch.empty_like(x)
+    ops.phase_shift(out, back, r, inverse=True)
+    assert torch.equal(back, x)
+
+
+def test_adam_matches_keras_rule():
+    ops = _ops()
+    from oracle import ref_ops
+    n = 10007
+    p = torch.randn(n, device="cuda")
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    step = torch.zeros(1, device="cuda", dtype=torch.int64)
+    pr, mr, vr = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
+    for it in range(3):
+        gte = torch.randn(n, device="cuda")
+        ops.adam_step(p, gte, m, v, step, lr=7e-4, eps=1e-8, decay=1e-6)
+        pr, mr, vr = ref_ops.keras_adam(pr, gte.cpu(), mr, vr, it, lr=7e-4, eps=1e-8, decay=1e-6)
+    assert step.item() == 3
+    assert rel_err(p.cpu(), pr) < 1e-6
+
+
+def test_cast_weight_and_confusion():
+    ops = _ops()
+    K, N = 96, 24
+    w = torch.randn(K, N, device="cuda")
+    wkn = torch.empty(K, N, device="cuda", dtype=torch.float16)
+    wnk = torch.empty(N, K, device="cuda", dtype=torch.float16)
+    ops.cast_weight(w, K, N, wkn, wnk)
+    assert torch.equal(wkn, w.half()) and torch.equal(wnk, w.half().t())
+    B, npix, C = 2, 5000, 21
+    labels = torch.randint(0, C + 1, (B, npix, 1), device="cuda").float()
+    am = torch.randint(0, C, (B, npix), device="cuda", dtype=torch.uint8)
+    conf = torch.zeros(B, C + 1, C, device="cuda", dtype=torch.int64)
+    ops.confusion(labels, am, C, conf)
+    ref = torch.zeros(B, C + 1, C, dtype=torch.int64)
+    for b in range(B):
+        idx = labels[b, :, 0].long().cpu() * C + am[b].long().cpu()
+        ref[b] = torch.bincount(idx, minlength=(C + 1) * C).view(C + 1, C)
+    assert torch.equal(conf.cpu(), ref)
