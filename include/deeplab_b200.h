@@ -161,6 +161,7 @@ typedef struct {
   const void* x; void* y; const void* res;
   const float* scale; const float* shift; int act;
   float drop_rate; uint64_t drop_seed;      /* Dropout(0.1), deeplabv3p.py:410; 0 = off */
+  const int64_t* drop_seed_dev;             /* optional device counter added to drop_seed (graph replay) */
 } dlb_bn_apply_params;
 int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream);
 /* Backward through  a = dropout(act(z)), z = x*scale + shift  where scale/shift come from batch statistics.
@@ -178,6 +179,7 @@ typedef struct {
   float* dgamma; float* dbeta;   /* fp32 results written by pass 2 (may be NULL) */
   float drop_rate; uint64_t drop_seed;
   int frozen_stats;
+  const int64_t* drop_seed_dev;
 } dlb_bn_bwd_params;
 int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream);
 int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream);

@@ -67,7 +67,7 @@ class StemConvParams(C.Structure):
 class BnApplyParams(C.Structure):
     _fields_ = [
         ("M", i64), ("C", i32), ("dtype", i32), ("x", vp), ("y", vp), ("res", vp),
-        ("scale", vp), ("shift", vp), ("act", i32), ("drop_rate", f32), ("drop_seed", u64),
+        ("scale", vp), ("shift", vp), ("act", i32), ("drop_rate", f32), ("drop_seed", u64), ("drop_seed_dev", vp),
     ]
 
 
@@ -76,6 +76,7 @@ class BnBwdParams(C.Structure):
         ("M", i64), ("C", i32), ("dtype", i32), ("x", vp), ("da", vp), ("dx", vp),
         ("scale", vp), ("shift", vp), ("mean", vp), ("rstd", vp), ("act", i32),
         ("red", vp), ("dgamma", vp), ("dbeta", vp), ("drop_rate", f32), ("drop_seed", u64), ("frozen_stats", i32),
+        ("drop_seed_dev", vp),
     ]
 
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
 
 struct ApplyArgs {
   long long nvec; int C; const void* x; void* y; const void* res;
-  const float* scale; const float* shift; int act; float drop_rate; uint64_t seed;
+  const float* scale; const float* shift; int act; float drop_rate; uint64_t seed; const long long* seed_dev;
 };
 
 template <typename T>
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
   const T* res = reinterpret_cast<const T*>(a.res);
   T* y = reinterpret_cast<T*>(a.y);
   const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+  const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long e0 = i * 8;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
     for (int k = 0; k < 8; ++k) {
       float z = a.scale ? fmaf(v[k], a.scale[c0 + k], a.shift[c0 + k]) : v[k];
       z = apply_act(z, a.act);
-      if (a.drop_rate > 0.f) z = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? z * keep_inv : 0.f;
+      if (a.drop_rate > 0.f) z = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? z * keep_inv : 0.f;
       v[k] = z;
     }
     if (res) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
 struct BwdArgs {
   long long M; int C; const void* x; const void* da; void* dx;
   const float* scale; const float* shift; const float* mean; const float* rstd; int act;
-  double* red; float* dgamma; float* dbeta; float drop_rate; uint64_t seed; int frozen;
+  double* red; float* dgamma; float* dbeta; float drop_rate; uint64_t seed; const long long* seed_dev; int frozen;
   int cv, rpb;   // channel vectors, rows per block
 };
 
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
     const T* x = reinterpret_cast<const T*>(a.x);
     const T* da = reinterpret_cast<const T*>(a.da);
     const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+    const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
     for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
          r += static_cast<long long>(gridDim.x) * a.rpb) {
       const long long e0 = r * a.C + c0;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
       for (int k = 0; k < 8; ++k) {
         const float z = fmaf(xv[k], sc[k], sh[k]);
         float dz = gv[k] * act_mask(z, a.act);
-        if (a.drop_rate > 0.f) dz = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+        if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
         s1[k] += dz;
         s2[k] += dz * (xv[k] - mu[k]) * rs[k];
       }
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   const T* da = reinterpret_cast<const T*>(a.da);
   T* dx = reinterpret_cast<T*>(a.dx);
   const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
+  const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
   for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
        r += static_cast<long long>(gridDim.x) * a.rpb) {
     const long long e0 = r * a.C + c0;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
     for (int k = 0; k < 8; ++k) {
       const float z = fmaf(xv[k], sc[k], sh[k]);
       float dz = gv[k] * act_mask(z, a.act);
-      if (a.drop_rate > 0.f) dz = hash_uniform(a.seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+      if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
       const float xhat = (xv[k] - mu[k]) * rs[k];
       o[k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
     }
@@ -277,7 +280,8 @@ extern "C" int dlb_bn_fold(int C, const float* gamma, const float* beta, const f
 extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   DLB_REQUIRE(p && p->x && p->y, "bn_act_apply: null pointer");
   DLB_REQUIRE(p->C % 8 == 0, "bn_act_apply: C must be a multiple of 8 (C=%d)", p->C);
-  ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed};
+  ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed,
+              reinterpret_cast<const long long*>(p->drop_seed_dev)};
   const int grid = grid_for(a.nvec, 256, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16) bn_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
@@ -293,6 +297,7 @@ static int fill_bwd(const dlb_bn_bwd_params* p, BwdArgs* a) {
   a->M = p->M; a->C = p->C; a->x = p->x; a->da = p->da; a->dx = p->dx;
   a->scale = p->scale; a->shift = p->shift; a->mean = p->mean; a->rstd = p->rstd; a->act = p->act;
   a->red = p->red; a->dgamma = p->dgamma; a->dbeta = p->dbeta; a->drop_rate = p->drop_rate; a->seed = p->drop_seed;
+  a->seed_dev = reinterpret_cast<const long long*>(p->drop_seed_dev);
   a->frozen = p->frozen_stats; a->cv = p->C / 8; a->rpb = 256 / a->cv;
   return DLB_OK;
 }

@@ -133,7 +133,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int nn = n + q * 4;
-          if (nn + 4 <= g.N) {
+          if (nn + 4 <= g.N && (g.N & 3) == 0) {
             *reinterpret_cast<float4*>(dst_row + nn) = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
                                                                    __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
           } else {

@@ -157,7 +157,7 @@ def bn_fold(gamma, beta, moving_mean, moving_var, eps: float, scale, shift):
 
 
 def bn_act_apply(x: torch.Tensor, y: torch.Tensor, *, scale=None, shift=None, act: int = ACT_NONE, res=None,
-                 drop_rate: float = 0.0, drop_seed: int = 0):
+                 drop_rate: float = 0.0, drop_seed: int = 0, drop_seed_dev=None):
     L.require_cuda(x, y)
     p = L.BnApplyParams()
     p.C = x.shape[-1]
@@ -165,12 +165,13 @@ def bn_act_apply(x: torch.Tensor, y: torch.Tensor, *, scale=None, shift=None, ac
     p.dtype = L.dt(x)
     p.x, p.y, p.res = x.data_ptr(), y.data_ptr(), L.ptr(res)
     p.scale, p.shift, p.act = L.ptr(scale), L.ptr(shift), act
-    p.drop_rate, p.drop_seed = drop_rate, drop_seed
+    p.drop_rate, p.drop_seed, p.drop_seed_dev = drop_rate, drop_seed, L.ptr(drop_seed_dev)
     L.check(L.lib().dlb_bn_act_apply(C.byref(p), L.stream_ptr()), "bn_act_apply")
     return y
 
 
-def _bn_bwd_params(x, da, dx, scale, shift, mean, rstd, act, red, dgamma, dbeta, drop_rate, drop_seed, frozen):
+def _bn_bwd_params(x, da, dx, scale, shift, mean, rstd, act, red, dgamma, dbeta, drop_rate, drop_seed, frozen,
+                   drop_seed_dev=None):
     p = L.BnBwdParams()
     p.C = x.shape[-1]
     p.M = x.numel() // p.C
@@ -179,14 +180,16 @@ def _bn_bwd_params(x, da, dx, scale, shift, mean, rstd, act, red, dgamma, dbeta,
     p.scale, p.shift, p.mean, p.rstd, p.act = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), act
     p.red, p.dgamma, p.dbeta = red.data_ptr(), L.ptr(dgamma), L.ptr(dbeta)
     p.drop_rate, p.drop_seed, p.frozen_stats = drop_rate, drop_seed, int(frozen)
+    p.drop_seed_dev = L.ptr(drop_seed_dev)
     return p
 
 
 def bn_bwd(x, da, dx, *, scale, shift, mean, rstd, act, red, dgamma=None, dbeta=None, drop_rate=0.0, drop_seed=0,
-           frozen=False):
+           frozen=False, drop_seed_dev=None):
     """Both passes of the BatchNorm(+activation, +dropout) backward; `red` ([2C] fp64) must be zero on entry."""
     L.require_cuda(x, da, dx)
-    p = _bn_bwd_params(x, da, dx, scale, shift, mean, rstd, act, red, dgamma, dbeta, drop_rate, drop_seed, frozen)
+    p = _bn_bwd_params(x, da, dx, scale, shift, mean, rstd, act, red, dgamma, dbeta, drop_rate, drop_seed, frozen,
+                       drop_seed_dev)
     L.check(L.lib().dlb_bn_bwd_reduce(C.byref(p), L.stream_ptr()), "bn_bwd_reduce")
     L.check(L.lib().dlb_bn_bwd_apply(C.byref(p), L.stream_ptr()), "bn_bwd_apply")
     return dx

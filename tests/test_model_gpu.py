@@ -1,0 +1,321 @@
+"""Network-level parity of the CUDA path (through the reference-facing API) against the oracle.
+
+  * config 1 (BASELINE.json): Deeplabv3(backbone='mobilenetv2', input_shape=(512,512,3), classes=21, OS=16) with the
+    reference's weights, fp32 mode vs the committed golden logits: 1e-3 relative (north_star tolerance).
+  * 16-bit tensor-core mode vs the oracle (looser: storage rounding at every layer).
+  * training step (fwd + bwd + Keras Adam + BN moving averages) vs the oracle's autograd step on seeded inputs.
+Tolerances are written at each assert.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _push_weights(model, W):
+    """oracle weight dict (Keras layer name -> list) into the model, by layer name."""
+    for l in model.layers:
+        if l.name in W:
+            l.set_weights([w.detach().float().numpy() for w in W[l.name]])
+
+
+def _pull_weights(model):
+    return {l.name: [torch.from_numpy(a) for a in l.get_weights()] for l in model.layers if l._rec is not None}
+
+
+# ----------------------------------------------------------------------------------------------- inference
+def test_config1_fp32_matches_golden_logits():
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    g = np.load(os.path.join(GOLD, "golden_mnv2.npz"))
+    model = Deeplabv3(weights=None, input_shape=(512, 512, 3), classes=21, backbone='mobilenetv2', OS=16,
+                      compute_dtype='float32')
+    model.load_weights(os.path.join(GOLD, "mobilenetv2_original.h5"))     # topological load (head: conv_upsample)
+    x = np.random.RandomState(0).randint(0, 256, (1, 512, 512, 3)).astype(np.float32)
+    probs = model.predict(x)
+    assert probs.shape == (1, 512 * 512, 21)
+    ws = model.engine.workspace(1, False)
+    logits = ws["logits"][..., :21].cpu().numpy()
+    ref = g["logits"]
+    # north_star: within 1e-3 rel fp32:  |a-b| <= 1e-3 * max|b|
+    assert np.abs(logits - ref).max() <= 1e-3 * np.abs(ref).max()
+    am = probs.argmax(-1).reshape(512, 512)
+    assert (am == g["argmax"]).mean() > 0.9995
+    assert abs(probs.max(-1).mean() - float(g["prob_max_mean"])) < 1e-4
+    np.testing.assert_allclose(probs.sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype,tol,agree", [("float16", 3e-2, 0.99), ("bfloat16", 2e-1, 0.95)])
+def test_config1_16bit_tensor_core_path(dtype, tol, agree):
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    g = np.load(os.path.join(GOLD, "golden_mnv2.npz"))
+    model = Deeplabv3(weights=None, input_shape=(512, 512, 3), compute_dtype=dtype)
+    model.load_weights(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    x = np.random.RandomState(0).randint(0, 256, (1, 512, 512, 3)).astype(np.float32)
+    probs = model.predict(x)
+    logits = model.engine.workspace(1, False)["logits"][..., :21].cpu().numpy()
+    assert np.abs(logits - g["logits"]).max() <= tol * np.abs(g["logits"]).max()
+    assert (probs.argmax(-1).reshape(512, 512) == g["argmax"]).mean() > agree
+
+
+def test_example_figures_semantic_known_answer():
+    """weak KAT on the reference's own example figures: dominant non-background classes."""
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    ex = np.load(os.path.join(GOLD, "example_crops.npz"))
+    model = Deeplabv3(weights=None, input_shape=(512, 512, 3), compute_dtype='float16')
+    model.load_weights(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    expect = {"exp1": 1, "exp3": 15, "exp4": 12}          # airplane / person(+sheep) / dog
+    for name, cls in expect.items():
+        p = model.predict(ex[name][None].astype(np.float32))
+        c, n = np.unique(p.argmax(-1), return_counts=True)
+        top = [int(k) for k in c[np.argsort(-n)] if k != 0]
+        assert top and top[0] == cls and top[0] == int(ex[f"dom_{name}_original"][0])
+
+
+def test_batched_inference_matches_oracle_small():
+    """B=3, 128x192 (non-square), fp32 mode, seeded random weights with non-trivial BN stats, vs the live oracle."""
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    from oracle import network as N
+    W = N.random_mobilenetv2_weights(seed=3)
+    model = Deeplabv3(weights=None, input_shape=(128, 192, 3), compute_dtype='float32')
+    _push_weights(model, W)
+    x = np.random.RandomState(1).randint(0, 256, (3, 128, 192, 3)).astype(np.float32)
+    probs = model.predict(x, batch_size=3)
+    with torch.no_grad():
+        _, pref, _ = N.deeplabv3_forward(W, torch.from_numpy(x))
+    assert rel(probs, pref) < 1e-3
+
+
+def test_subpixel_model_inference_matches_oracle():
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    d = np.load(os.path.join(GOLD, "subpixel_delta.npz"))
+    W = N.weights_from_h5(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    head = N.find_head_layer(W)
+    Ws = type(W)()
+    for k, v in W.items():
+        if k == head:
+            Ws["subpixel_1"] = [torch.from_numpy(d["subpixel_1::0"]), torch.from_numpy(d["subpixel_1::1"])]
+        elif k == "concat_projection_BN":
+            Ws[k] = [torch.from_numpy(d[f"{k}::{i}"]) for i in range(4)]
+        else:
+            Ws[k] = v
+    x = np.random.RandomState(0).randint(0, 256, (1, 512, 512, 3)).astype(np.float32)
+    with torch.no_grad():
+        _, pref, _ = N.deeplabv3_forward(Ws, torch.from_numpy(x), net="subpixel")
+    sm = SegModel(image_size=(512, 512), compute_dtype='float32')
+    model = sm.create_seg_model('subpixel', n=21)
+    assert model.layers[-3].name.startswith("subpixel") and model.layers[-1].name == "pred_mask"
+    _push_weights(model, {**Ws, model.layers[-3].name: Ws["subpixel_1"]})
+    probs = model.predict(x)
+    assert rel(probs, pref) < 1e-3
+    sm16 = SegModel(image_size=(512, 512), compute_dtype='float16')
+    m16 = sm16.create_seg_model('subpixel', n=21)
+    _push_weights(m16, {**Ws, m16.layers[-3].name: Ws["subpixel_1"]})
+    p16 = m16.predict(x)
+    assert (p16.argmax(-1) == pref.argmax(-1).numpy()).mean() > 0.98
+
+
+# ----------------------------------------------------------------------------------------------- training
+def _synthetic_batch(B, H, W, C=21, seed=0):
+    rng = np.random.RandomState(seed)
+    x = rng.randint(0, 256, (B, H, W, 3)).astype(np.float32)
+    y = np.zeros((B, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        for k in range(3):
+            cy, cx, ry, rx = rng.randint(0, H), rng.randint(0, W), rng.randint(H // 8, H // 2), rng.randint(W // 8, W // 2)
+            d = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2
+            lab = rng.randint(1, C)
+            y[b][d < 1.0] = lab
+            y[b][(d >= 1.0) & (d < 1.2)] = C          # void ring
+    sw = rng.uniform(0.5, 2.0, (B, H * W)).astype(np.float32)
+    sw[rng.uniform(size=sw.shape) < 0.1] = 0.0
+    return x, y.reshape(B, H * W, 1), sw
+
+
+@pytest.mark.parametrize("net", ["original", "subpixel"])
+def test_train_step_fp32_matches_oracle(net):
+    """one full step (all layers trainable, dropout off): loss, updated parameters, BN moving stats."""
+    from deeplab_b200.model import Adam
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import train as T
+    B, H, Wd = 2, 64, 96
+    sm = SegModel(image_size=(H, Wd), compute_dtype='float32')
+    model = sm.create_seg_model(net, n=21, seed=5)
+    model.dropout_in_training = False
+    head_name = model.engine.head_conv.name
+    W = N.random_mobilenetv2_weights(seed=7, head=head_name, head_filters=21 * 64 if net == "subpixel" else 21)
+    _push_weights(model, W)
+    model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+    x, y, sw = _synthetic_batch(B, H, Wd)
+    vals = model.train_on_batch(x, y, {"pred_mask": sw})
+    loss_ref, W1, _ = T.train_step(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw), net=net)
+    assert abs(vals[0] - loss_ref.item()) < 2e-4 * abs(loss_ref.item())
+    got = _pull_weights(model)
+    worst = 0.0
+    for name, ws in W1.items():
+        for i, w in enumerate(ws):
+            w0 = W[name][i].double()
+            upd_ref = (w.double() - w0)
+            upd_got = (got[name][i].double() - w0)
+            # Adam's first step is +-lr per element wherever |g| >> eps: compare the updates themselves
+            denom = upd_ref.abs().max().clamp_min(1e-12)
+            err = ((upd_got - upd_ref).abs().max() / denom).item()
+            worst = max(worst, err)
+            assert err < 5e-2, (name, i, err)
+    # second step continues from the device-side Adam state and iteration counter
+    vals2 = model.train_on_batch(x, y, {"pred_mask": sw})
+    assert np.isfinite(vals2[0]) and vals2[0] < vals[0] * 1.5
+
+
+def test_gradients_fp32_match_oracle_autograd():
+    """raw gradients of every parameter tensor vs torch autograd through the oracle (fp64), before the optimizer."""
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import train as T
+    B, H, Wd = 2, 64, 64
+    sm = SegModel(image_size=(H, Wd), compute_dtype='float32')
+    model = sm.create_seg_model("original", n=21)
+    W = N.random_mobilenetv2_weights(seed=11, head="conv_upsample")
+    _push_weights(model, W)
+    e = model.engine
+    x, y, sw = _synthetic_batch(B, H, Wd, seed=4)
+    ws = e.workspace(B, True)
+    e.refresh_weight_copies()
+    ws["img"].copy_(torch.from_numpy(x))
+    ws["labels"].copy_(torch.from_numpy(y))
+    ws["sample_w"].copy_(torch.from_numpy(sw))
+    e.forward_train(ws, B, dropout=False)
+    e.loss_and_head_grad(ws, B, True)
+    e.backward(ws, B, dropout=False)
+    torch.cuda.synchronize()
+    loss, grads, _, _ = T.loss_and_grads(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw))
+    assert abs(ws["loss_sum"].item() / ws["wcount"].item() - loss.item()) < 1e-4 * abs(loss.item())
+    bad = []
+    for rec in e.layers:
+        for i, p in enumerate(rec.params):
+            if not p.trainable_kind:
+                continue
+            gref = grads[rec.name][i].reshape(p.shape)
+            err = rel(p.grad.cpu() / e.loss_scale, gref)
+            if err > 2e-3:
+                bad.append((rec.name, i, err))
+    assert not bad, bad[:10]
+
+
+def test_frozen_prefix_regime_and_keras_surface():
+    """the notebook's fine-tuning regime (ipynb:147-155): everything before concat_projection frozen."""
+    from deeplab_b200.model import Adam
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import train as T
+    B, H, Wd = 2, 64, 64
+    sm = SegModel(image_size=(H, Wd), compute_dtype='float32')
+    model = sm.create_seg_model("original", n=21)
+    model.dropout_in_training = False
+    W = N.random_mobilenetv2_weights(seed=2, head="conv_upsample")
+    _push_weights(model, W)
+    frozen = []
+    for layer in model.layers:
+        if layer.name == 'concat_projection':
+            break
+        layer.trainable = False
+        frozen.append(layer.name)
+    model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+    x, y, sw = _synthetic_batch(B, H, Wd, seed=9)
+    vals = model.train_on_batch(x, y, {"pred_mask": sw})
+    loss_ref, W1, _ = T.train_step(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw),
+                                   frozen=set(frozen))
+    assert abs(vals[0] - loss_ref.item()) < 2e-4 * abs(loss_ref.item())
+    got = _pull_weights(model)
+    for name, ws in W1.items():
+        for i, w in enumerate(ws):
+            if name in frozen:
+                assert torch.equal(got[name][i], W[name][i]), name      # bit-identical: untouched
+            else:
+                upd_ref = w.double() - W[name][i].double()
+                upd_got = got[name][i].double() - W[name][i].double()
+                assert ((upd_got - upd_ref).abs().max() / upd_ref.abs().max().clamp_min(1e-12)).item() < 5e-2, name
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_train_step_16bit_close_to_oracle(dtype):
+    """tensor-core path: loss within 2%, gradient direction of the big conv kernels within cos > 0.98."""
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import train as T
+    B, H, Wd = 2, 128, 128
+    sm = SegModel(image_size=(H, Wd), compute_dtype=dtype)
+    model = sm.create_seg_model("original", n=21)
+    W = N.random_mobilenetv2_weights(seed=13, head="conv_upsample")
+    _push_weights(model, W)
+    e = model.engine
+    x, y, sw = _synthetic_batch(B, H, Wd, seed=6)
+    ws = e.workspace(B, True)
+    e.refresh_weight_copies()
+    ws["img"].copy_(torch.from_numpy(x)); ws["labels"].copy_(torch.from_numpy(y)); ws["sample_w"].copy_(torch.from_numpy(sw))
+    e.forward_train(ws, B, dropout=False)
+    e.loss_and_head_grad(ws, B, True)
+    e.backward(ws, B, dropout=False)
+    torch.cuda.synchronize()
+    loss, grads, _, _ = T.loss_and_grads(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw),
+                                         dtype=torch.float32)
+    got = ws["loss_sum"].item() / ws["wcount"].item()
+    assert abs(got - loss.item()) < 2e-2 * abs(loss.item())
+    for name in ["conv_upsample", "concat_projection", "aspp0", "expanded_conv_16_project", "expanded_conv_13_expand",
+                 "expanded_conv_6_depthwise", "expanded_conv_3_expand", "Conv"]:
+        p = e._by_name[name].params[0]
+        g = (p.grad.double().cpu() / e.loss_scale).flatten()
+        r = grads[name][0].double().flatten()
+        cos = torch.dot(g, r) / (g.norm() * r.norm())
+        assert cos > (0.98 if dtype == "float16" else 0.90), (name, cos.item())
+
+
+def test_graph_replay_equals_eager_and_mious_match():
+    """CUDA-graph replay reproduces the eager step; mIoU on a held-out synthetic mask set equals the oracle's +-0.1%."""
+    from deeplab_b200.model import Adam
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import ref_ops as R
+    B, H, Wd = 2, 64, 64
+    x, y, sw = _synthetic_batch(B, H, Wd, seed=21)
+    outs = []
+    for use_graph in (False, True):
+        sm = SegModel(image_size=(H, Wd), compute_dtype='float32')
+        model = sm.create_seg_model("original", n=21)
+        model.dropout_in_training = False
+        _push_weights(model, N.random_mobilenetv2_weights(seed=5, head="conv_upsample"))
+        model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6))
+        e = model.engine
+        losses = []
+        for it in range(4):
+            ls, wc = e.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(sw).cuda(),
+                                  dropout=False, use_graph=use_graph)
+            losses.append(ls.item() / wc.item())
+        outs.append((losses, _pull_weights(model)["concat_projection"][0]))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-4)
+    assert rel(outs[1][1], outs[0][1]) < 1e-4
+    assert outs[0][0][-1] < outs[0][0][0]                  # it learns
+    # held-out mIoU: model prediction vs oracle prediction under the notebook's mIOU (ipynb:203-210)
+    W = _pull_weights(model)
+    xv, yv, _ = _synthetic_batch(4, H, Wd, seed=99)
+    p = model.predict(xv)
+    with torch.no_grad():
+        _, pref, _ = N.deeplabv3_forward({k: [t.float() for t in v] for k, v in W.items()}, torch.from_numpy(xv))
+    for b in range(4):
+        gt = yv[b, :, 0].astype(np.int64)
+        m1 = R.notebook_miou(gt, p[b].argmax(-1))
+        m2 = R.notebook_miou(gt, pref[b].argmax(-1).numpy())
+        assert abs(m1 - m2) <= 1e-3
