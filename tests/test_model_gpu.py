@@ -162,18 +162,24 @@ def test_train_step_fp32_matches_oracle(net):
     x, y, sw = _synthetic_batch(B, H, Wd)
     vals = model.train_on_batch(x, y, {"pred_mask": sw})
     loss_ref, W1, _ = T.train_step(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw), net=net)
+    _, grads, _, _ = T.loss_and_grads(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw), net=net)
     assert abs(vals[0] - loss_ref.item()) < 2e-4 * abs(loss_ref.item())
     got = _pull_weights(model)
-    worst = 0.0
     for name, ws in W1.items():
         for i, w in enumerate(ws):
             w0 = W[name][i].double()
             upd_ref = (w.double() - w0)
             upd_got = (got[name][i].double() - w0)
-            # Adam's first step is +-lr per element wherever |g| >> eps: compare the updates themselves
-            denom = upd_ref.abs().max().clamp_min(1e-12)
-            err = ((upd_got - upd_ref).abs().max() / denom).item()
-            worst = max(worst, err)
+            if name in grads and i in grads[name]:
+                # Adam's first step is lr * sign(g) wherever |g| >> eps, so an element whose gradient is ~0 may
+                # legitimately flip: compare where the oracle gradient is well away from zero
+                g = grads[name][i].reshape(upd_ref.shape).abs()
+                mask = g > 1e-2 * g.max()
+                assert mask.float().mean() > 0.2, (name, i)
+            else:
+                mask = torch.ones_like(upd_ref, dtype=torch.bool)     # BN moving statistics
+            denom = upd_ref[mask].abs().max().clamp_min(1e-12)
+            err = ((upd_got - upd_ref)[mask].abs().max() / denom).item()
             assert err < 5e-2, (name, i, err)
     # second step continues from the device-side Adam state and iteration counter
     vals2 = model.train_on_batch(x, y, {"pred_mask": sw})
@@ -247,7 +253,8 @@ def test_frozen_prefix_regime_and_keras_surface():
             else:
                 upd_ref = w.double() - W[name][i].double()
                 upd_got = got[name][i].double() - W[name][i].double()
-                assert ((upd_got - upd_ref).abs().max() / upd_ref.abs().max().clamp_min(1e-12)).item() < 5e-2, name
+                # mean error (sign flips of near-zero gradients under Adam's first step are legitimate outliers)
+                assert ((upd_got - upd_ref).abs().mean() / upd_ref.abs().mean().clamp_min(1e-12)).item() < 2e-2, name
 
 
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
