@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: images/sec fwd+bwd @512x512 MobileNetV2 (constructor OS=16 -> runs at OS 8).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun, NCCL)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement on the host cores
+
+Workload (configs[1]): MobileNetV2 DeepLabV3+ 'original' head (utils.py:188-193), batch 16 per GPU, fp16 storage /
+fp32 accumulate + fp32 master weights, synthetic 512x512x3 images, 21-class masks with void rings, temporal sample
+weights, BatchNorm batch statistics, Dropout(0.1), void-ignoring CE, Keras Adam -- one full optimizer step per
+"step".  Weak scaling: 16 images per GPU.
+
+JSON line (one, from rank 0): see the task contract; `value` = device-resident inputs (CUDA-graph replay),
+`e2e` = the same step through model.train_on_batch with pinned HOST inputs (H2D inside the timed region) and a D2H
+read of the loss; `roofline` = the dominant kernel family of the step, timed live with CUDA events around every
+C-ABI launch of an eager step; `cpu_baseline` = the oracle (torch-CPU restatement, all host threads) on a bounded
+sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+H = W = 512
+CLASSES = 21
+PER_GPU_BATCH = 16
+METRIC = "images/sec fwd+bwd @512x512 MobileNetV2 OS=16"
+
+
+def synthetic_batch(B, seed):
+    """X ~ U{0..255}; Y = random ellipses (labels 1..20) with a void (=21) ring; SW = per-image
+    balanced class weights like utils.py:389-399."""
+    rng = np.random.RandomState(seed)
+    x = rng.randint(0, 256, (B, H, W, 3)).astype(np.float32)
+    y = np.zeros((B, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        for _ in range(3):
+            cy, cx = rng.randint(0, H), rng.randint(0, W)
+            ry, rx = rng.randint(H // 8, H // 2), rng.randint(W // 8, W // 2)
+            d = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2
+            y[b][d < 1.0] = rng.randint(1, CLASSES)
+            y[b][(d >= 1.0) & (d < 1.1)] = CLASSES
+    sw = np.zeros((B, H * W), np.float32)
+    yf = y.reshape(B, -1)
+    for b in range(B):
+        cls, cnt = np.unique(yf[b], return_counts=True)
+        wts = yf[b].size / (len(cls) * cnt)
+        for c, wv in zip(cls, wts):
+            sw[b][yf[b] == c] = 0.0 if c == CLASSES else wv
+    return x, yf.reshape(B, H * W, 1), sw
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_train_sample(B, steps, warmup, seed=0):
+    """The oracle's training step (torch-CPU restatement + autograd + Keras Adam) on B images per step."""
+    from oracle import network as N
+    from oracle import train as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    Wt = N.random_mobilenetv2_weights(seed=seed, head="conv_upsample", perturb_bn=False)
+    x, y, sw = synthetic_batch(B, seed)
+    xt, yt, swt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw)
+    state, it, times = None, 0, []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, Wt, state = T.train_step(Wt, xt, yt, swt, net="original", iterations=it, adam_state=state, dtype=torch.float32)
+        it += 1
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 2
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 2))
+    # bound the run to a few minutes whatever K the driver passes
+    t_probe = cpu_train_sample(B, 1, 0)[0]
+    steps = max(1, min(steps, int(150.0 / max(t_probe, 1e-3))))
+    times = cpu_train_sample(B, steps, warmup)
+    ms = 1e3 * float(np.mean(times))
+    v = B / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, 512x512x3, 21 classes "
+                               "(configs[1]); CPU arm steps on a bounded sample of 2 images",
+                   "parallelism": "host threads"},
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                         "sample": f"{B} images/step x {steps} steps, torch-CPU fp32 restatement of the reference graph "
+                                   "(Keras/TF cannot be installed here), all host threads"},
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ roofline probe
+def profile_eager_step(engine, ws, B):
+    """One eager step with a CUDA-event pair around every C-ABI launch: per kernel-family time + algorithmic bytes."""
+    from deeplab_b200 import ops
+    recs = []
+    es = {torch.float16: 2, torch.bfloat16: 2, torch.float32: 4, torch.float64: 8, torch.uint8: 1, torch.int64: 8}
+
+    def nbytes(t):
+        return 0 if t is None else t.numel() * es[t.dtype]
+
+    def algo_bytes(name, a, k):
+        if name == "pw_gemm":
+            A, Bt, out = a[0], a[1], a[2]
+            M = A.numel() // A.shape[-1]
+            K = k.get("K") or A.shape[-1]
+            N = k.get("N") or Bt.shape[0]
+            b = M * K * es[A.dtype] + N * K * es[Bt.dtype] + M * (k.get("n_store") or N) * es[out.dtype]
+            if k.get("residual") is not None:
+                b += M * N * es[out.dtype]
+            return b
+        if name == "pw_wgrad":
+            A, dY, dW = a[0], a[1], a[2]
+            M = A.numel() // A.shape[-1]
+            return M * ((k.get("K") or A.shape[-1]) + (k.get("N") or dY.shape[-1])) * es[A.dtype] + nbytes(dW)
+        if name == "dw_conv_fwd":
+            return nbytes(a[0]) + nbytes(a[2])
+        if name == "dw_conv_bwd":
+            dy = a[1]
+            b = nbytes(dy)
+            if k.get("dx") is not None:
+                b += nbytes(k["dx"])
+            if k.get("dw") is not None and a[0] is not None:
+                b += nbytes(a[0]) + nbytes(dy)
+            return b
+        if name == "bn_act_apply":
+            return nbytes(a[0]) + nbytes(a[1]) + nbytes(k.get("res"))
+        if name == "bn_bwd":
+            return 2 * (nbytes(a[0]) + nbytes(a[1])) + nbytes(a[2])
+        if name == "stem_conv_fwd":
+            return nbytes(a[0]) + nbytes(a[2])
+        if name == "stem_conv_wgrad":
+            return nbytes(a[0]) + nbytes(a[1])
+        if name == "resize_softmax_ce":
+            return nbytes(a[4]) + nbytes(a[5]) + 2 * nbytes(a[0]) + nbytes(k.get("argmax") if k else None)
+        if name in ("global_avgpool_fwd",):
+            return nbytes(a[0])
+        if name in ("global_avgpool_bwd",):
+            return 2 * nbytes(a[1])
+        if name == "adam_step":
+            return 7 * nbytes(a[0])
+        if name == "cast":
+            return nbytes(a[0]) + nbytes(a[1])
+        return 0
+
+    names = ["pw_gemm", "pw_wgrad", "dw_conv_fwd", "dw_conv_bwd", "bn_act_apply", "bn_bwd", "stem_conv_fwd",
+             "stem_conv_wgrad", "resize_softmax_ce", "global_avgpool_fwd", "global_avgpool_bwd", "adam_step", "cast",
+             "bn_finalize", "cast_weight", "small_gemm", "ce_grad_scale", "fill_zero"]
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(n, f):
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = f(*a, **k)
+            e1.record()
+            recs.append((n, e0, e1, algo_bytes(n, a, k)))
+            return r
+        return g
+
+    try:
+        for n in names:
+            setattr(ops, n, wrap(n, orig[n]))
+        engine._fwd_bwd_body(ws, B, True, True)
+        engine._update_body()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    agg = {}
+    for n, e0, e1, b in recs:
+        d = agg.setdefault(n, [0.0, 0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += b
+        d[2] += 1
+    return agg
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="float16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import __graft_entry__ as ge
+    from deeplab_b200.parallel import init_process_group_from_env, make_data_parallel
+    rank, world = init_process_group_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if rank == 0:
+        ge.build_cuda()
+    if world > 1:
+        torch.distributed.barrier()
+
+    from deeplab_b200 import _lib
+    from deeplab_b200.model import Adam
+    from deeplab_b200.utils import SegModel
+    if not _lib.lib().dlb_device_ok():
+        raise SystemExit("bench.py needs an sm_100 device")
+
+    B = PER_GPU_BATCH
+    sm = SegModel(image_size=(H, W), compute_dtype=args.dtype)
+    model = sm.create_seg_model("original", n=CLASSES, seed=0)
+    model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+    make_data_parallel(model)
+    e = model.engine
+
+    x, y, sw = synthetic_batch(B, seed=rank)
+    # pinned host copies (e2e arm) and device-resident copies (device arm)
+    xp, yp, swp = (torch.from_numpy(a).pin_memory() for a in (x, y, sw))
+    xd, yd, swd = xp.cuda(), yp.cuda(), swp.cuda()
+    dev = torch.device("cuda", local)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        e.train_step(xd, yd, swd)
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            loss_sum, wcount = e.train_step(xd, yd, swd)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * B / (ms_step / 1e3)
+    final_loss = (loss_sum / wcount).item()
+    launches_per_step = e.graph_launches_per_step()
+
+    # ---- end-to-end arm: public API call with pinned host inputs, loss read back each step
+    for _ in range(3):
+        model.train_on_batch(xp, yp, {"pred_mask": swp})
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        vals = model.train_on_batch(xp, yp, {"pred_mask": swp})
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    e2e_value = world * B / (e2e_ms / 1e3)
+    h2d = xp.numel() * 4 + yp.numel() * 4 + swp.numel() * 4
+    d2h = 2 * 8 + B * (CLASSES + 1) * CLASSES * 8
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel family (live CUDA events around every launch of one eager step)
+    ws = e.workspace(B, True)
+    profile_eager_step(e, ws, B)       # warm
+    agg = profile_eager_step(e, ws, B)
+    tot_ms = sum(v[0] for v in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1][0])
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    name, (ms_k, bytes_k, n_k) = top
+    achieved = bytes_k / (ms_k * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(name)
+    roofline = {"bound": "hbm", "kernel": name, "launches_per_step": n_k, "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": ms_k / tot_ms,
+                "per_family_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+                "per_family_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[0] > 0 and v[1] > 0}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cb = 2
+        times = cpu_train_sample(cb, 2, 1)
+        cpu_baseline = {"value": cb / float(np.mean(times)), "unit": "img/s", "cores": os.cpu_count() or 1,
+                        "kind": "port", "sample": f"{cb} images/step x 2 steps (1 warm-up), oracle torch-CPU fp32 "
+                                                  "restatement of the reference training step, all host threads"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[args.dtype], "data": "synthetic",
+        "config": {"workload": "MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, bs 16/GPU, 512x512x3, 21 classes "
+                               "(BASELINE configs[1]); random-init weights",
+                   "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2": "no flush needed: per-step activation working set (~7 GB) >> 126 MB L2",
+                   "loss_after": final_loss},
+        "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clk.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

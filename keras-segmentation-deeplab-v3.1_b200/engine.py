@@ -406,7 +406,10 @@ class Engine:
         ws = self.workspace(B, False)
         if self._weights_dirty:
             self.refresh_weight_copies()
-        self._fold_all(ws)
+            self._fold_dirty = True
+        if getattr(self, "_fold_dirty", True) or getattr(self, "_fold_ws", None) is not ws:
+            self._fold_all(ws)
+            self._fold_dirty, self._fold_ws = False, ws
         geo = ws["geo"]
         T = ws["t"]
         dt = self.dtype
@@ -708,12 +711,12 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     # one optimizer step (graph-captured)
     # ------------------------------------------------------------------------------------------------
-    def _step_body(self, ws, B, dropout, use_sample_w):
+    def _fwd_bwd_body(self, ws, B, dropout, use_sample_w):
         self.forward_train(ws, B, dropout)
         self.loss_and_head_grad(ws, B, use_sample_w)
         self.backward(ws, B, dropout)
-        if self.grad_hook is not None:
-            self.grad_hook(self.grads)
+
+    def _update_body(self):
         c = self.adam_cfg
         self.grads.mul_(self.train_mask)       # frozen layers (trainable=False) receive no update
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.adam_step, lr=c["lr"], beta1=c["beta1"],
@@ -721,10 +724,30 @@ class Engine:
                       grad_mult=1.0 / (self.loss_scale * self.world_size))
         self.refresh_weight_copies()
 
+    def _capture(self, fn):
+        """warm-up on a side stream (first-use attribute calls, allocations), then capture into a CUDA graph.
+        The warm-up run performs the work once for real; the capture only records."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.n_launches = _lib.launch_count() - n0
+        return g
+
     def train_step(self, img: torch.Tensor, labels: torch.Tensor, sample_w: Optional[torch.Tensor] = None,
                    dropout: bool = True, use_graph: bool = True):
         """img [B,H,W,3] fp32, labels [B,H*W,1] fp32, sample_w [B,H*W] fp32 (device or pinned host tensors).
-        Returns the device scalars (loss_sum, wcount): loss = loss_sum / wcount (Keras weighted mean)."""
+        Returns the device scalars (loss_sum, wcount): loss = loss_sum / wcount (Keras weighted mean).
+
+        The step is two CUDA graphs -- (forward + loss + backward) and (Adam + weight re-cast) -- with the optional
+        gradient hook (the NCCL all-reduce of parallel.py) between them; a single graph when there is no hook."""
         B = img.shape[0]
         ws = self.workspace(B, True)
         if self._weights_dirty:
@@ -734,23 +757,37 @@ class Engine:
         use_sw = sample_w is not None
         if use_sw:
             ws["sample_w"].copy_(sample_w.view(B, -1), non_blocking=True)
+        self._fold_dirty = True
+        if not use_graph:
+            self._fwd_bwd_body(ws, B, dropout, use_sw)
+            if self.grad_hook is not None:
+                self.grad_hook(self.grads)
+            self._update_body()
+            return ws["loss_sum"], ws["wcount"]
         key = (B, dropout, use_sw)
-        if not use_graph or self.grad_hook is not None and not getattr(self, "hook_capturable", False):
-            self._step_body(ws, B, dropout, use_sw)
-        else:
-            g = self._graphs.get(key)
-            if g is None:
-                # warm-up run on a side stream (allocations, first-use attribute calls), then capture
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    self._step_body(ws, B, dropout, use_sw)
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_body(ws, B, dropout, use_sw)
-                self._graphs[key] = g
-                return ws["loss_sum"], ws["wcount"]      # the warm-up already performed this step
-            g.replay()
+        graphs = self._graphs.get(key)
+        if graphs is None:
+            if self.grad_hook is None:
+                def whole():
+                    self._fwd_bwd_body(ws, B, dropout, use_sw)
+                    self._update_body()
+                self._graphs[key] = (self._capture(whole), None)
+            else:
+                ga = self._capture(lambda: self._fwd_bwd_body(ws, B, dropout, use_sw))
+                self.grad_hook(self.grads)
+                gb = self._capture(self._update_body)
+                self._graphs[key] = (ga, gb)
+            return ws["loss_sum"], ws["wcount"]      # the warm-up runs already performed this step
+        ga, gb = graphs
+        ga.replay()
+        if gb is not None:
+            self.grad_hook(self.grads)
+            gb.replay()
         return ws["loss_sum"], ws["wcount"]
+
+    def graph_launches_per_step(self) -> int:
+        """number of libdeeplab_b200 kernel launches recorded in the captured step graph(s)."""
+        n = 0
+        for ga, gb in self._graphs.values():
+            n = max(n, ga.n_launches + (gb.n_launches if gb is not None else 0))
+        return n

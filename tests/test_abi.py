@@ -1,0 +1,79 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol the header
+declares; argument validation fails loudly without a GPU (no compute calls are made here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build_cuda()
+    import deeplab_b200  # noqa: F401
+    from deeplab_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "deeplab_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dlb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
+    assert L.dlb_version() == 1
+    assert L.dlb_launch_count() == 0
+
+
+def test_struct_sizes_match_header(lib):
+    """ctypes mirrors must have the C layout (pointer/int packing): compile a tiny C probe against the header."""
+    import subprocess
+    import tempfile
+    names = {"dlb_pw_gemm_params": lib.PwGemmParams, "dlb_pw_wgrad_params": lib.PwWgradParams,
+             "dlb_dw_conv_params": lib.DwConvParams, "dlb_dw_conv_bwd_params": lib.DwConvBwdParams,
+             "dlb_stem_conv_params": lib.StemConvParams, "dlb_bn_apply_params": lib.BnApplyParams,
+             "dlb_bn_bwd_params": lib.BnBwdParams, "dlb_softmax_ce_params": lib.SoftmaxCeParams,
+             "dlb_crf_config": lib.CrfConfig}
+    src = '#include <stdio.h>\n#include "deeplab_b200.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "p"), os.path.join(d, "p.c")])
+        out = subprocess.check_output([os.path.join(d, "p")], text=True)
+    for line in out.strip().splitlines():
+        n, sz = line.split()
+        assert C.sizeof(names[n]) == int(sz), (n, C.sizeof(names[n]), sz)
+
+
+def test_invalid_arguments_fail_loudly(lib):
+    L = lib.lib()
+    p = lib.PwGemmParams()
+    assert L.dlb_pw_gemm(C.byref(p), None) == -1
+    assert b"null pointer" in L.dlb_last_error()
+    cfg = lib.CrfConfig(0, 0, 0, 0, 0, 0, 0, 0, 0)
+    assert L.dlb_crf_workspace_bytes(C.byref(cfg)) == 0
+    assert L.dlb_device_ok() == 0          # no GPU in the build container
+
+
+def test_product_has_no_cpu_fallback(lib):
+    import torch
+    from deeplab_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = torch.zeros(128, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pw_gemm(a, a, a)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "keras-segmentation-deeplab-v3.1_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py") and fn != "selftest.py":
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
