@@ -102,11 +102,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def cpu_threads():
+    """torch intra-op threads for the CPU arm: all host cores up to 32 (beyond that the many small depthwise /
+    BatchNorm ops of this network get *slower* from oversubscription: 128 threads measured 60x slower than 8)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_train_sample(B, steps, warmup, seed=0):
     """The oracle's training step (torch-CPU restatement + autograd + Keras Adam) on B images per step."""
     from oracle import network as N
     from oracle import train as T
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     Wt = N.random_mobilenetv2_weights(seed=seed, head="conv_upsample", perturb_bn=False)
     x, y, sw = synthetic_batch(B, seed)
     xt, yt, swt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw)
@@ -132,7 +138,7 @@ def run_reference(args):
     times = cpu_train_sample(B, steps, warmup)
     ms = 1e3 * float(np.mean(times))
     v = B / (ms / 1e3)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -245,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-eager", action="store_true", help="run eager (un-captured) steps only; for ncu")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -287,6 +294,13 @@ def main():
         if world > 1:
             torch.distributed.barrier()
             torch.cuda.synchronize()
+
+    if args.profile_eager:
+        for _ in range(args.warmup + args.steps):
+            e.train_step(xd, yd, swd, use_graph=False)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_eager_steps": args.warmup + args.steps}))
+        return
 
     # ---- device-resident arm
     for _ in range(args.warmup):
@@ -354,11 +368,12 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cb = 2
-        times = cpu_train_sample(cb, 2, 1)
-        cpu_baseline = {"value": cb / float(np.mean(times)), "unit": "img/s", "cores": os.cpu_count() or 1,
-                        "kind": "port", "sample": f"{cb} images/step x 2 steps (1 warm-up), oracle torch-CPU fp32 "
-                                                  "restatement of the reference training step, all host threads"}
+        cb = 1
+        times = cpu_train_sample(cb, 1, 1)
+        cpu_baseline = {"value": cb / float(np.mean(times)), "unit": "img/s", "cores": cpu_threads(),
+                        "kind": "port", "sample": f"{cb} image/step x 1 step (1 warm-up), oracle torch-CPU fp32 "
+                                                  f"restatement of the reference training step, {cpu_threads()} of "
+                                                  f"{os.cpu_count()} host threads"}
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -224,6 +224,253 @@ __global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const DwBwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// shared-memory tiled depthwise kernels (the fast path).
+//   CTA = TH x TW output pixels x 64 channels.  The input tile (with halo) is staged once in shared memory with the
+//   consumer-side prologue (BN + activation of the producing layer) and the zero padding already applied, so every
+//   input element is read from HBM/L2 once per tile instead of 9 times, and transformed once instead of 9 times.
+//   A thread owns one 8-channel vector (its 72 filter taps live in registers) and 4 output pixels.
+//   flip = 1 turns the same kernel into the backward-data pass of a stride-1 SAME conv (correlation with the
+//   180-degree rotated filter on dy).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTH = 8, kTW = 16, kCV = 8;     // tile rows, cols, channel vectors (64 channels)
+
+struct DwTileArgs {
+  int B, H, W, C, Ho, Wo, stride, dil, pad_t, pad_l;
+  const void* x; void* y; const float* w;
+  const float* in_scale; const float* in_shift; int in_act;
+  const float* out_scale; const float* out_shift; int out_act;
+  double* stat_sum; double* stat_sqs;
+  const void* dy; float* dw;     // backward-weight mode
+  int flip;
+  int tiles_x, tiles_y, chunks, num_tiles, ih, iw;
+};
+
+template <typename T>
+__device__ __forceinline__ void dw_stage_input(const DwTileArgs& a, T* s_in, int b, int oy0, int ox0, int c0, bool cv_ok) {
+  // cooperative load of the (ih x iw) x 64-channel input tile, prologue + zero padding applied
+  const int tid = threadIdx.x, v = tid & 7;
+  const int cc = c0 + v * 8;
+  float isc[8], ish[8];
+  if (a.in_scale && cv_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { isc[i] = a.in_scale[cc + i]; ish[i] = a.in_shift[cc + i]; }
+  }
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
+  const int npos = a.ih * a.iw;
+  for (int p = tid >> 3; p < npos; p += 32) {
+    const int py = p / a.iw, px = p - py * a.iw;
+    const int gy = gy0 + py, gx = gx0 + px;
+    float vals[8];
+    if (cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+      Vec8<T>::ld(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc, vals);
+      if (a.in_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vals[i] = apply_act(fmaf(vals[i], isc[i], ish[i]), a.in_act);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+    }
+    Vec8<T>::st(s_in + (static_cast<size_t>(p) * kCV + v) * 8, vals);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) dw_fwd_tiled_kernel(const DwTileArgs a) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  T* s_in = reinterpret_cast<T*>(s_raw);
+  float* s_stats = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T));   // [2][64]
+  const int tid = threadIdx.x, v = tid & 7;
+  const bool stats = a.stat_sum != nullptr;
+  float wreg[9][8];
+  float ssum[8], ssqs[8];
+  int cur_chunk = -1;
+  T* y = reinterpret_cast<T*>(a.y);
+  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int chunk = tile / per_chunk;
+    int r = tile - chunk * per_chunk;
+    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
+    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (stats && cur_chunk >= 0) {
+        // flush the statistics of the finished channel chunk
+        __syncthreads();
+        if (tid < 128) s_stats[tid] = 0.f;
+        __syncthreads();
+        const int pc = cur_chunk * 64 + v * 8;
+        if (pc < a.C) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
+        }
+        __syncthreads();
+        if (tid < 64 && cur_chunk * 64 + tid < a.C) {
+          atomicAdd(&a.stat_sum[cur_chunk * 64 + tid], static_cast<double>(s_stats[tid]));
+          atomicAdd(&a.stat_sqs[cur_chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
+        }
+      }
+      cur_chunk = chunk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
+      if (cv_ok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int ts = a.flip ? 8 - t : t;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wreg[t][i] = a.w[ts * a.C + cc + i];
+        }
+      }
+    }
+    const int oy0 = ty * kTH, ox0 = tx * kTW;
+    __syncthreads();                       // previous tile's compute is done with s_in
+    dw_stage_input<T>(a, s_in, b, oy0, ox0, c0, cv_ok);
+    __syncthreads();
+    if (cv_ok) {
+      float osc[8], osh[8];
+      if (a.out_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { osc[i] = a.out_scale[cc + i]; osh[i] = a.out_shift[cc + i]; }
+      }
+#pragma unroll 1
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int p = (oy * a.stride + ky * a.dil) * a.iw + ox * a.stride + kx * a.dil;
+            float xv[8];
+            Vec8<T>::ld(s_in + (static_cast<size_t>(p) * kCV + v) * 8, xv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[i], wreg[ky * 3 + kx][i], acc[i]);
+          }
+        if (a.out_scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], osc[i], osh[i]), a.out_act);
+        }
+        if (stats) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float qv = Act<T>::rnd(acc[i]); ssum[i] += qv; ssqs[i] += qv * qv; }
+        }
+        Vec8<T>::st(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, acc);
+      }
+    }
+  }
+  if (stats && cur_chunk >= 0) {
+    __syncthreads();
+    if (tid < 128) s_stats[tid] = 0.f;
+    __syncthreads();
+    const int pc = cur_chunk * 64 + v * 8;
+    if (pc < a.C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
+    }
+    __syncthreads();
+    if (tid < 64 && cur_chunk * 64 + tid < a.C) {
+      atomicAdd(&a.stat_sum[cur_chunk * 64 + tid], static_cast<double>(s_stats[tid]));
+      atomicAdd(&a.stat_sqs[cur_chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
+    }
+  }
+}
+
+// backward-weight, tiled: dw[tap, c] += sum_pixels a[pix + tap] * dy[pix]; 72 accumulators per thread
+template <typename T>
+__global__ void __launch_bounds__(256, 2) dw_wgrad_tiled_kernel(const DwTileArgs a) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  T* s_in = reinterpret_cast<T*>(s_raw);
+  float* s_dw = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T));   // [9][64]
+  const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
+  float acc[9][8];
+  int cur_chunk = -1;
+  const T* dy = reinterpret_cast<const T*>(a.dy);
+  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
+
+  auto flush = [&](int chunk) {
+    // reduce over the 32 threads that share channel vector v: lanes v, v+8, v+16, v+24 of each of the 8 warps
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = acc[t][i];
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        acc[t][i] = x;
+      }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) s_dw[i] = 0.f;
+    __syncthreads();
+    if (lane < 8) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * 64 + v * 8 + i], acc[t][i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) {
+      const int t = i >> 6, c = chunk * 64 + (i & 63);
+      if (c < a.C) atomicAdd(&a.dw[t * a.C + c], s_dw[i]);
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int chunk = tile / per_chunk;
+    int r = tile - chunk * per_chunk;
+    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
+    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0) flush(cur_chunk);
+      cur_chunk = chunk;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    }
+    const int oy0 = ty * kTH, ox0 = tx * kTW;
+    __syncthreads();
+    dw_stage_input<T>(a, s_in, b, oy0, ox0, c0, cv_ok);
+    __syncthreads();
+    if (cv_ok) {
+#pragma unroll 1
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
+        float g[8];
+        Vec8<T>::ld(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, g);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int p = (oy * a.stride + ky * a.dil) * a.iw + ox * a.stride + kx * a.dil;
+            float xv[8];
+            Vec8<T>::ld(s_in + (static_cast<size_t>(p) * kCV + v) * 8, xv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[ky * 3 + kx][i] = fmaf(xv[i], g[i], acc[ky * 3 + kx][i]);
+          }
+      }
+    }
+  }
+  if (cur_chunk >= 0) flush(cur_chunk);
+}
+
+static void fill_tile_geometry(DwTileArgs& a) {
+  a.tiles_y = (a.Ho + kTH - 1) / kTH;
+  a.tiles_x = (a.Wo + kTW - 1) / kTW;
+  a.chunks = (a.C + 63) / 64;
+  a.num_tiles = a.chunks * a.B * a.tiles_y * a.tiles_x;
+  a.ih = (kTH - 1) * a.stride + 2 * a.dil + 1;
+  a.iw = (kTW - 1) * a.stride + 2 * a.dil + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // stem conv: 3x3 stride 2, Cin = 3, TF-SAME ((0,1) padding for even sizes), preprocessing fused
 // ---------------------------------------------------------------------------------------------
 struct StemArgs {
@@ -355,65 +602,96 @@ static int pick_grid(long long work_blocks, int per_sm) {
 
 using namespace dlb;
 
+template <typename T>
+static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
+  fill_tile_geometry(a);
+  const size_t smem = static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T) + 128 * sizeof(float);
+  DLB_REQUIRE(smem <= 200 * 1024, "dw_conv: dilation %d needs a %zu-byte tile (> 200 KB)", a.dil, smem);
+  if (smem > 48 * 1024)
+    DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  const int cap = num_sms() * per_sm;
+  const int grid = a.num_tiles < cap ? a.num_tiles : cap;
+  dw_fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+  g_launches++;
+  return check_launch("dw_fwd_tiled_kernel");
+}
+
+template <typename T>
+static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
+  fill_tile_geometry(a);
+  const size_t smem = static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T) + 9 * 64 * sizeof(float);
+  DLB_REQUIRE(smem <= 200 * 1024, "dw_conv_bwd: dilation %d needs a %zu-byte tile (> 200 KB)", a.dil, smem);
+  if (smem > 48 * 1024)
+    DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  const int cap = num_sms() * per_sm;
+  const int grid = a.num_tiles < cap ? a.num_tiles : cap;
+  dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+  g_launches++;
+  return check_launch("dw_wgrad_tiled_kernel");
+}
+
 extern "C" int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream) {
   DLB_REQUIRE(p && p->x && p->y && p->w, "dw_conv_fwd: null pointer");
-  DLB_REQUIRE(p->C % 8 == 0 && p->C / 8 <= 256, "dw_conv_fwd: C must be a multiple of 8 and <= 2048 (C=%d)", p->C);
+  DLB_REQUIRE(p->C % 8 == 0, "dw_conv_fwd: C must be a multiple of 8 (C=%d)", p->C);
   DLB_REQUIRE(p->stride == 1 || p->stride == 2, "dw_conv_fwd: stride %d", p->stride);
-  DwArgs a{};
+  DwTileArgs a{};
   a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
   a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
   a.x = p->x; a.y = p->y; a.w = p->w;
   a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
   a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
   a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
-  a.cv = p->C / 8; a.ppb = 256 / a.cv; a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
-  const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
-  const size_t smem = p->stat_sum ? 2 * p->C * sizeof(float) : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16) dw_fwd_kernel<__half><<<grid, 256, smem, st>>>(a);
-  else if (p->dtype == DLB_BF16) dw_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
-  else dw_fwd_kernel<float><<<grid, 256, smem, st>>>(a);
-  g_launches++;
-  return check_launch("dw_fwd_kernel");
+  if (p->dtype == DLB_F16) return launch_dw_tiled<__half>(a, st);
+  if (p->dtype == DLB_BF16) return launch_dw_tiled<__nv_bfloat16>(a, st);
+  return launch_dw_tiled<float>(a, st);
 }
 
 extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
   DLB_REQUIRE(p && p->dy && p->w, "dw_conv_bwd: null pointer");
-  DLB_REQUIRE(p->C % 8 == 0 && p->C / 8 <= 256, "dw_conv_bwd: C must be a multiple of 8 and <= 2048 (C=%d)", p->C);
-  DwBwdArgs a{};
-  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
-  a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
-  a.x = p->x; a.dy = p->dy; a.dx = p->dx; a.w = p->w; a.dw = p->dw;
-  a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
-  a.cv = p->C / 8; a.ppb = 256 / a.cv;
+  DLB_REQUIRE(p->C % 8 == 0, "dw_conv_bwd: C must be a multiple of 8 (C=%d)", p->C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dx) {
-    a.npix = static_cast<long long>(p->B) * p->H * p->W;
-    const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
-    if (p->dtype == DLB_F16) dw_bwd_data_kernel<__half><<<grid, 256, 0, st>>>(a);
-    else if (p->dtype == DLB_BF16) dw_bwd_data_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
-    else dw_bwd_data_kernel<float><<<grid, 256, 0, st>>>(a);
-    g_launches++;
-    int rc = check_launch("dw_bwd_data_kernel");
-    if (rc) return rc;
+    if (p->stride == 1) {
+      // backward-data of a stride-1 conv = correlation of dy with the rotated filter, padding 2*d - pad
+      DwTileArgs a{};
+      a.B = p->B; a.H = p->Ho; a.W = p->Wo; a.C = p->C; a.Ho = p->H; a.Wo = p->W;
+      a.stride = 1; a.dil = p->dilation; a.pad_t = 2 * p->dilation - p->pad_top; a.pad_l = 2 * p->dilation - p->pad_left;
+      a.x = p->dy; a.y = p->dx; a.w = p->w; a.flip = 1;
+      int rc;
+      if (p->dtype == DLB_F16) rc = launch_dw_tiled<__half>(a, st);
+      else if (p->dtype == DLB_BF16) rc = launch_dw_tiled<__nv_bfloat16>(a, st);
+      else rc = launch_dw_tiled<float>(a, st);
+      if (rc) return rc;
+    } else {
+      DLB_REQUIRE(p->C / 8 <= 256, "dw_conv_bwd: C <= 2048 for the strided backward-data kernel");
+      DwBwdArgs a{};
+      a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+      a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
+      a.x = p->x; a.dy = p->dy; a.dx = p->dx; a.w = p->w; a.dw = p->dw;
+      a.cv = p->C / 8; a.ppb = 256 / a.cv;
+      a.npix = static_cast<long long>(p->B) * p->H * p->W;
+      const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
+      if (p->dtype == DLB_F16) dw_bwd_data_kernel<__half><<<grid, 256, 0, st>>>(a);
+      else if (p->dtype == DLB_BF16) dw_bwd_data_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+      else dw_bwd_data_kernel<float><<<grid, 256, 0, st>>>(a);
+      g_launches++;
+      int rc = check_launch("dw_bwd_data_kernel");
+      if (rc) return rc;
+    }
   }
   if (p->dw) {
     DLB_REQUIRE(p->x, "dw_conv_bwd: x required for the weight gradient");
-    a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
-    const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 2);
-    const size_t smem = 9 * p->C * sizeof(float);
-#define L(TT)                                                                                                  \
-  do {                                                                                                         \
-    if (smem > 48 * 1024)                                                                                      \
-      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_weight_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dw_bwd_weight_kernel<TT><<<grid, 256, smem, st>>>(a);                                                      \
-  } while (0)
-    if (p->dtype == DLB_F16) L(__half);
-    else if (p->dtype == DLB_BF16) L(__nv_bfloat16);
-    else L(float);
-#undef L
-    g_launches++;
-    return check_launch("dw_bwd_weight_kernel");
+    DwTileArgs a{};
+    a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+    a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
+    a.x = p->x; a.dy = p->dy; a.dw = p->dw;
+    a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
+    if (p->dtype == DLB_F16) return launch_dw_wgrad_tiled<__half>(a, st);
+    if (p->dtype == DLB_BF16) return launch_dw_wgrad_tiled<__nv_bfloat16>(a, st);
+    return launch_dw_wgrad_tiled<float>(a, st);
   }
   return DLB_OK;
 }

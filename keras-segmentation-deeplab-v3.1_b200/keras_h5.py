@@ -279,10 +279,10 @@ class _Writer:
     def _dataspace(dims) -> bytes:
         return struct.pack("<BBB5x", 1, len(dims), 0) + b"".join(struct.pack("<Q", d) for d in dims)
 
-    def _attr_strings(self, name: str, values: List[bytes]) -> bytes:
+    def _attr_strings(self, name: str, values: List[bytes], scalar: bool = False) -> bytes:
         sz = max([len(v) for v in values] + [1])
         nm = name.encode() + b"\0"
-        dt, ds = self._dt_string(sz), self._dataspace([len(values)])
+        dt, ds = self._dt_string(sz), self._dataspace([] if scalar else [len(values)])
         pad8 = lambda b: b + b"\0" * ((-len(b)) % 8)
         body = struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(ds)) + pad8(nm) + pad8(dt) + pad8(ds)
         body += b"".join(v.ljust(sz, b"\0") for v in values)
@@ -377,7 +377,8 @@ def save_keras_weights(path: str, layers: "OrderedDict[str, list]", backend: byt
                 [w._attr_strings("weight_names", [])]
         top[lname] = w.group(ent, attrs)[0]
     root_attrs = [w._attr_strings("layer_names", [n.encode() for n in layers]),
-                  w._attr_strings("backend", [backend]), w._attr_strings("keras_version", [keras_version])]
+                  w._attr_strings("backend", [backend], scalar=True),
+                  w._attr_strings("keras_version", [keras_version], scalar=True)]
     root_hdr, root_tree, root_heap = w.group(top, root_attrs)
     with open(path, "wb") as f:
         f.write(w.finish(root_hdr, root_tree, root_heap))

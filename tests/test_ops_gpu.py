@@ -134,6 +134,32 @@ def test_pw_wgrad(M, K, N, dtype):
     assert rel_err(dW, 2 * ref) < 1e-4
 
 
+MNV2_KN = [(16, 96), (96, 24), (24, 144), (144, 24), (144, 32), (32, 192), (192, 32), (192, 64), (64, 384), (384, 64),
+           (384, 96), (96, 576), (576, 96), (576, 160), (160, 960), (960, 160), (960, 320), (320, 256), (256, 256),
+           (256, 24), (256, 1344), (32, 16)]
+
+
+@pytest.mark.parametrize("K,N", MNV2_KN)
+def test_all_mobilenet_layer_shapes_fwd_dgrad_wgrad(K, N):
+    """every (Cin, Cout) pair of the network through the three tensor-core GEMM roles, fp16, ragged M."""
+    ops = _ops()
+    M = 128 * 21 + 64
+    g = torch.Generator(device="cuda").manual_seed(K * 1000 + N)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    Wm = (torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K)).half()      # [K, N] Keras layout
+    dY = torch.randn(M, N, device="cuda", generator=g).half()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ops.pw_gemm(A, Wm.t().contiguous(), out)                                        # forward: Bt = W^T [N, K]
+    assert rel_err(out, A.float() @ Wm.float()) < 4e-3
+    dA = torch.empty(M, K, device="cuda", dtype=torch.float16)
+    ops.pw_gemm(dY, Wm, dA)                                                         # dgrad: Bt = W [K, N]
+    assert rel_err(dA, dY.float() @ Wm.float().t()) < 4e-3
+    dW = torch.empty(K, N, device="cuda")
+    ws = torch.empty(ops.pw_wgrad_workspace_bytes(M, N, K) // 4, device="cuda")
+    ops.pw_wgrad(A, dY, dW, workspace=ws)
+    assert rel_err(dW, A.float().t() @ dY.float()) < 1e-4
+
+
 def _dw_ref(x, w, stride, dil, in_scale=None, in_shift=None, in_act=0):
     """NHWC fp32 reference with TF-SAME padding (oracle/ref_ops.py has the CPU twin)."""
     a = x.float()

@@ -1,0 +1,158 @@
+"""CPU tests that pin the ORACLE itself: against the committed golden vectors derived from the reference's own
+artefacts (weights/*.h5, examples/*.JPG) and against closed-form / brute-force properties.  No GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_weight_file_known_answers():
+    """SURVEY 8c KAT (1): 165 layers, 272 datasets, 2 146 645 floats, head (1,1,256,21)+(21,), Keras 2.2.4/TF."""
+    from oracle.hdf5_reader import load_keras_weights
+    layers, attrs = load_keras_weights(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    assert len(layers) == 165
+    assert sum(len(v) for v in layers.values()) == 272
+    assert sum(a.size for v in layers.values() for _, a in v) == 2146645
+    assert attrs["backend"] == b"tensorflow" and attrs["keras_version"] == b"2.2.4"
+    names = list(layers)
+    assert names[2:4] == ["Conv", "Conv_BN"] and names[-1] == "pred_mask" and names[-4] == "conv_upsample"
+    k, b = layers["conv_upsample"]
+    assert k[1].shape == (1, 1, 256, 21) and b[1].shape == (21,)
+    assert layers["expanded_conv_depthwise"][0][1].shape == (3, 3, 32, 1)
+    d = np.load(os.path.join(GOLD, "subpixel_delta.npz"))
+    assert d["subpixel_1::0"].shape == (1, 1, 256, 1344) and d["subpixel_1::1"].shape == (1344,)
+
+
+def test_oracle_reproduces_golden_logits():
+    """The restatement, re-run here, reproduces the committed outputs (guards oracle drift)."""
+    from oracle import network as N
+    g = np.load(os.path.join(GOLD, "golden_mnv2.npz"))
+    W = N.weights_from_h5(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    x = torch.from_numpy(np.random.RandomState(0).randint(0, 256, (1, 512, 512, 3)).astype(np.float32))
+    with torch.no_grad():
+        logits, probs, _ = N.deeplabv3_forward(W, x)
+    assert np.abs(logits.numpy() - g["logits"]).max() < 1e-4 * np.abs(g["logits"]).max()
+    assert (probs.argmax(-1).numpy().reshape(512, 512) == g["argmax"]).mean() > 0.9999
+
+
+def test_fp64_vs_fp32_self_consistency():
+    from oracle import network as N
+    W = N.random_mobilenetv2_weights(seed=0)
+    x = torch.from_numpy(np.random.RandomState(1).randint(0, 256, (1, 96, 96, 3)).astype(np.float32))
+    with torch.no_grad():
+        l32, _, _ = N.deeplabv3_forward(W, x)
+        W64 = {k: [t.double() for t in v] for k, v in W.items()}
+        l64, _, _ = N.deeplabv3_forward(W64, x.double())
+    assert (l32.double() - l64).abs().max() < 1e-4 * l64.abs().max()
+
+
+def test_phase_shift_closed_form_vs_literal_and_not_depth_to_space():
+    from oracle import ref_ops as R
+    x = torch.arange(2 * 3 * 5 * 7 * 16, dtype=torch.float32).reshape(2, 3, 5, 7 * 16)
+    a, b = R.phase_shift_literal(x, 4), R.phase_shift(x, 4)
+    assert torch.equal(a, b)
+    # out[n, a*r+j, b*r+i, k] = in[n, a, b, k*r*r + i*r + j]
+    assert a[1, 2 * 4 + 3, 4 * 4 + 1, 5] == x[1, 2, 4, 5 * 16 + 1 * 4 + 3]
+    ps = torch.pixel_shuffle(x.permute(0, 3, 1, 2), 4).permute(0, 2, 3, 1)
+    assert not torch.equal(a, ps)
+    perm = R.subpixel_column_perm(7, 4)
+    assert sorted(perm.tolist()) == list(range(7 * 16))
+    # permuted columns -> contiguous (i, k) runs per (row, jj)
+    y = x[..., perm].reshape(2, 3, 5, 4, 4 * 7).permute(0, 1, 3, 2, 4).reshape(2, 12, 20, 7)
+    assert torch.equal(y, a)
+
+
+def test_tf_same_padding_and_legacy_bilinear():
+    from oracle import ref_ops as R
+    assert R.tf_same_pad(512, 3, 2, 1) == (256, 0, 1)        # stride-2 even input: extra pixel AFTER
+    assert R.tf_same_pad(513, 3, 2, 1) == (257, 1, 1)
+    assert R.tf_same_pad(64, 3, 1, 4) == (64, 4, 4)
+    assert R.tf_same_pad(64, 3, 1, 36) == (64, 36, 36)
+    x = torch.arange(4.0).reshape(1, 1, 4, 1)
+    up = R.resize_bilinear_tf1(x, 1, 32)[0, 0, :, 0]
+    # src = dst/8: weights k/8, last 7 outputs clamp to the edge value
+    assert torch.allclose(up[:9], torch.arange(9.0) / 8)
+    assert torch.all(up[24:] == 3.0)
+    # differs from the half-pixel-centre resize torch implements
+    tr = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(1, 32), mode="bilinear", align_corners=False)
+    assert not torch.allclose(tr[0, 0, 0], up)
+
+
+def test_loss_and_metrics_definitions():
+    from oracle import ref_ops as R
+    y = torch.tensor([[[0.], [1.], [2.], [3.]]])                 # 3 == void for 3 classes
+    p = torch.tensor([[[.7, .2, .1], [.1, .8, .1], [.3, .3, .4], [.2, .5, .3]]])
+    l = R.sparse_crossentropy_ignoring_last_label(y, p)
+    assert torch.allclose(l[0], torch.tensor([-np.log(.7), -np.log(.8), -np.log(.4), 0.0]).float(), atol=1e-6)
+    sw = torch.tensor([[1., 0., 2., 1.]])
+    tot = R.keras_weighted_loss(y, p, sw)
+    assert abs(tot.item() - ((-np.log(.7) - 2 * np.log(.4)) / 4 / 0.75)) < 1e-6
+    assert abs(R.sparse_accuracy_ignoring_last_label(y, p).item() - 1.0) < 1e-6
+    # the void pixel is predicted as class 1 and counts in that class's union (utils.py:146-147): (1 + 1/2 + 1) / 3
+    assert abs(R.jaccard(y, p).item() - 2.5 / 3) < 1e-6
+    assert abs(R.notebook_miou(np.array([0, 0, 1, 1]), np.array([0, 1, 1, 1])) - (0.5 + 2 / 3) / 2) < 1e-9
+
+
+def test_keras_adam_first_steps():
+    from oracle import ref_ops as R
+    p, m, v = torch.ones(3), torch.zeros(3), torch.zeros(3)
+    g = torch.tensor([1.0, -2.0, 0.5])
+    p1, m, v = R.keras_adam(p, g, m, v, 0, lr=0.1, eps=1e-8, decay=0.0)
+    assert torch.allclose(p1, torch.tensor([0.9, 1.1, 0.9]), atol=1e-6)      # first step = lr * sign(g)
+    p2, _, _ = R.keras_adam(p1, g, m, v, 1, lr=0.1, eps=1e-8, decay=0.5)
+    assert torch.allclose(p1 - p2, torch.tensor([1., -1., 1.]) * 0.1 / 1.5, atol=1e-6)
+
+
+def test_permutohedral_oracle_properties():
+    """barycentric weights >= 0 and sum to 1; K1 gain 0.882 of the exact Gaussian mass in the
+    interior (d=2); normalised filter within ~1e-2 of the exact normalised Gaussian."""
+    from oracle import crf
+    H = W = 40
+    ys, xs = np.mgrid[0:H, 0:W]
+    f = np.stack([xs / 3.0, ys / 3.0], -1).reshape(-1, 2).astype(np.float32)
+    v = np.random.RandomState(0).rand(H * W, 2).astype(np.float32)
+    out, M, off, bary = crf.lattice_filter(f, np.concatenate([v, np.ones((H * W, 1), np.float32)], 1))
+    assert bary.min() > -1e-6 and np.abs(bary.sum(1) - 1).max() < 1e-5
+    assert off.min() >= 0 and off.max() < M
+    d2 = ((f[:, None, :] - f[None, :, :]) ** 2).sum(-1)
+    K = np.exp(-0.5 * d2)
+    ratio = (out[:, 2] / K.sum(1)).reshape(H, W)[12:-12, 12:-12]
+    assert abs(ratio.mean() - 0.882) < 0.01 and ratio.std() < 0.01
+    assert np.abs(out[:, :2] / out[:, 2:3] - (K @ v) / K.sum(1, keepdims=True)).max() < 2e-2
+    # d = 5 weights are a partition of unity too
+    f5 = np.random.RandomState(1).rand(500, 5).astype(np.float32) * 10
+    _, _, _, b5 = crf.lattice_filter(f5, np.ones((500, 1), np.float32))
+    assert b5.min() > -1e-5 and np.abs(b5.sum(1) - 1).max() < 1e-5
+
+
+def test_crf_oracle_semantics():
+    from oracle import crf
+    # one label: Q == 1 ; uniform image + uniform unary: Q stays uniform
+    img = np.full((16, 16, 3), 128, np.uint8)
+    Q = crf.dense_crf(np.zeros((3, 256), np.float32), img, iters=3)
+    assert np.abs(Q - 1 / 3).max() < 1e-5
+    U = crf.unary_from_labels(np.array([0, 1, 2, 1]), 3, 0.7, zero_unsure=False)
+    assert abs(U[0, 0] + np.log(0.7)) < 1e-6 and abs(U[1, 0] + np.log(0.15)) < 1e-6
+    Uz = crf.unary_from_labels(np.array([0, 1, 2, 1]), 3, 0.7, zero_unsure=True)
+    assert np.allclose(Uz[:, 0], -np.log(1 / 3)) and abs(Uz[0, 1] + np.log(0.7)) < 1e-6   # label 1 -> row 0
+    # smoothing: an isolated wrong pixel inside a uniform region gets corrected
+    mask = np.zeros((24, 24), np.int32)
+    mask[:, 12:] = 1
+    mask[5, 3] = 1
+    img2 = np.zeros((24, 24, 3), np.uint8)
+    img2[:, 12:] = 255                                   # colour edge coincides with the label edge
+    out = crf.do_crf(img2, mask, zero_unsure=False)
+    assert out[5, 3] == 0 and out[5, 20] == 1 and (out[:, 12:] == 1).all()
+
+
+def test_icnr_matches_reference_sequence():
+    from oracle import ref_ops as R
+    sub = torch.randn(1, 1, 8, 3)
+    w = R.icnr(sub, 4)
+    assert w.shape == (1, 1, 8, 48)
+    # every group of scale^2 consecutive-by-C' channels repeats the sub-kernel: w[..., (i*s+j)*C' + k] == sub[..., k]
+    for q in range(16):
+        assert torch.equal(w[0, 0, :, q * 3:(q + 1) * 3], sub[0, 0])
