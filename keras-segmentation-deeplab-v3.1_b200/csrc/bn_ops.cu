@@ -57,33 +57,49 @@ struct ApplyArgs {
   const float* scale; const float* shift; int act; float drop_rate; uint64_t seed; const long long* seed_dev;
 };
 
+// thread = fixed 8-channel vector (scale/shift in registers), rows strided over the grid, 4 rows in flight
 template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(const ApplyArgs a) {
   const T* x = reinterpret_cast<const T*>(a.x);
   const T* res = reinterpret_cast<const T*>(a.res);
   T* y = reinterpret_cast<T*>(a.y);
+  const int cv = a.C >> 3;
+  const int rpb = 256 / cv;
+  if (static_cast<int>(threadIdx.x) >= rpb * cv) return;
+  const int r_in = threadIdx.x / cv;
+  const int c0 = (threadIdx.x - r_in * cv) * 8;
+  const long long M = a.nvec / cv;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = a.scale ? a.scale[c0 + k] : 1.f; sh[k] = a.scale ? a.shift[c0 + k] : 0.f; }
   const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
   const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long e0 = i * 8;
-    const int c0 = static_cast<int>(e0 % a.C);
-    float v[8];
-    Vec8<T>::ld(x + e0, v);
+  const long long rstride = static_cast<long long>(gridDim.x) * rpb;
+  constexpr int U = 4;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * rpb + r_in; r0 < M; r0 += rstride * U) {
+    float v[U][8], rr[U][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float z = a.scale ? fmaf(v[k], a.scale[c0 + k], a.shift[c0 + k]) : v[k];
-      z = apply_act(z, a.act);
-      if (a.drop_rate > 0.f) z = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? z * keep_inv : 0.f;
-      v[k] = z;
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r < M) {
+        Vec8<T>::ld(x + r * a.C + c0, v[u]);
+        if (res) Vec8<T>::ld(res + r * a.C + c0, rr[u]);
+      }
     }
-    if (res) {
-      float r[8];
-      Vec8<T>::ld(res + e0, r);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r >= M) continue;
+      const long long e0 = r * a.C + c0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = apply_act(fmaf(v[u][k], sc[k], sh[k]), a.act);
+        if (a.drop_rate > 0.f) z = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? z * keep_inv : 0.f;
+        if (res) z += rr[u][k];
+        v[u][k] = z;
+      }
+      Vec8<T>::st(y + e0, v[u]);
     }
-    Vec8<T>::st(y + e0, v);
   }
 }
 
@@ -95,7 +111,7 @@ struct BwdArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float s_red[];   // [2*C]
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
@@ -111,19 +127,28 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
     const T* da = reinterpret_cast<const T*>(a.da);
     const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
     const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
-    for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
-         r += static_cast<long long>(gridDim.x) * a.rpb) {
-      const long long e0 = r * a.C + c0;
-      float xv[8], gv[8];
-      Vec8<T>::ld(x + e0, xv);
-      Vec8<T>::ld(da + e0, gv);
+    const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
+    constexpr int U = 4;
+    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+      float xv[U][8], gv[U][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z = fmaf(xv[k], sc[k], sh[k]);
-        float dz = gv[k] * act_mask(z, a.act);
-        if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
-        s1[k] += dz;
-        s2[k] += dz * (xv[k] - mu[k]) * rs[k];
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * rstride;
+        if (r < a.M) { Vec8<T>::ld(x + r * a.C + c0, xv[u]); Vec8<T>::ld(da + r * a.C + c0, gv[u]); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * rstride;
+        if (r >= a.M) continue;
+        const long long e0 = r * a.C + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(xv[u][k], sc[k], sh[k]);
+          float dz = gv[u][k] * act_mask(z, a.act);
+          if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+          s1[k] += dz;
+          s2[k] += dz * (xv[u][k] - mu[k]) * rs[k];
+        }
       }
     }
 #pragma unroll
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
   const int tid = threadIdx.x;
   if (blockIdx.x == 0) {
     for (int c = tid; c < a.C; c += blockDim.x) {
@@ -159,21 +184,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   T* dx = reinterpret_cast<T*>(a.dx);
   const float keep_inv = a.drop_rate > 0.f ? 1.f / (1.f - a.drop_rate) : 1.f;
   const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
-  for (long long r = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r < a.M;
-       r += static_cast<long long>(gridDim.x) * a.rpb) {
-    const long long e0 = r * a.C + c0;
-    float xv[8], gv[8], o[8];
-    Vec8<T>::ld(x + e0, xv);
-    Vec8<T>::ld(da + e0, gv);
+  const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
+  constexpr int U = 4;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+    float xv[U][8], gv[U][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float z = fmaf(xv[k], sc[k], sh[k]);
-      float dz = gv[k] * act_mask(z, a.act);
-      if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
-      const float xhat = (xv[k] - mu[k]) * rs[k];
-      o[k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r < a.M) { Vec8<T>::ld(x + r * a.C + c0, xv[u]); Vec8<T>::ld(da + r * a.C + c0, gv[u]); }
     }
-    Vec8<T>::st(dx + e0, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r >= a.M) continue;
+      const long long e0 = r * a.C + c0;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(xv[u][k], sc[k], sh[k]);
+        float dz = gv[u][k] * act_mask(z, a.act);
+        if (a.drop_rate > 0.f) dz = hash_uniform(seed, static_cast<uint64_t>(e0 + k)) >= a.drop_rate ? dz * keep_inv : 0.f;
+        const float xhat = (xv[u][k] - mu[k]) * rs[k];
+        o[k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
+      }
+      Vec8<T>::st(dx + e0, o);
+    }
   }
 }
 
@@ -280,9 +315,13 @@ extern "C" int dlb_bn_fold(int C, const float* gamma, const float* beta, const f
 extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   DLB_REQUIRE(p && p->x && p->y, "bn_act_apply: null pointer");
   DLB_REQUIRE(p->C % 8 == 0, "bn_act_apply: C must be a multiple of 8 (C=%d)", p->C);
+  DLB_REQUIRE(p->C / 8 <= 256, "bn_act_apply: C <= 2048");
   ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed,
               reinterpret_cast<const long long*>(p->drop_seed_dev)};
-  const int grid = grid_for(a.nvec, 256, 8);
+  const int rpb_ = 256 / (p->C / 8);
+  long long blocks_ = (p->M + static_cast<long long>(rpb_) * 4 - 1) / (static_cast<long long>(rpb_) * 4);
+  const long long cap_ = static_cast<long long>(num_sms()) * 8;
+  const int grid = static_cast<int>(blocks_ < cap_ ? (blocks_ > 0 ? blocks_ : 1) : cap_);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16) bn_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
@@ -306,9 +345,9 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   BwdArgs a{};
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
-  long long blocks = (a.M + a.rpb - 1) / a.rpb;
-  long long cap = static_cast<long long>(num_sms()) * 4;
-  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  long long blocks = (a.M + a.rpb * 4LL - 1) / (a.rpb * 4LL);
+  long long cap = static_cast<long long>(num_sms()) * 6;
+  const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   const size_t smem = 2 * p->C * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
@@ -323,9 +362,9 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
   DLB_REQUIRE(p->dx, "bn_bwd_apply: dx is null");
-  long long blocks = (a.M + a.rpb - 1) / a.rpb;
-  long long cap = static_cast<long long>(num_sms()) * 8;
-  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  long long blocks = (a.M + a.rpb * 4LL - 1) / (a.rpb * 4LL);
+  long long cap = static_cast<long long>(num_sms()) * 6;
+  const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);

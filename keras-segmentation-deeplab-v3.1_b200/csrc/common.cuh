@@ -100,6 +100,28 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+// raw (unconverted) 8-element vectors: keep many loads in flight at 4 registers each, convert at use
+template <typename T> struct Raw8 { uint4 q; };
+template <> struct Raw8<float> { uint4 q, r; };
+template <typename T> __device__ __forceinline__ void raw_ld(const T* p, Raw8<T>& o) { o.q = *reinterpret_cast<const uint4*>(p); }
+template <> __device__ __forceinline__ void raw_ld<float>(const float* p, Raw8<float>& o) {
+  o.q = *reinterpret_cast<const uint4*>(p); o.r = *reinterpret_cast<const uint4*>(p + 4);
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<__half>& r, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = __uint_as_float(r.q.x); v[1] = __uint_as_float(r.q.y); v[2] = __uint_as_float(r.q.z); v[3] = __uint_as_float(r.q.w);
+  v[4] = __uint_as_float(r.r.x); v[5] = __uint_as_float(r.r.y); v[6] = __uint_as_float(r.r.z); v[7] = __uint_as_float(r.r.w);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == DLB_ACT_RELU) return fmaxf(v, 0.f);
   if (act == DLB_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);

@@ -258,21 +258,36 @@ __device__ __forceinline__ void dw_stage_input(const DwTileArgs& a, T* s_in, int
   const T* x = reinterpret_cast<const T*>(a.x);
   const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
   const int npos = a.ih * a.iw;
-  for (int p = tid >> 3; p < npos; p += 32) {
-    const int py = p / a.iw, px = p - py * a.iw;
-    const int gy = gy0 + py, gx = gx0 + px;
-    float vals[8];
-    if (cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-      Vec8<T>::ld(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc, vals);
-      if (a.in_scale) {
+  // 4 positions per thread in flight (loads first, then transform + st.shared): the staging is latency bound otherwise
+  constexpr int U = 4;
+  for (int p0 = tid >> 3; p0 < npos; p0 += 32 * U) {
+    Raw8<T> raw[U];
+    bool inb[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) vals[i] = apply_act(fmaf(vals[i], isc[i], ish[i]), a.in_act);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + 32 * u;
+      const int py = p / a.iw, px = p - py * a.iw;
+      const int gy = gy0 + py, gx = gx0 + px;
+      inb[u] = p < npos && cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      if (inb[u]) raw_ld<T>(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc, raw[u]);
     }
-    Vec8<T>::st(s_in + (static_cast<size_t>(p) * kCV + v) * 8, vals);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + 32 * u;
+      if (p >= npos) continue;
+      float vals[8];
+      if (inb[u]) {
+        raw_unpack(raw[u], vals);
+        if (a.in_scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vals[i] = apply_act(fmaf(vals[i], isc[i], ish[i]), a.in_act);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+      }
+      Vec8<T>::st(s_in + (static_cast<size_t>(p) * kCV + v) * 8, vals);
+    }
   }
 }
 
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_kernel(const DwTileArgs a
 
 // backward-weight, tiled: dw[tap, c] += sum_pixels a[pix + tap] * dy[pix]; 72 accumulators per thread
 template <typename T>
-__global__ void __launch_bounds__(256, 2) dw_wgrad_tiled_kernel(const DwTileArgs a) {
+__global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs a) {
   extern __shared__ __align__(16) uint8_t s_raw[];
   T* s_in = reinterpret_cast<T*>(s_raw);
   float* s_dw = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T));   // [9][64]
@@ -438,13 +453,21 @@ __global__ void __launch_bounds__(256, 2) dw_wgrad_tiled_kernel(const DwTileArgs
     dw_stage_input<T>(a, s_in, b, oy0, ox0, c0, cv_ok);
     __syncthreads();
     if (cv_ok) {
-#pragma unroll 1
+      Raw8<T> gall[(kTH * kTW) / 32];
+#pragma unroll
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        if (oy0 + oy < a.Ho && ox0 + ox < a.Wo)
+          raw_ld<T>(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, gall[j]);
+      }
+#pragma unroll
       for (int j = 0; j < (kTH * kTW) / 32; ++j) {
         const int q = (tid >> 3) + 32 * j;
         const int oy = q / kTW, ox = q - oy * kTW;
         if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
         float g[8];
-        Vec8<T>::ld(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, g);
+        raw_unpack(gall[j], g);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -602,6 +625,30 @@ static int pick_grid(long long work_blocks, int per_sm) {
 
 using namespace dlb;
 
+// the halo tile must fit in shared memory: large ASPP dilations (12/24/36) on small maps take the gather kernels
+static bool dw_tile_fits(int stride, int dil, int elem) {
+  const size_t ih = (kTH - 1) * stride + 2 * dil + 1, iw = (kTW - 1) * stride + 2 * dil + 1;
+  return ih * iw * kCV * 8 * elem + 9 * 64 * sizeof(float) <= 96 * 1024;
+}
+
+template <typename T>
+static int launch_dw_gather_fwd(const dlb_dw_conv_params* p, cudaStream_t st) {
+  DLB_REQUIRE(p->C / 8 <= 256, "dw_conv_fwd: C <= 2048 for the gather kernel");
+  DwArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+  a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;
+  a.x = p->x; a.y = p->y; a.w = p->w;
+  a.in_scale = p->in_scale; a.in_shift = p->in_shift; a.in_act = p->in_act;
+  a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
+  a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
+  a.cv = p->C / 8; a.ppb = 256 / a.cv; a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
+  const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
+  const size_t smem = p->stat_sum ? 2 * p->C * sizeof(float) : 0;
+  dw_fwd_kernel<T><<<grid, 256, smem, st>>>(a);
+  g_launches++;
+  return check_launch("dw_fwd_kernel");
+}
+
 template <typename T>
 static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
   fill_tile_geometry(a);
@@ -624,8 +671,7 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
   DLB_REQUIRE(smem <= 200 * 1024, "dw_conv_bwd: dilation %d needs a %zu-byte tile (> 200 KB)", a.dil, smem);
   if (smem > 48 * 1024)
     DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_sm = smem > 100 * 1024 ? 1 : 2;
-  const int cap = num_sms() * per_sm;
+  const int cap = num_sms();           // 1 CTA/SM (72 accumulators + staging need ~200 registers)
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
   dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
   g_launches++;
@@ -644,6 +690,11 @@ extern "C" int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream) {
   a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
   a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!dw_tile_fits(p->stride, p->dilation, dtype_size(p->dtype))) {
+    if (p->dtype == DLB_F16) return launch_dw_gather_fwd<__half>(p, st);
+    if (p->dtype == DLB_BF16) return launch_dw_gather_fwd<__nv_bfloat16>(p, st);
+    return launch_dw_gather_fwd<float>(p, st);
+  }
   if (p->dtype == DLB_F16) return launch_dw_tiled<__half>(a, st);
   if (p->dtype == DLB_BF16) return launch_dw_tiled<__nv_bfloat16>(a, st);
   return launch_dw_tiled<float>(a, st);
@@ -654,7 +705,8 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
   DLB_REQUIRE(p->C % 8 == 0, "dw_conv_bwd: C must be a multiple of 8 (C=%d)", p->C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dx) {
-    if (p->stride == 1) {
+    const bool tiled = dw_tile_fits(p->stride, p->dilation, dtype_size(p->dtype));
+    if (p->stride == 1 && tiled) {
       // backward-data of a stride-1 conv = correlation of dy with the rotated filter, padding 2*d - pad
       DwTileArgs a{};
       a.B = p->B; a.H = p->Ho; a.W = p->Wo; a.C = p->C; a.Ho = p->H; a.Wo = p->W;
@@ -684,6 +736,30 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
   }
   if (p->dw) {
     DLB_REQUIRE(p->x, "dw_conv_bwd: x required for the weight gradient");
+    if (!dw_tile_fits(p->stride, p->dilation, dtype_size(p->dtype))) {
+      DLB_REQUIRE(p->C / 8 <= 256, "dw_conv_bwd: C <= 2048 for the gather kernel");
+      DwBwdArgs g{};
+      g.B = p->B; g.H = p->H; g.W = p->W; g.C = p->C; g.Ho = p->Ho; g.Wo = p->Wo;
+      g.stride = p->stride; g.dil = p->dilation; g.pad_t = p->pad_top; g.pad_l = p->pad_left;
+      g.x = p->x; g.dy = p->dy; g.dx = p->dx; g.w = p->w; g.dw = p->dw;
+      g.in_scale = p->in_scale; g.in_shift = p->in_shift; g.in_act = p->in_act;
+      g.cv = p->C / 8; g.ppb = 256 / g.cv;
+      g.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
+      const int grid = pick_grid((g.npix + g.ppb - 1) / g.ppb, 2);
+      const size_t smem = 9 * p->C * sizeof(float);
+#define LG(TT)                                                                                                 \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_weight_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dw_bwd_weight_kernel<TT><<<grid, 256, smem, st>>>(g);                                                      \
+  } while (0)
+      if (p->dtype == DLB_F16) LG(__half);
+      else if (p->dtype == DLB_BF16) LG(__nv_bfloat16);
+      else LG(float);
+#undef LG
+      g_launches++;
+      return check_launch("dw_bwd_weight_kernel");
+    }
     DwTileArgs a{};
     a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
     a.stride = p->stride; a.dil = p->dilation; a.pad_t = p->pad_top; a.pad_l = p->pad_left;

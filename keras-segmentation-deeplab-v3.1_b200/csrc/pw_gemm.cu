@@ -14,8 +14,9 @@
 //   * warp 0   : TMA producer  (cp.async.bulk.tensor 2D, 128-byte swizzle, OOB zero fill pads K and N)
 //   * warp 1   : tcgen05.mma issuer (one thread), accumulators in TMEM (up to 512 fp32 columns,
 //                double-buffered when a column group is <= 256 wide), tcgen05.commit -> mbarriers
-//   * warps 2-5: epilogue, tcgen05.ld 32x32b -> registers -> fused BN-affine / bias / per-image bias /
-//                activation / residual / BatchNorm batch statistics / Subpixel phase-shift store
+//   * warps 2-9: epilogue (two warps per TMEM lane quarter, 32 columns per iteration), tcgen05.ld 32x32b ->
+//                registers -> fused BN-affine / bias / per-image bias / activation / residual / BatchNorm batch
+//                statistics / Subpixel phase-shift store
 //   * N > 512 (expand convs, Subpixel) is processed in column groups; A tiles are re-fetched through L2.
 //
 // DLB_F32 inputs take an exact-fp32 SIMT path (the 1e-3 parity mode of BASELINE.json; tf32 would not hold it).
@@ -33,7 +34,8 @@ constexpr int kBlockM = 128;
 constexpr int kSwzBytes = 128;
 constexpr int kABytes = kBlockM * kSwzBytes;   // 16 KB per A stage
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 
 struct GemmArgs {
   int M, N, K;
@@ -83,7 +85,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads / 32); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -158,8 +160,12 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    // Two warps per TMEM lane quarter; each takes every other 32-column block of the accumulator group.  The
+    // epilogue is latency bound (tcgen05.ld -> math -> shuffles -> st.global, one warp per scheduler), so each
+    // iteration keeps two independent 16-column chains in flight.
     const int quad = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;           // which 32-column blocks
     const bool do_stats = g.stat_sum != nullptr;
     const int red_col = reduce16_col_of_lane(lane);
     int it = 0;
@@ -168,13 +174,11 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool row_ok = m < g.M;
       const float* rb = nullptr;
       if (g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
-      // Subpixel store geometry
       size_t shuf_row_base = 0;
       if (g.shuffle_r > 0 && row_ok) {
         const int hw = g.shuffle_h * g.shuffle_w;
         const int b = m / hw, rem = m - b * hw;
         const int a = rem / g.shuffle_w, bb = rem - a * g.shuffle_w;
-        // element offset of out[b, a*r + 0, bb*r + 0, 0]
         shuf_row_base = ((static_cast<size_t>(b) * g.shuffle_h * g.shuffle_r + static_cast<size_t>(a) * g.shuffle_r) *
                              (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) +
                          static_cast<size_t>(bb) * g.shuffle_r) *
@@ -188,42 +192,53 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after();
         const int gcols = chunks * g.chunk_n;
         const int col_base = grp * group_rows;
-        for (int j = 0; j < gcols; j += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j, r);
+        for (int j = half * 32; j < gcols; j += 64) {
+          const bool two = j + 16 < gcols;
+          uint32_t r[2][16];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j;
+          tmem_ld16(taddr, r[0]);
+          if (two) tmem_ld16(taddr + 16, r[1]);
           tmem_ld_wait();
-          const int n0 = col_base + j;
-          float v[16];
+          float v[2][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(r[i]) * s_scale[n0 + i] + s_shift[n0 + i];
-            if (rb && n0 + i < g.N) x += rb[n0 + i];
-            v[i] = x;
-          }
-          if (do_stats) {
-            float s1[16], s2[16];
+          for (int h = 0; h < 2; ++h) {
+            const int n0 = col_base + j + h * 16;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float q = row_ok ? Act<OutT>::rnd(v[i]) : 0.f;
-              s1[i] = q; s2[i] = q * q;
-            }
-            const float t1 = warp_reduce16(s1, lane);
-            const float t2 = warp_reduce16(s2, lane);
-            if ((lane & 1) == 0) {
-              atomicAdd(&s_sum[n0 + red_col], t1);
-              atomicAdd(&s_sqs[n0 + red_col], t2);
+              float x = __uint_as_float(r[h][i]) * s_scale[n0 + i] + s_shift[n0 + i];
+              if (rb && n0 + i < g.N) x += rb[n0 + i];
+              v[h][i] = (h == 0 || two) ? x : 0.f;
             }
           }
+          if (do_stats) {
+            float s1[2][16], s2[2][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], g.act);
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float q = row_ok ? Act<OutT>::rnd(v[h][i]) : 0.f;
+                s1[h][i] = q; s2[h][i] = q * q;
+              }
+            const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
+            const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
+            if ((lane & 1) == 0) {
+              const int n0 = col_base + j;
+              atomicAdd(&s_sum[n0 + red_col], t1a);
+              atomicAdd(&s_sqs[n0 + red_col], t2a);
+              if (two) {
+                atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
+                atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
+              }
+            }
+          }
           if (row_ok) {
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const int n = n0 + h8 * 8;
-              if (n >= g.n_store) continue;
+            for (int h8 = 0; h8 < 4; ++h8) {
+              const int n = col_base + j + h8 * 8;
+              if (n >= g.n_store || (h8 >= 2 && !two)) continue;
               float o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = v[h8 * 8 + i];
+              for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
               if (g.R) {
                 float rr[8];
                 Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
@@ -240,9 +255,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
               }
               if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
-                // fp32 outputs may end on a multiple of 4
-                float4 lo4 = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(dst) = lo4;
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
               } else {
                 Vec8<OutT>::st(dst, o);
               }
@@ -255,8 +268,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
     if (do_stats) {
-      named_bar_sync(1, 128);
-      for (int n = threadIdx.x - 64; n < g.N; n += 128) {
+      named_bar_sync(1, kEpiThreads);
+      for (int n = threadIdx.x - 64; n < g.N; n += kEpiThreads) {
         atomicAdd(&g.stat_sum[n], static_cast<double>(s_sum[n]));
         atomicAdd(&g.stat_sqs[n], static_cast<double>(s_sqs[n]));
       }
@@ -416,7 +429,9 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   const int npad = (p->N + 15) / 16 * 16;
   g.n_chunks = (npad + 255) / 256;
   g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
-  g.chunks_per_group = g.n_chunks >= 2 ? 2 : 1;
+  // Two chunks per accumulator group share one A fetch (matters when K is large); for small K prefer one chunk per
+  // group so the group fits twice in TMEM and the epilogue of one group overlaps the MMAs of the next.
+  g.chunks_per_group = (g.n_chunks >= 2 && p->K > 256) ? 2 : 1;
   if (g.chunks_per_group * g.chunk_n > 512) g.chunks_per_group = 1;
   g.n_groups = (g.n_chunks + g.chunks_per_group - 1) / g.chunks_per_group;
   g.acc_cols = g.chunks_per_group * g.chunk_n;

@@ -279,7 +279,7 @@ def test_train_step_16bit_close_to_oracle(dtype):
     from deeplab_b200.utils import SegModel
     from oracle import network as N
     from oracle import train as T
-    B, H, Wd = 2, 256, 256
+    B, H, Wd = 4, 256, 256
     sm = SegModel(image_size=(H, Wd), compute_dtype=dtype)
     model = sm.create_seg_model("original", n=21)
     W = N.weights_from_h5(os.path.join(GOLD, "mobilenetv2_original.h5"))     # the reference's trained parameters
@@ -306,7 +306,7 @@ def test_train_step_16bit_close_to_oracle(dtype):
         g = (p.grad.double().cpu() / e.loss_scale).flatten()
         r = grads[name][0].double().flatten()
         cos = torch.dot(g, r) / (g.norm() * r.norm())
-        assert cos > (0.98 if dtype == "float16" else 0.90), (name, cos.item())
+        assert cos > (0.995 if dtype == "float16" else 0.97), (name, cos.item())
     flat, ref = [], []
     for rec in e.layers:
         for i, p in enumerate(rec.params):
@@ -315,7 +315,7 @@ def test_train_step_16bit_close_to_oracle(dtype):
                 ref.append(grads[rec.name][i].double().flatten())
     flat, ref = torch.cat(flat), torch.cat(ref)
     cos = torch.dot(flat, ref) / (flat.norm() * ref.norm())
-    assert cos > (0.95 if dtype == "float16" else 0.80), cos.item()
+    assert cos > (0.97 if dtype == "float16" else 0.85), cos.item()     # measured 0.99 / 0.92 (tools/diag_grads.py)
 
 
 def test_graph_replay_equals_eager_and_mious_match():
