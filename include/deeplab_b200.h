@@ -143,6 +143,16 @@ int dlb_stem_conv_fwd(const dlb_stem_conv_params* p, void* stream);
 int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, const float* x, const void* dy, float* dw,
                         void* stream);
 
+/* Xception-only helpers (backbone='xception', deeplabv3p.py:272-313, decoder :414-429):
+ *   dense 3x3 stride-1 SAME conv (entry_flow_conv1_2, :287), [3,3,Cin,Cout] HWIO fp32 weights, folded BN + act epilogue;
+ *   pixel subsampling = the input gather of a 1x1 stride-2 'valid' conv (_conv2d_same with kernel_size=1, :106-116);
+ *   legacy TF1 bilinear resize of a feature map (:418), output written with channel pitch ldo (concat slice). */
+int dlb_conv3x3_fwd(int B, int H, int W, int Cin, int Cout, int dtype, const void* x, const float* w, void* y,
+                    const float* out_scale, const float* out_shift, int out_act, void* stream);
+int dlb_subsample(int B, int H, int W, int C, int step, int dtype, const void* x, void* y, void* stream);
+int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int ldo, int dtype, const void* x, void* y,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * BatchNormalization (deeplabv3p.py:76,80,178,189,197,322,379,386,408), training mode = batch statistics.
  * ------------------------------------------------------------------------------------------------- */

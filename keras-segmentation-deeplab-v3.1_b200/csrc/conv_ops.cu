@@ -616,6 +616,119 @@ __global__ void __launch_bounds__(864) stem_wgrad_kernel(int B, int H, int W, in
   atomicAdd(&dw[tap * 32 + co], acc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// dense 3x3 conv, stride 1, SAME (Xception entry_flow_conv1_2, deeplabv3p.py:287-291 via _conv2d_same :87-103)
+// direct conv: 256 threads = 64 pixels x 4 groups of 16 output channels; weights [3,3,Cin,Cout] staged in smem
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv3x3_fwd_kernel(int B, int H, int W, int Cin, int Cout, const T* __restrict__ x,
+                                                          const float* __restrict__ w, T* __restrict__ y,
+                                                          const float* __restrict__ out_scale,
+                                                          const float* __restrict__ out_shift, int out_act) {
+  extern __shared__ float s_w[];   // [9*Cin][Cout]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * Cin * Cout; i += 256) s_w[i] = w[i];
+  __syncthreads();
+  const int cog = tid >> 6;                 // output-channel group of 16 within a 64-channel slab
+  const int pl = tid & 63;
+  const long long npix = static_cast<long long>(B) * H * W;
+  for (int co_base = 0; co_base < Cout; co_base += 64) {
+    const int co0 = co_base + cog * 16;
+    if (co0 >= Cout) continue;
+    for (long long pix = static_cast<long long>(blockIdx.x) * 64 + pl; pix < npix; pix += static_cast<long long>(gridDim.x) * 64) {
+      const int wx = static_cast<int>(pix % W);
+      const long long t1 = pix / W;
+      const int hy = static_cast<int>(t1 % H);
+      const int b = static_cast<int>(t1 / H);
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = hy - 1 + ky;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = wx - 1 + kx;
+          if (xx < 0 || xx >= W) continue;
+          const T* px = x + ((static_cast<size_t>(b) * H + yy) * W + xx) * Cin;
+          const float* wt = s_w + static_cast<size_t>((ky * 3 + kx) * Cin) * Cout + co0;
+          for (int c8 = 0; c8 < Cin; c8 += 8) {
+            float v[8];
+            Vec8<T>::ld(px + c8, v);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const float* wr = wt + static_cast<size_t>(c8 + ci) * Cout;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = fmaf(v[ci], wr[i], acc[i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float vv = acc[h8 * 8 + i];
+          if (out_scale) vv = fmaf(vv, out_scale[co0 + h8 * 8 + i], out_shift[co0 + h8 * 8 + i]);
+          o[i] = apply_act(vv, out_act);
+        }
+        Vec8<T>::st(y + static_cast<size_t>(pix) * Cout + co0 + h8 * 8, o);
+      }
+    }
+  }
+}
+
+// every `step`-th pixel of x in both dimensions (input of a 1x1 stride-2 'valid' conv, deeplabv3p.py:106-116 with k=1)
+template <typename T>
+__global__ void __launch_bounds__(256) subsample_kernel(int B, int H, int W, int C, int step, int Ho, int Wo,
+                                                        const T* __restrict__ x, T* __restrict__ y) {
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int v = static_cast<int>(i % cv);
+    long long t = i / cv;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long b = t / Ho;
+    float vals[8];
+    Vec8<T>::ld(x + ((b * H + static_cast<long long>(ho) * step) * W + static_cast<long long>(wo) * step) * C + v * 8, vals);
+    Vec8<T>::st(y + i * 8, vals);
+  }
+}
+
+// legacy TF1 bilinear resize of an NHWC feature map (deeplabv3p.py:418), output channel pitch ldo (concat slices)
+template <typename T>
+__global__ void __launch_bounds__(256) resize_feat_kernel(int B, int h, int w, int C, int H, int W, int ldo,
+                                                          const T* __restrict__ x, T* __restrict__ y) {
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(B) * H * W * cv;
+  const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int v = static_cast<int>(i % cv);
+    long long t = i / cv;
+    const int X = static_cast<int>(t % W); t /= W;
+    const int Y = static_cast<int>(t % H);
+    const long long b = t / H;
+    const float fy_ = Y * sy, fx_ = X * sx;
+    const int y0 = static_cast<int>(floorf(fy_)), x0 = static_cast<int>(floorf(fx_));
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float fy = fy_ - y0, fx = fx_ - x0;
+    float tl[8], tr[8], bl[8], br[8], o[8];
+    const T* base = x + b * h * w * C + v * 8;
+    Vec8<T>::ld(base + (static_cast<size_t>(y0) * w + x0) * C, tl);
+    Vec8<T>::ld(base + (static_cast<size_t>(y0) * w + x1) * C, tr);
+    Vec8<T>::ld(base + (static_cast<size_t>(y1) * w + x0) * C, bl);
+    Vec8<T>::ld(base + (static_cast<size_t>(y1) * w + x1) * C, br);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float top = tl[k] + (tr[k] - tl[k]) * fx;
+      const float bot = bl[k] + (br[k] - bl[k]) * fx;
+      o[k] = top + (bot - top) * fy;
+    }
+    Vec8<T>::st(y + ((b * H + Y) * W + X) * ldo + v * 8, o);
+  }
+}
+
 static int pick_grid(long long work_blocks, int per_sm) {
   long long cap = static_cast<long long>(num_sms()) * per_sm;
   return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
@@ -811,4 +924,53 @@ extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, con
     stem_wgrad_kernel<float><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
   g_launches++;
   return check_launch("stem_wgrad_kernel");
+}
+
+extern "C" int dlb_conv3x3_fwd(int B, int H, int W, int Cin, int Cout, int dtype, const void* x, const float* w, void* y,
+                               const float* out_scale, const float* out_shift, int out_act, void* stream) {
+  DLB_REQUIRE(x && w && y, "conv3x3_fwd: null pointer");
+  DLB_REQUIRE(Cin % 8 == 0 && Cout % 16 == 0, "conv3x3_fwd: Cin %% 8 == 0 and Cout %% 16 == 0 required");
+  const size_t smem = static_cast<size_t>(9) * Cin * Cout * sizeof(float);
+  DLB_REQUIRE(smem <= 200 * 1024, "conv3x3_fwd: weights (%zu B) do not fit in shared memory", smem);
+  const long long npix = static_cast<long long>(B) * H * W;
+  const int grid = pick_grid((npix + 63) / 64, 2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define L3(TT)                                                                                                   \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      DLB_CUDA(cudaFuncSetAttribute(conv3x3_fwd_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3x3_fwd_kernel<TT><<<grid, 256, smem, st>>>(B, H, W, Cin, Cout, (const TT*)x, w, (TT*)y, out_scale, out_shift, out_act); \
+  } while (0)
+  if (dtype == DLB_F16) L3(__half);
+  else if (dtype == DLB_BF16) L3(__nv_bfloat16);
+  else L3(float);
+#undef L3
+  g_launches++;
+  return check_launch("conv3x3_fwd_kernel");
+}
+
+extern "C" int dlb_subsample(int B, int H, int W, int C, int step, int dtype, const void* x, void* y, void* stream) {
+  DLB_REQUIRE(x && y && C % 8 == 0 && step >= 1, "subsample: bad arguments");
+  const int Ho = (H + step - 1) / step, Wo = (W + step - 1) / step;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  const int grid = pick_grid((total + 255) / 256, 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLB_F32) subsample_kernel<float><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const float*)x, (float*)y);
+  else if (dtype == DLB_F16) subsample_kernel<__half><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const __half*)x, (__half*)y);
+  else subsample_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  g_launches++;
+  return check_launch("subsample_kernel");
+}
+
+extern "C" int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int ldo, int dtype, const void* x, void* y,
+                                   void* stream) {
+  DLB_REQUIRE(x && y && C % 8 == 0 && ldo >= C && ldo % 8 == 0, "resize_bilinear: bad arguments");
+  const long long total = static_cast<long long>(B) * H * W * (C / 8);
+  const int grid = pick_grid((total + 255) / 256, 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLB_F32) resize_feat_kernel<float><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const float*)x, (float*)y);
+  else if (dtype == DLB_F16) resize_feat_kernel<__half><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const __half*)x, (__half*)y);
+  else resize_feat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  g_launches++;
+  return check_launch("resize_feat_kernel");
 }

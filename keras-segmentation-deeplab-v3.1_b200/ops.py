@@ -273,3 +273,25 @@ def confusion(labels: torch.Tensor, argmax: torch.Tensor, C_: int, conf: torch.T
     npix = argmax.numel() // B
     L.check(L.lib().dlb_confusion(B, npix, C_, labels.data_ptr(), argmax.data_ptr(), conf.data_ptr(), L.stream_ptr()),
             "confusion")
+
+
+def conv3x3_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, out_scale=None, out_shift=None, out_act=ACT_NONE):
+    B, H, W_, Cin = x.shape
+    L.check(L.lib().dlb_conv3x3_fwd(B, H, W_, Cin, y.shape[-1], L.dt(x), x.data_ptr(), w.data_ptr(), y.data_ptr(),
+                                    L.ptr(out_scale), L.ptr(out_shift), out_act, L.stream_ptr()), "conv3x3_fwd")
+    return y
+
+
+def subsample(x: torch.Tensor, y: torch.Tensor, step: int = 2):
+    B, H, W_, C_ = x.shape
+    L.check(L.lib().dlb_subsample(B, H, W_, C_, step, L.dt(x), x.data_ptr(), y.data_ptr(), L.stream_ptr()), "subsample")
+    return y
+
+
+def resize_bilinear(x: torch.Tensor, y: torch.Tensor, C_: Optional[int] = None):
+    """x [B,h,w,C] -> y[..., :C] of a [B,H,W,ldo] buffer (legacy TF1 bilinear)."""
+    B, h, w, C0 = x.shape
+    C_ = C_ or C0
+    L.check(L.lib().dlb_resize_bilinear(B, h, w, C_, y.shape[1], y.shape[2], y.stride(2), L.dt(x), x.data_ptr(),
+                                        y.data_ptr(), L.stream_ptr()), "resize_bilinear")
+    return y
