@@ -158,6 +158,70 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
   for (int i = tid; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.red[i], static_cast<double>(s_red[i]));
 }
 
+// fp16 specialisation of the reduce pass: packed half2 arithmetic, 4-row partial sums on half2 folded into fp32
+// accumulators (the generic kernel is instruction-issue bound: ~13 instructions per element, 1.7 TB/s)
+struct __align__(16) BH8 { __half2 h[4]; };
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
+  extern __shared__ float s_red[];   // [2*C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  if (tid < a.rpb * a.cv) {
+    const int r_in = tid / a.cv;
+    const int c0 = (tid - r_in * a.cv) * 8;
+    __half2 sc2[4], sh2[4], mu2[4], rs2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sc2[k] = __floats2half2_rn(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
+      sh2[k] = __floats2half2_rn(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
+      mu2[k] = __floats2half2_rn(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
+      rs2[k] = __floats2half2_rn(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
+    }
+    const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __half* x = reinterpret_cast<const __half*>(a.x);
+    const __half* da = reinterpret_cast<const __half*>(a.da);
+    const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
+    constexpr int U = 4;
+    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+      BH8 xv[U], gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * rstride;
+        if (r < a.M) {
+          xv[u] = *reinterpret_cast<const BH8*>(x + r * a.C + c0);
+          gv[u] = *reinterpret_cast<const BH8*>(da + r * a.C + c0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { xv[u].h[k] = zero2; gv[u].h[k] = zero2; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half2 p1 = zero2, p2 = zero2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          __half2 dz = gv[u].h[k];
+          if (a.act != DLB_ACT_NONE) {
+            const __half2 z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
+            __half2 m = __hgt2(z, zero2);
+            if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
+            dz = __hmul2(dz, m);
+          }
+          p1 = __hadd2(p1, dz);
+          p2 = __hfma2(dz, __hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]), p2);
+        }
+        const float2 f1 = __half22float2(p1), f2 = __half22float2(p2);
+        s1[2 * k] += f1.x; s1[2 * k + 1] += f1.y; s2[2 * k] += f2.x; s2[2 * k + 1] += f2.y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_red[c0 + k], s1[k]); atomicAdd(&s_red[a.C + c0 + k], s2[k]); }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.red[i], static_cast<double>(s_red[i]));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
   const int tid = threadIdx.x;
@@ -350,7 +414,8 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   const size_t smem = 2 * p->C * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
+  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_reduce_h_kernel<<<grid, 256, smem, st>>>(a);
+  else if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
   else bn_bwd_reduce_kernel<float><<<grid, 256, smem, st>>>(a);
   g_launches++;

@@ -10,6 +10,7 @@
 // These kernels are HBM/L2-bandwidth bound: per output element 2 B read + 2 B write algorithmic traffic at
 // 16 bit for 18 flop.  Grids are sized as a multiple of the SM count and loop (persistent style).
 #include <atomic>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -484,6 +485,262 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs
   if (cur_chunk >= 0) flush(cur_chunk);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp16 specialisations of the tiled kernels.  The generic versions above are instruction-issue bound (ncu: ~750
+// warp instructions per 8-channel output vector, 40 % issue utilisation at 0.5 TB/s).  Here the prologue and the
+// 3-tap row sums run on packed half2 (HFMA2 / HMNMX2), rows are added in fp32, filter taps are 36 half2
+// registers instead of 72 floats, and tap offsets are precomputed: ~4x fewer instructions per output.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) H8 { __half2 h[4]; };
+
+__device__ __forceinline__ void dw_stage_input_h(const DwTileArgs& a, H8* s_in, int b, int oy0, int ox0, int c0, bool cv_ok) {
+  const int tid = threadIdx.x, v = tid & 7;
+  const int cc = c0 + v * 8;
+  __half2 sc2[4], sh2[4];
+  const bool pro = a.in_scale != nullptr;
+  if (pro && cv_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sc2[i] = __floats2half2_rn(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
+      sh2[i] = __floats2half2_rn(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
+    }
+  }
+  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+  const __half* x = reinterpret_cast<const __half*>(a.x);
+  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
+  const int npos = a.ih * a.iw;
+  constexpr int U = 4;
+  for (int p0 = tid >> 3; p0 < npos; p0 += 32 * U) {
+    H8 raw[U];
+    bool inb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + 32 * u;
+      const int py = p / a.iw, px = p - py * a.iw;
+      const int gy = gy0 + py, gx = gx0 + px;
+      inb[u] = p < npos && cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      if (inb[u]) raw[u] = *reinterpret_cast<const H8*>(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + 32 * u;
+      if (p >= npos) continue;
+      H8 o;
+      if (inb[u]) {
+        o = raw[u];
+        if (pro) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __half2 z = __hfma2(o.h[i], sc2[i], sh2[i]);
+            if (a.in_act == DLB_ACT_RELU6) z = __hmin2(__hmax2(z, zero2), six2);
+            else if (a.in_act == DLB_ACT_RELU) z = __hmax2(z, zero2);
+            o.h[i] = z;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.h[i] = zero2;
+      }
+      s_in[static_cast<size_t>(p) * kCV + v] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) dw_fwd_tiled_h_kernel(const DwTileArgs a) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  H8* s_in = reinterpret_cast<H8*>(s_raw);
+  float* s_stats = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * sizeof(H8));   // [2][64]
+  const int tid = threadIdx.x, v = tid & 7;
+  const bool stats = a.stat_sum != nullptr;
+  __half2 w2[9][4];
+  float ssum[8], ssqs[8];
+  int off[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+  int cur_chunk = -1;
+  __half* y = reinterpret_cast<__half*>(a.y);
+  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
+
+  auto flush_stats = [&](int chunk) {
+    __syncthreads();
+    if (tid < 128) s_stats[tid] = 0.f;
+    __syncthreads();
+    if (chunk * 64 + v * 8 < a.C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
+    }
+    __syncthreads();
+    if (tid < 64 && chunk * 64 + tid < a.C) {
+      atomicAdd(&a.stat_sum[chunk * 64 + tid], static_cast<double>(s_stats[tid]));
+      atomicAdd(&a.stat_sqs[chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int chunk = tile / per_chunk;
+    int r = tile - chunk * per_chunk;
+    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
+    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
+      cur_chunk = chunk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
+      if (cv_ok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int ts = a.flip ? 8 - t : t;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
+        }
+      }
+    }
+    const int oy0 = ty * kTH, ox0 = tx * kTW;
+    __syncthreads();
+    dw_stage_input_h(a, s_in, b, oy0, ox0, c0, cv_ok);
+    __syncthreads();
+    if (cv_ok) {
+#pragma unroll 2
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
+        const H8* base = s_in + static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          __half2 racc[4];
+          {
+            const H8 xv = base[off[ky * 3]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) racc[i] = __hmul2(xv.h[i], w2[ky * 3][i]);
+          }
+#pragma unroll
+          for (int kx = 1; kx < 3; ++kx) {
+            const H8 xv = base[off[ky * 3 + kx]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
+        if (a.out_scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], a.out_scale[cc + i], a.out_shift[cc + i]), a.out_act);
+        }
+        if (stats) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssqs[i] = fmaf(acc[i], acc[i], ssqs[i]); }
+        }
+        H8 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc) = o;
+      }
+    }
+  }
+  if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
+}
+
+__global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileArgs a) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  H8* s_in = reinterpret_cast<H8*>(s_raw);
+  float* s_dw = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * sizeof(H8));   // [9][64]
+  const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
+  float acc[9][8];
+  int off[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+  int cur_chunk = -1;
+  const __half* dy = reinterpret_cast<const __half*>(a.dy);
+  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
+
+  auto flush = [&](int chunk) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = acc[t][i];
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        acc[t][i] = x;
+      }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) s_dw[i] = 0.f;
+    __syncthreads();
+    if (lane < 8) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * 64 + v * 8 + i], acc[t][i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) {
+      const int t = i >> 6, c = chunk * 64 + (i & 63);
+      if (c < a.C) atomicAdd(&a.dw[t * a.C + c], s_dw[i]);
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int chunk = tile / per_chunk;
+    int r = tile - chunk * per_chunk;
+    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
+    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0) flush(cur_chunk);
+      cur_chunk = chunk;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    }
+    const int oy0 = ty * kTH, ox0 = tx * kTW;
+    __syncthreads();
+    dw_stage_input_h(a, s_in, b, oy0, ox0, c0, cv_ok);
+    __syncthreads();
+    if (cv_ok) {
+      constexpr int NP = (kTH * kTW) / 32;
+      H8 g[NP];
+      bool ok[NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        ok[j] = oy0 + oy < a.Ho && ox0 + ox < a.Wo;
+        if (ok[j]) g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
+        }
+      }
+      // products of the thread's 4 pixels are summed on packed half2, then folded into the fp32 accumulators
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        __half2 p2[4];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const int q = (tid >> 3) + 32 * j;
+          const int oy = q / kTW, ox = q - oy * kTW;
+          const H8 xv = s_in[static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v + off[t]];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) p2[i] = j == 0 ? __hmul2(xv.h[i], g[j].h[i]) : __hfma2(xv.h[i], g[j].h[i], p2[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(p2[i]); acc[t][2 * i] += f.x; acc[t][2 * i + 1] += f.y; }
+      }
+    }
+  }
+  if (cur_chunk >= 0) flush(cur_chunk);
+}
+
 static void fill_tile_geometry(DwTileArgs& a) {
   a.tiles_y = (a.Ho + kTH - 1) / kTH;
   a.tiles_x = (a.Wo + kTW - 1) / kTW;
@@ -769,6 +1026,15 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
   DLB_REQUIRE(smem <= 200 * 1024, "dw_conv: dilation %d needs a %zu-byte tile (> 200 KB)", a.dil, smem);
   if (smem > 48 * 1024)
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+    if (smem > 48 * 1024)
+      DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm_h = smem > 100 * 1024 ? 1 : 2;
+    const int cap_h = num_sms() * per_sm_h;
+    dw_fwd_tiled_h_kernel<<<a.num_tiles < cap_h ? a.num_tiles : cap_h, 256, smem, st>>>(a);
+    g_launches++;
+    return check_launch("dw_fwd_tiled_h_kernel");
+  }
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   const int cap = num_sms() * per_sm;
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
@@ -786,6 +1052,13 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
     DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cap = num_sms();           // 1 CTA/SM (72 accumulators + staging need ~200 registers)
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
+  if (std::is_same<T, __half>::value) {
+    if (smem > 48 * 1024)
+      DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dw_wgrad_tiled_h_kernel<<<grid, 256, smem, st>>>(a);
+    g_launches++;
+    return check_launch("dw_wgrad_tiled_h_kernel");
+  }
   dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
   g_launches++;
   return check_launch("dw_wgrad_tiled_kernel");

@@ -195,11 +195,12 @@ def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
     ssqs = torch.zeros(C, device="cuda", dtype=torch.float64)
     ops.dw_conv_fwd(x, w, y, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc, in_shift=ish,
                     in_act=2, stat_sum=ssum, stat_sqs=ssqs)
-    tol = 3e-3 if dtype == torch.float16 else 1e-5
+    # fp16: the prologue and the 3-tap row sums run on packed half2 (rows are added in fp32)
+    tol = 8e-3 if dtype == torch.float16 else 1e-5
     assert rel_err(y, ref) < tol
     yr = y.double()
-    assert rel_err(ssum, yr.sum((0, 1, 2))) < 1e-4 + 1e-9
-    assert rel_err(ssqs, (yr * yr).sum((0, 1, 2))) < 1e-4
+    assert rel_err(ssum, yr.sum((0, 1, 2))) < (2e-3 if dtype == torch.float16 else 1e-4)
+    assert rel_err(ssqs, (yr * yr).sum((0, 1, 2))) < (2e-3 if dtype == torch.float16 else 1e-4)
     # backward: gradient w.r.t. the *activated* input a and w.r.t. the weights
     dy = torch.randn(B, Ho, Wo, C, device="cuda", generator=g).to(dtype)
     a = (x.float() * isc + ish).clamp(0, 6).requires_grad_(True)
@@ -210,7 +211,7 @@ def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
     ops.dw_conv_bwd(x, dy, w, dx=dx, dw=dw, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc,
                     in_shift=ish, in_act=2)
     assert rel_err(dx, ga) < tol
-    assert rel_err(dw, gw) < 1e-3
+    assert rel_err(dw, gw) < (5e-3 if dtype == torch.float16 else 1e-3)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
@@ -275,8 +276,8 @@ def test_bn_train_fwd_bwd(dtype):
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_bwd(x, da, dx, scale=scale, shift=shift, mean=mean, rstd=rstd, act=2, red=red, dgamma=dgamma, dbeta=dbeta)
     assert rel_err(dx, gx) < (5e-3 if dtype == torch.float16 else 1e-4)
-    assert rel_err(dgamma, gg) < 1e-3
-    assert rel_err(dbeta, gb) < 1e-3
+    assert rel_err(dgamma, gg) < (5e-3 if dtype == torch.float16 else 1e-3)
+    assert rel_err(dbeta, gb) < (5e-3 if dtype == torch.float16 else 1e-3)
 
 
 def test_dropout_apply_and_bwd_consistent():

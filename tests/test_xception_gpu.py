@@ -62,8 +62,9 @@ def test_xception_helper_kernels():
     for dt, tol in ((torch.float32, 1e-5), (torch.float16, 4e-3)):
         y = torch.empty(2, 20, 24, 64, device="cuda", dtype=dt)
         ops.conv3x3_fwd(x.to(dt), w, y, out_scale=sc, out_shift=sh, out_act=1)
-        ref = F.conv2d(x.to(dt).float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
-        ref = (ref * sc + sh).clamp_min(0)
+        # CPU reference: torch's CUDA conv2d may use TF32
+        ref = F.conv2d(x.to(dt).float().cpu().permute(0, 3, 1, 2), w.cpu().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+        ref = (ref * sc.cpu() + sh.cpu()).clamp_min(0).cuda()
         assert ((y.float() - ref).abs().max() / ref.abs().max()).item() < tol
     sub = torch.empty(2, 10, 12, 32, device="cuda")
     ops.subsample(x, sub, 2)
