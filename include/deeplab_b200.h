@@ -152,6 +152,11 @@ int dlb_conv3x3_fwd(int B, int H, int W, int Cin, int Cout, int dtype, const voi
 int dlb_subsample(int B, int H, int W, int C, int step, int dtype, const void* x, void* y, void* stream);
 int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int ldo, int dtype, const void* x, void* y,
                         void* stream);
+/* Fused ASPP atrous depthwise stage (deeplabv3p.py:392-399): the depthwise 3x3 + BN + ReLU halves of aspp1..3
+ * (three dilation rates) in one pass over x [B,H,W,C]: reads x once, writes y[0..2] [B,H,W,C].
+ * w[i]: [3,3,C] fp32, scale/shift[i]: folded depthwise BN.  H*W*32 bytes must fit in shared memory (<= 80x80). */
+int dlb_aspp_dw3_fwd(int B, int H, int W, int C, int dtype, const void* x, const float* const* w, const int* rates,
+                     const float* const* scale, const float* const* shift, void* const* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * BatchNormalization (deeplabv3p.py:76,80,178,189,197,322,379,386,408), training mode = batch statistics.

@@ -103,7 +103,7 @@ EXPORTS = [
     "dlb_bn_bwd_apply", "dlb_global_avgpool_fwd", "dlb_global_avgpool_bwd", "dlb_small_gemm",
     "dlb_resize_softmax_fwd", "dlb_resize_softmax_ce", "dlb_ce_grad_scale", "dlb_phase_shift", "dlb_adam_step",
     "dlb_cast_weight", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
-    "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear",
+    "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
 ]
 
 _lib = None
@@ -141,6 +141,7 @@ def lib() -> C.CDLL:
         L.dlb_conv3x3_fwd.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
         L.dlb_subsample.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp]
         L.dlb_resize_bilinear.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+        L.dlb_aspp_dw3_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.dlb_crf_workspace_bytes.argtypes = [vp]
         L.dlb_crf_inference.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
         for name in ("dlb_pw_gemm", "dlb_pw_wgrad", "dlb_dw_conv_fwd", "dlb_dw_conv_bwd", "dlb_stem_conv_fwd",

@@ -986,6 +986,91 @@ __global__ void __launch_bounds__(256) resize_feat_kernel(int B, int h, int w, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused ASPP atrous depthwise stage (deeplabv3p.py:392-399, the three SepConv_BN depthwise halves with rates
+// 6/12/18 or 12/24/36 + BN + ReLU): ONE pass over the backbone feature map produces all three branch inputs.
+// With rate 36 on a 64x64 map the halo is the map, so a CTA stages the whole HxW plane of a 32-byte channel slice
+// (16 fp16 / 8 fp32 channels, <= 200 KB) in shared memory and computes 3 rates x 9 taps from it.
+// Algorithmic traffic: read x once + write three outputs (4 x |x|) instead of 3 reads + 3 writes.
+// ---------------------------------------------------------------------------------------------
+struct AsppArgs {
+  int B, H, W, C;
+  const void* x;
+  const float* w[3]; int rate[3];
+  const float* scale[3]; const float* shift[3];
+  void* y[3];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1) aspp_dw3_kernel(const AsppArgs a) {
+  constexpr int VP = 32 / (8 * sizeof(T));          // 8-channel vectors per pixel in the slice (2 for 16-bit, 1 for fp32)
+  constexpr int CC = VP * 8;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  T* plane = reinterpret_cast<T*>(s_raw);
+  const int tid = threadIdx.x;
+  const int npix = a.H * a.W;
+  const int slices = a.C / CC;
+  const T* x = reinterpret_cast<const T*>(a.x);
+  for (int item = blockIdx.x; item < a.B * slices; item += gridDim.x) {
+    const int b = item / slices, c0 = (item - b * slices) * CC;
+    __syncthreads();
+    constexpr int U = 4;
+    for (int i0 = tid; i0 < npix * VP; i0 += 256 * U) {
+      Raw8<T> raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 256 * u;
+        if (i < npix * VP) raw_ld<T>(x + (static_cast<size_t>(b) * npix + i / VP) * a.C + c0 + (i % VP) * 8, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 256 * u;
+        if (i < npix * VP) {
+          float v[8];
+          raw_unpack(raw[u], v);
+          Vec8<T>::st(plane + static_cast<size_t>(i) * 8, v);
+        }
+      }
+    }
+    __syncthreads();
+    const int v = tid % VP;
+    const int cc = c0 + v * 8;
+#pragma unroll 1
+    for (int br = 0; br < 3; ++br) {
+      float wreg[9][8], sc[8], sh[8];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wreg[t][i] = a.w[br][t * a.C + cc + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sc[i] = a.scale[br][cc + i]; sh[i] = a.shift[br][cc + i]; }
+      const int d = a.rate[br];
+      T* y = reinterpret_cast<T*>(a.y[br]);
+      for (int p = tid / VP; p < npix; p += 256 / VP) {
+        const int py = p / a.W, px = p - py * a.W;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = py + (ky - 1) * d;
+          if (yy < 0 || yy >= a.H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = px + (kx - 1) * d;
+            if (xx < 0 || xx >= a.W) continue;
+            float xv[8];
+            Vec8<T>::ld(plane + (static_cast<size_t>(yy * a.W + xx) * VP + v) * 8, xv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[i], wreg[ky * 3 + kx][i], acc[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(fmaf(acc[i], sc[i], sh[i]), 0.f);
+        Vec8<T>::st(y + (static_cast<size_t>(b) * npix + p) * a.C + cc, acc);
+      }
+    }
+  }
+}
+
 static int pick_grid(long long work_blocks, int per_sm) {
   long long cap = static_cast<long long>(num_sms()) * per_sm;
   return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
@@ -1246,4 +1331,31 @@ extern "C" int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int
   else resize_feat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
   g_launches++;
   return check_launch("resize_feat_kernel");
+}
+
+extern "C" int dlb_aspp_dw3_fwd(int B, int H, int W, int C, int dtype, const void* x, const float* const* w,
+                                const int* rates, const float* const* scale, const float* const* shift,
+                                void* const* y, void* stream) {
+  DLB_REQUIRE(x && w && rates && scale && shift && y, "aspp_dw3_fwd: null pointer");
+  const int cc = dtype == DLB_F32 ? 8 : 16;
+  DLB_REQUIRE(C % cc == 0, "aspp_dw3_fwd: C must be a multiple of %d", cc);
+  const size_t smem = static_cast<size_t>(H) * W * 32;
+  if (smem > 200 * 1024) { set_last_error("aspp_dw3_fwd: %dx%d plane does not fit in shared memory", H, W); return DLB_ERR_UNSUPPORTED; }
+  AsppArgs a{};
+  a.B = B; a.H = H; a.W = W; a.C = C; a.x = x;
+  for (int i = 0; i < 3; ++i) { a.w[i] = w[i]; a.rate[i] = rates[i]; a.scale[i] = scale[i]; a.shift[i] = shift[i]; a.y[i] = y[i]; }
+  const int items = B * (C / cc);
+  const int grid = items < num_sms() ? items : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LA(TT)                                                                                              \
+  do {                                                                                                      \
+    DLB_CUDA(cudaFuncSetAttribute(aspp_dw3_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    aspp_dw3_kernel<TT><<<grid, 256, smem, st>>>(a);                                                        \
+  } while (0)
+  if (dtype == DLB_F16) LA(__half);
+  else if (dtype == DLB_BF16) LA(__nv_bfloat16);
+  else LA(float);
+#undef LA
+  g_launches++;
+  return check_launch("aspp_dw3_kernel");
 }

@@ -295,3 +295,17 @@ def resize_bilinear(x: torch.Tensor, y: torch.Tensor, C_: Optional[int] = None):
     L.check(L.lib().dlb_resize_bilinear(B, h, w, C_, y.shape[1], y.shape[2], y.stride(2), L.dt(x), x.data_ptr(),
                                         y.data_ptr(), L.stream_ptr()), "resize_bilinear")
     return y
+
+
+def aspp_dw3_fwd(x: torch.Tensor, ws, rates, scales, shifts, ys):
+    """Fused ASPP atrous depthwise stage: x [B,H,W,C] -> ys[0..2] (dw 3x3 at rates[i] + folded BN + ReLU)."""
+    B, H, W_, C_ = x.shape
+    P3 = C.c_void_p * 3
+    wv = P3(*[t.data_ptr() for t in ws])
+    sc = P3(*[t.data_ptr() for t in scales])
+    sh = P3(*[t.data_ptr() for t in shifts])
+    yv = P3(*[t.data_ptr() for t in ys])
+    rt = (C.c_int * 3)(*rates)
+    L.check(L.lib().dlb_aspp_dw3_fwd(B, H, W_, C_, L.dt(x), x.data_ptr(), wv, rt, sc, sh, yv, L.stream_ptr()),
+            "aspp_dw3_fwd")
+    return ys

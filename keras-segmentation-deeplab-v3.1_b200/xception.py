@@ -39,6 +39,7 @@ class XceptionEngine(Engine):
         super().__init__(input_shape=(H, W, 3), classes=classes, head="bare", compute_dtype=compute_dtype, device=device,
                          seed=seed)
         self.scale = 4
+        self.fused_aspp = True
         self._bufs: Dict = {}
         self._ones = torch.ones(2048, device=self.device)
         self._zeros = torch.zeros(2048, device=self.device)
@@ -213,8 +214,18 @@ class XceptionEngine(Engine):
         bn0 = self.aspp0_bn
         ops.pw_gemm(x, self.wcopies["aspp0"]["nk"], cat[..., 0:256], N=256, n_store=256, col_scale=bn0.fscale,
                     col_shift=bn0.fshift, act=ACT_RELU)
-        for i, sep in enumerate(self.aspp):
-            self._sepconv(f"aspp{i + 1}", x, sep, 1, self.atrous[i], True, out=cat[..., 256 * (i + 1):256 * (i + 2)])
+        if self.fused_aspp and fh * fw * 32 <= 200 * 1024:
+            # fused atrous depthwise stage: x is read once for the three rates (dlb_aspp_dw3_fwd)
+            dws = [self._buf(f"aspp{i + 1}/dw", B, fh, fw, 2048) for i in range(3)]
+            ops.aspp_dw3_fwd(x, [s_["dw"].params[0].data for s_ in self.aspp], list(self.atrous),
+                             [s_["dw_bn"].fscale for s_ in self.aspp], [s_["dw_bn"].fshift for s_ in self.aspp], dws)
+            for i, sep in enumerate(self.aspp):
+                pwbn = sep["pw_bn"]
+                ops.pw_gemm(dws[i], self.wcopies[sep["pw"].name]["nk"], cat[..., 256 * (i + 1):256 * (i + 2)], N=256,
+                            n_store=256, col_scale=pwbn.fscale, col_shift=pwbn.fshift, act=ACT_RELU)
+        else:
+            for i, sep in enumerate(self.aspp):
+                self._sepconv(f"aspp{i + 1}", x, sep, 1, self.atrous[i], True, out=cat[..., 256 * (i + 1):256 * (i + 2)])
         feat = self._buf("aspp_out", B, fh, fw, 256)
         ops.pw_gemm(cat, wcp["nk"][:, 256:], feat, col_scale=cbn.fscale, col_shift=cbn.fshift, row_bias=rowbias,
                     rows_per_img=fh * fw, act=ACT_RELU)
