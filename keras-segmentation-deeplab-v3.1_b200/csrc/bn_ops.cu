@@ -276,6 +276,76 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
   }
 }
 
+// fp16 specialisation of the apply pass: mask and x-hat on packed half2, the projection
+// dz - mean(dz) - xhat * mean(dz * xhat) in fp32 (the mean terms are far below one fp16 ulp of dz)
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0) {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      if (a.dbeta) a.dbeta[c] = static_cast<float>(a.red[c]);
+      if (a.dgamma) a.dgamma[c] = static_cast<float>(a.red[a.C + c]);
+    }
+  }
+  if (tid >= a.rpb * a.cv) return;
+  const int r_in = tid / a.cv;
+  const int c0 = (tid - r_in * a.cv) * 8;
+  __half2 sc2[4], sh2[4], mu2[4], rs2[4];
+  float sc[8], k1[8], k2[8];
+  const float invM = 1.f / static_cast<float>(a.M);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sc2[k] = __floats2half2_rn(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
+    sh2[k] = __floats2half2_rn(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
+    mu2[k] = __floats2half2_rn(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
+    rs2[k] = __floats2half2_rn(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = a.scale[c0 + k];
+    k1[k] = a.frozen ? 0.f : static_cast<float>(a.red[c0 + k]) * invM;
+    k2[k] = a.frozen ? 0.f : static_cast<float>(a.red[a.C + c0 + k]) * invM;
+  }
+  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+  const __half* x = reinterpret_cast<const __half*>(a.x);
+  const __half* da = reinterpret_cast<const __half*>(a.da);
+  __half* dx = reinterpret_cast<__half*>(a.dx);
+  const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
+  constexpr int U = 4;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+    BH8 xv[U], gv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r < a.M) {
+        xv[u] = *reinterpret_cast<const BH8*>(x + r * a.C + c0);
+        gv[u] = *reinterpret_cast<const BH8*>(da + r * a.C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * rstride;
+      if (r >= a.M) continue;
+      BH8 o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half2 dz = gv[u].h[k];
+        if (a.act != DLB_ACT_NONE) {
+          const __half2 z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
+          __half2 m = __hgt2(z, zero2);
+          if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
+          dz = __hmul2(dz, m);
+        }
+        const float2 dzf = __half22float2(dz);
+        const float2 xh = __half22float2(__hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]));
+        const float o0 = sc[2 * k] * (dzf.x - k1[2 * k] - xh.x * k2[2 * k]);
+        const float o1 = sc[2 * k + 1] * (dzf.y - k1[2 * k + 1] - xh.y * k2[2 * k + 1]);
+        o.h[k] = __floats2half2_rn(o0, o1);
+      }
+      *reinterpret_cast<BH8*>(dx + r * a.C + c0) = o;
+    }
+  }
+}
+
 // global average pool over HW of act(x*scale+shift): out[b, c] (+)= partial means (out pre-zeroed)
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(int HW, int C, int cv, int rpb, int splits, const T* x,
@@ -431,7 +501,8 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   long long cap = static_cast<long long>(num_sms()) * 6;
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
+  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<<<grid, 256, 0, st>>>(a);
+  else if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(a);
   g_launches++;

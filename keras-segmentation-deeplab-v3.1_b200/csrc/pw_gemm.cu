@@ -80,6 +80,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   float* s_shift = s_scale + npad;
   float* s_sum = s_shift + npad;
   float* s_sqs = s_sum + npad;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_sqs + npad) + 15) & ~uintptr_t(15));   // 8 warps x 4 KB
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -161,16 +162,23 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
-    // Two warps per TMEM lane quarter; each takes every other 32-column block of the accumulator group.  The
-    // epilogue is latency bound (tcgen05.ld -> math -> shuffles -> st.global, one warp per scheduler), so each
-    // iteration keeps two independent 16-column chains in flight.
+    // Two warps per TMEM lane quarter; each takes every other 64-column block of the accumulator group.
+    //  * thread = accumulator row: tcgen05.ld (2 x 16 columns in flight) -> BN-affine / per-image bias -> BatchNorm
+    //    statistics (recursive-halving warp reduction) -> activation
+    //  * 16-bit outputs are staged through a swizzled 32 x 64 shared-memory tile per warp and written back with
+    //    4 rows x 128 B per instruction (a thread-per-row store costs 32 L1 wavefronts per 512 B; ncu showed the LSU
+    //    pipe, not HBM, bounding the wide expand / dgrad GEMMs); the residual is added in that coalesced phase.
     const int quad = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;           // which 32-column blocks
+    const int half = (warp - 2) >> 2;           // which 64-column blocks
     const bool do_stats = g.stat_sum != nullptr;
     const int red_col = reduce16_col_of_lane(lane);
+    constexpr bool kStaged = sizeof(OutT) == 2;
+    uint4* stg = reinterpret_cast<uint4*>(s_stage) + static_cast<size_t>(warp - 2) * 32 * 8;   // [32 rows][8 chunks of 16 B]
+    const bool staged = kStaged && g.shuffle_r == 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
-      const int m = tile * kBlockM + quad * 32 + lane;
+      const int m_base = tile * kBlockM + quad * 32;
+      const int m = m_base + lane;
       const bool row_ok = m < g.M;
       const float* rb = nullptr;
       if (g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
@@ -192,74 +200,117 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after();
         const int gcols = chunks * g.chunk_n;
         const int col_base = grp * group_rows;
-        for (int j = half * 32; j < gcols; j += 64) {
-          const bool two = j + 16 < gcols;
-          uint32_t r[2][16];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j;
-          tmem_ld16(taddr, r[0]);
-          if (two) tmem_ld16(taddr + 16, r[1]);
-          tmem_ld_wait();
-          float v[2][16];
+        for (int j64 = half * 64; j64 < gcols; j64 += 128) {
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            const int j = j64 + sub * 32;
+            if (j >= gcols) break;
+            const bool two = j + 16 < gcols;
+            uint32_t r[2][16];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j;
+            tmem_ld16(taddr, r[0]);
+            if (two) tmem_ld16(taddr + 16, r[1]);
+            tmem_ld_wait();
+            float v[2][16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int n0 = col_base + j + h * 16;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(r[h][i]) * s_scale[n0 + i] + s_shift[n0 + i];
-              if (rb && n0 + i < g.N) x += rb[n0 + i];
-              v[h][i] = (h == 0 || two) ? x : 0.f;
-            }
-          }
-          if (do_stats) {
-            float s1[2][16], s2[2][16];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h) {
+              const int n0 = col_base + j + h * 16;
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float q = row_ok ? Act<OutT>::rnd(v[h][i]) : 0.f;
-                s1[h][i] = q; s2[h][i] = q * q;
+                float x = __uint_as_float(r[h][i]);
+                if (g.col_scale || g.col_shift) x = fmaf(x, s_scale[n0 + i], s_shift[n0 + i]);
+                if (rb && n0 + i < g.N) x += rb[n0 + i];
+                v[h][i] = (h == 0 || two) ? x : 0.f;
               }
-            const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
-            const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
-            if ((lane & 1) == 0) {
-              const int n0 = col_base + j;
-              atomicAdd(&s_sum[n0 + red_col], t1a);
-              atomicAdd(&s_sqs[n0 + red_col], t2a);
-              if (two) {
-                atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
-                atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
+            }
+            if (do_stats) {
+              float s1[2][16], s2[2][16];
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float q = row_ok ? v[h][i] : 0.f;
+                  s1[h][i] = q; s2[h][i] = q * q;
+                }
+              const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
+              const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
+              if ((lane & 1) == 0) {
+                const int n0 = col_base + j;
+                atomicAdd(&s_sum[n0 + red_col], t1a);
+                atomicAdd(&s_sqs[n0 + red_col], t2a);
+                if (two) {
+                  atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
+                  atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
+                }
+              }
+            }
+            if (staged) {
+              // pack to 16 bit and park in the swizzled staging tile: chunk c of row `lane` -> slot c ^ (lane & 7)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = apply_act(v[c >> 1][(c & 1) * 8 + i], g.act);
+                uint4 pk;
+                Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
+                stg[lane * 8 + ((sub * 4 + c) ^ (lane & 7))] = pk;
+              }
+            } else if (row_ok) {
+#pragma unroll
+              for (int h8 = 0; h8 < 4; ++h8) {
+                const int n = col_base + j + h8 * 8;
+                if (n >= g.n_store || (h8 >= 2 && !two)) continue;
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
+                if (g.R) {
+                  float rr[8];
+                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o[i] += rr[i];
+                }
+                OutT* dst;
+                if (g.shuffle_r > 0) {
+                  const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
+                  const int jj = n / rowlen, rem = n - jj * rowlen;
+                  dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
+                        static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
+                } else {
+                  dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
+                }
+                if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
+                } else {
+                  Vec8<OutT>::st(dst, o);
+                }
               }
             }
           }
-          if (row_ok) {
+          if (staged) {
+            __syncwarp();
+            // coalesced write-back: 8 lanes cover the 128 B of one row, 4 rows per instruction
+            const int cchunk = lane & 7;
+            const int n = col_base + j64 + cchunk * 8;
 #pragma unroll
-            for (int h8 = 0; h8 < 4; ++h8) {
-              const int n = col_base + j + h8 * 8;
-              if (n >= g.n_store || (h8 >= 2 && !two)) continue;
-              float o[8];
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);
+              const int mm = m_base + row;
+              if (mm < g.M && n < g.n_store && j64 + cchunk * 8 < gcols) {
+                uint4 pk = stg[row * 8 + (cchunk ^ (row & 7))];
+                OutT* dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(mm) * g.ldc + n;
+                if (g.R) {
+                  float o[8], rr[8];
+                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
+                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(mm) * g.ldr + n, rr);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
-              if (g.R) {
-                float rr[8];
-                Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] += rr[i];
-              }
-              OutT* dst;
-              if (g.shuffle_r > 0) {
-                const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
-                const int jj = n / rowlen, rem = n - jj * rowlen;
-                dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
-                      static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
-              } else {
-                dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
-              }
-              if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
-                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
-              } else {
-                Vec8<OutT>::st(dst, o);
+                  for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                  Vec8<OutT>::st(dst, o);
+                } else {
+                  *reinterpret_cast<uint4*>(dst) = pk;
+                }
               }
             }
+            __syncwarp();
           }
         }
         tc_fence_before();
@@ -440,7 +491,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.num_k_blocks = (p->K + 63) / 64;
   g.num_m_tiles = (p->M + kBlockM - 1) / kBlockM;
   g.stage_bytes = kABytes + g.acc_cols * kSwzBytes;
-  const int smem_budget = 200 * 1024;
+  const int smem_budget = 168 * 1024;      // + 32 KB epilogue staging + barriers / per-column vectors
   g.num_stages = smem_budget / g.stage_bytes;
   if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
   if (g.num_stages < 2) g.num_stages = 2;
@@ -452,7 +503,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, 64);
   if (rc) return rc;
 
-  const size_t tail = (2 * kMaxStages + 4) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4;
+  const size_t tail = (2 * kMaxStages + 4) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 + 8 * 4096;
   const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
   const int grid = g.num_m_tiles < num_sms() ? g.num_m_tiles : num_sms();
 

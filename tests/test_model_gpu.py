@@ -234,6 +234,11 @@ def test_gradients_fp32_match_oracle_autograd():
             err = rel(p.grad.cpu() / e.loss_scale, gref)
             if err > max(2e-3, 5 * floor):
                 bad.append((rec.name, i, err, floor))
+    if bad:
+        import json
+        os.makedirs(os.path.join(os.path.dirname(GOLD), '..', 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(os.path.dirname(GOLD), '..', 'gpurun_out', 'grad_fail.json'), 'w') as f:
+            json.dump(bad, f)
     assert not bad, bad[:10]
 
 
