@@ -304,7 +304,11 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_kernel(const DwTileArgs a
   int cur_chunk = -1;
   T* y = reinterpret_cast<T*>(a.y);
   const int per_chunk = a.B * a.tiles_y * a.tiles_x;
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
+  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int chunk = tile / per_chunk;
     int r = tile - chunk * per_chunk;
     const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
@@ -434,7 +438,11 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs
     }
   };
 
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
+  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int chunk = tile / per_chunk;
     int r = tile - chunk * per_chunk;
     const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
@@ -578,7 +586,11 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_h_kernel(const DwTileArgs
     }
   };
 
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
+  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int chunk = tile / per_chunk;
     int r = tile - chunk * per_chunk;
     const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
@@ -687,7 +699,11 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileAr
     }
   };
 
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
+  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int chunk = tile / per_chunk;
     int r = tile - chunk * per_chunk;
     const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -223,7 +224,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 v[h][i] = (h == 0 || two) ? x : 0.f;
               }
             }
-            if (do_stats) {
+            if (do_stats && !staged) {
               float s1[2][16], s2[2][16];
 #pragma unroll
               for (int h = 0; h < 2; ++h)
@@ -250,7 +251,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int c = 0; c < 4; ++c) {
                 float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = apply_act(v[c >> 1][(c & 1) * 8 + i], g.act);
+                for (int i = 0; i < 8; ++i) o[i] = (do_stats && !row_ok) ? 0.f : v[c >> 1][(c & 1) * 8 + i];
                 uint4 pk;
                 Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
                 stg[lane * 8 + ((sub * 4 + c) ^ (lane & 7))] = pk;
@@ -288,6 +289,31 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           if (staged) {
             __syncwarp();
+            if (do_stats) {
+              // BatchNorm statistics of the (rounded, pre-activation) tile: lane owns 2 adjacent columns, walks the
+              // 32 rows of the staging tile (conflict-free: a warp reads one 128-byte row per step)
+              const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
+              const int chunk = lane >> 2, wsel = lane & 3;
+              float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll 8
+              for (int row = 0; row < 32; ++row) {
+                const uint32_t wv = words[row * 32 + ((chunk ^ (row & 7)) << 2) + wsel];
+                float fa, fb;
+                if (sizeof(OutT) == 2 && std::is_same<OutT, __half>::value) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv));
+                  fa = f.x; fb = f.y;
+                } else {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+                  fa = f.x; fb = f.y;
+                }
+                sa += fa; sb += fb; qa = fmaf(fa, fa, qa); qb = fmaf(fb, fb, qb);
+              }
+              const int jc = j64 + 2 * lane;
+              if (jc < gcols) {
+                atomicAdd(&s_sum[col_base + jc], sa); atomicAdd(&s_sum[col_base + jc + 1], sb);
+                atomicAdd(&s_sqs[col_base + jc], qa); atomicAdd(&s_sqs[col_base + jc + 1], qb);
+              }
+            }
             // coalesced write-back: 8 lanes cover the 128 B of one row, 4 rows per instruction
             const int cchunk = lane & 7;
             const int n = col_base + j64 + cchunk * 8;
@@ -298,12 +324,17 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (mm < g.M && n < g.n_store && j64 + cchunk * 8 < gcols) {
                 uint4 pk = stg[row * 8 + (cchunk ^ (row & 7))];
                 OutT* dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(mm) * g.ldc + n;
-                if (g.R) {
-                  float o[8], rr[8];
+                if (g.R || g.act != DLB_ACT_NONE) {
+                  float o[8];
                   Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
-                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(mm) * g.ldr + n, rr);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                  for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                  if (g.R) {
+                    float rr[8];
+                    Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(mm) * g.ldr + n, rr);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                  }
                   Vec8<OutT>::st(dst, o);
                 } else {
                   *reinterpret_cast<uint4*>(dst) = pk;

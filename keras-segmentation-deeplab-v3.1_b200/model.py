@@ -359,6 +359,66 @@ class Model:
         jac, acc = _metrics_from_confusion(conf.cpu().numpy(), e.n_out)
         return [float(score.mean().item()), jac, acc]
 
+    def _train_pipelined(self, batches, max_steps):
+        """Software-pipelined training loop: the host->device copy of batch i+1 (copy stream, double-buffered
+        device slots) overlaps the captured step of batch i, and the loss / confusion read-back of step i happens
+        after step i+1 has been enqueued.  Yields [loss, Jaccard, accuracy] per step, in order."""
+        if self.optimizer is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        e = self.engine
+        dev = e.device
+        main = torch.cuda.current_stream()
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream()
+        slots = getattr(self, "_slots", None)
+        pending = None
+
+        def finish(p):
+            vals = torch.stack([p["loss"][0], p["wcount"][0]]).cpu().numpy()
+            loss = float(vals[0] / vals[1]) if vals[1] > 0 else float("nan")
+            jac, acc = _metrics_from_confusion(p["conf"].cpu().numpy(), e.n_out)
+            return [loss, jac, acc]
+
+        for i, batch in enumerate(batches):
+            if i >= max_steps:
+                break
+            x, y, sw = self._unpack(batch)
+            if isinstance(sw, dict):
+                sw = sw.get("pred_mask", next(iter(sw.values())))
+            xt = x if torch.is_tensor(x) else self._stage(("x", i % 2), x)
+            yt = y if torch.is_tensor(y) else self._stage(("y", i % 2), y)
+            swt = None if sw is None else (sw if torch.is_tensor(sw) else self._stage(("sw", i % 2), sw))
+            B = xt.shape[0]
+            if slots is None or slots[0]["img"].shape[0] != B:
+                slots = self._slots = [dict(img=torch.empty(B, e.H, e.W, 3, device=dev),
+                                            labels=torch.empty(B, e.H * e.W, 1, device=dev),
+                                            sw=torch.empty(B, e.H * e.W, device=dev),
+                                            ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+                for sl in slots:
+                    sl["free"].record(main)
+            sl = slots[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(sl["free"])
+                sl["img"].copy_(xt, non_blocking=True)
+                sl["labels"].copy_(yt.view(B, -1, 1), non_blocking=True)
+                if swt is not None:
+                    sl["sw"].copy_(swt.view(B, -1), non_blocking=True)
+                sl["ready"].record(copy_stream)
+            main.wait_event(sl["ready"])
+            loss_sum, wcount = e.train_step(sl["img"], sl["labels"], sl["sw"] if swt is not None else None,
+                                            dropout=self.dropout_in_training)
+            sl["free"].record(main)
+            ws = e.workspace(B, True)
+            conf = torch.zeros(B, e.n_out + 1, e.n_out, device=dev, dtype=torch.int64)
+            ops.confusion(ws["labels"], ws["argmax"], e.n_out, conf)
+            cur = dict(loss=loss_sum.clone(), wcount=wcount.clone(), conf=conf)
+            if pending is not None:
+                yield finish(pending)
+            pending = cur
+        if pending is not None:
+            yield finish(pending)
+
     @staticmethod
     def _unpack(batch):
         if len(batch) == 3:
@@ -380,11 +440,7 @@ class Model:
             agg = np.zeros(3)
             cnt = 0
             it = (generator[i] for i in range(steps)) if hasattr(generator, "__getitem__") else generator
-            for step, batch in enumerate(it):
-                if step >= steps:
-                    break
-                x, y, sw = self._unpack(batch)
-                vals = self.train_on_batch(x, y, sw)
+            for vals in self._train_pipelined(it, steps):
                 agg += np.nan_to_num(np.array(vals))
                 cnt += 1
             logs = {n: v for n, v in zip(self.metrics_names, agg / max(cnt, 1))}
