@@ -849,24 +849,31 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemArgs a) {
   }
 }
 
-// stem weight gradient: one thread per (tap*ci, co) pair, CTA loops over a slab of output pixels staged in smem
+// stem weight gradient dW[27, 32] = sum_pixels xcol[pix, 27] * dy[pix, 32], register blocked:
+// 224 threads = 4 pixel groups x (7 tap groups of 4) x (8 output-channel groups of 4), 16 accumulators each;
+// a CTA stages 64-pixel slabs of the (preprocessed, padded) 27-tap patch matrix and of dy in shared memory.
 template <typename T>
-__global__ void __launch_bounds__(864) stem_wgrad_kernel(int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+__global__ void __launch_bounds__(224) stem_wgrad_kernel(int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
                                                          const float* __restrict__ x, const T* __restrict__ dy,
                                                          float* __restrict__ dw, long long npix) {
   constexpr int PIX = 64;
-  __shared__ float s_x[PIX][28];
-  __shared__ float s_dy[PIX][32];
+  __shared__ __align__(16) float s_x[PIX][28];
+  __shared__ __align__(16) float s_dy[PIX][32];
   const int tid = threadIdx.x;
-  const int tap = tid >> 5, co = tid & 31;   // tap in 0..26 = (ky*3+kx)*3+ci
-  float acc = 0.f;
+  const int pg = tid / 56, rem = tid - pg * 56;
+  const int tg = rem >> 3, cg = rem & 7;       // taps tg*4.., output channels cg*4..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long long p0 = static_cast<long long>(blockIdx.x) * PIX; p0 < npix; p0 += static_cast<long long>(gridDim.x) * PIX) {
     __syncthreads();
-    for (int i = tid; i < PIX * 27; i += blockDim.x) {
-      const int p = i / 27, t = i - p * 27;
+    for (int i = tid; i < PIX * 28; i += 224) {
+      const int p = i / 28, t = i - p * 28;
       const long long pix = p0 + p;
       float v = 0.f;
-      if (pix < npix) {
+      if (pix < npix && t < 27) {
         const int wo = static_cast<int>(pix % Wo);
         const long long t1 = pix / Wo;
         const int ho = static_cast<int>(t1 % Ho);
@@ -877,16 +884,34 @@ __global__ void __launch_bounds__(864) stem_wgrad_kernel(int B, int H, int W, in
       }
       s_x[p][t] = v;
     }
-    for (int i = tid; i < PIX * 32; i += blockDim.x) {
-      const int p = i >> 5, c = i & 31;
+    for (int i = tid; i < PIX * 4; i += 224) {
+      const int p = i >> 2, c8 = (i & 3) * 8;
       const long long pix = p0 + p;
-      s_dy[p][c] = pix < npix ? Act<T>::ld(dy + static_cast<size_t>(pix) * 32 + c) : 0.f;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (pix < npix) Vec8<T>::ld(dy + static_cast<size_t>(pix) * 32 + c8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_dy[p][c8 + k] = v[k];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int p = 0; p < PIX; ++p) acc = fmaf(s_x[p][tap], s_dy[p][co], acc);
+#pragma unroll 4
+    for (int pp = 0; pp < PIX / 4; ++pp) {
+      const int p = pg * (PIX / 4) + pp;
+      const float4 xv = *reinterpret_cast<const float4*>(&s_x[p][tg * 4]);
+      const float4 gv = *reinterpret_cast<const float4*>(&s_dy[p][cg * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
+    }
   }
-  atomicAdd(&dw[tap * 32 + co], acc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tap = tg * 4 + i;
+    if (tap >= 27) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&dw[tap * 32 + cg * 4 + j], acc[i][j]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1288,14 +1313,14 @@ extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, con
   const int pt = (Ho - 1) * 2 + 3 - H, pl = (Wo - 1) * 2 + 3 - W;
   const int pad_t = (pt > 0 ? pt : 0) / 2, pad_l = (pl > 0 ? pl : 0) / 2;
   const long long npix = static_cast<long long>(B) * Ho * Wo;
-  const int grid = pick_grid((npix + 63) / 64, 2);
+  const int grid = pick_grid((npix + 63) / 64, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == DLB_F16)
-    stem_wgrad_kernel<__half><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
+    stem_wgrad_kernel<__half><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
   else if (dtype == DLB_BF16)
-    stem_wgrad_kernel<__nv_bfloat16><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __nv_bfloat16*)dy, dw, npix);
+    stem_wgrad_kernel<__nv_bfloat16><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __nv_bfloat16*)dy, dw, npix);
   else
-    stem_wgrad_kernel<float><<<grid, 864, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
+    stem_wgrad_kernel<float><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
   g_launches++;
   return check_launch("stem_wgrad_kernel");
 }
