@@ -757,6 +757,297 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileAr
   if (cur_chunk >= 0) flush(cur_chunk);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged, double-buffered fp16 depthwise kernels.  One cp.async.bulk.tensor (4D box [ih, iw, 64 ch], zero fill
+// outside the image = the convolution's padding) brings in the halo tile of the NEXT output tile while the current
+// one is being computed; the consumer-side BatchNorm+ReLU6 prologue is an in-place pass over the landed tile.
+// (The register-staged version above spends most of a tile's time waiting on its own loads: 2 CTAs/SM, no overlap.)
+// ---------------------------------------------------------------------------------------------
+int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w, int box_h);
+
+__device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int tile, int& chunk, int& b, int& oy0, int& ox0) {
+  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
+  chunk = tile / per_chunk;
+  int r = tile - chunk * per_chunk;
+  b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
+  const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+  oy0 = ty * kTH; ox0 = tx * kTW;
+}
+
+__device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, H8* s_in, int oy0, int ox0, int c0, bool cv_ok) {
+  // in place: a = act(x * scale + shift) inside the image, exact zeros in the padding
+  const int tid = threadIdx.x, v = tid & 7;
+  const int cc = c0 + v * 8;
+  if (!cv_ok) return;
+  __half2 sc2[4], sh2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc2[i] = __floats2half2_rn(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
+    sh2[i] = __floats2half2_rn(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
+  }
+  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
+  const int npos = a.ih * a.iw;
+  for (int p = tid >> 3; p < npos; p += 32) {
+    const int py = p / a.iw, px = p - py * a.iw;
+    const int gy = gy0 + py, gx = gx0 + px;
+    H8 o;
+    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+      o = s_in[static_cast<size_t>(p) * kCV + v];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __half2 z = __hfma2(o.h[i], sc2[i], sh2[i]);
+        if (a.in_act == DLB_ACT_RELU6) z = __hmin2(__hmax2(z, zero2), six2);
+        else if (a.in_act == DLB_ACT_RELU) z = __hmax2(z, zero2);
+        o.h[i] = z;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o.h[i] = zero2;
+    }
+    s_in[static_cast<size_t>(p) * kCV + v] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
+  const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
+  H8* bufs[2] = {reinterpret_cast<H8*>(s_raw), reinterpret_cast<H8*>(s_raw + buf_stride)};
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
+  float* s_stats = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [2][64]
+  const int tid = threadIdx.x, v = tid & 7;
+  const bool stats = a.stat_sum != nullptr;
+  const bool pro = a.in_scale != nullptr;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  __half2 w2[9][4];
+  float ssum[8], ssqs[8];
+  int off[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+  int cur_chunk = -1;
+  __half* y = reinterpret_cast<__half*>(a.y);
+
+  auto flush_stats = [&](int chunk) {
+    __syncthreads();
+    if (tid < 128) s_stats[tid] = 0.f;
+    __syncthreads();
+    if (chunk * 64 + v * 8 < a.C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
+    }
+    __syncthreads();
+    if (tid < 64 && chunk * 64 + tid < a.C) {
+      atomicAdd(&a.stat_sum[chunk * 64 + tid], static_cast<double>(s_stats[tid]));
+      atomicAdd(&a.stat_sqs[chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
+    }
+  };
+  auto issue = [&](int tile, int slot) {
+    int chunk, b, oy0, ox0;
+    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    mbar_expect_tx(&full[slot], tile_bytes);
+    tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
+  };
+
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  if (tid == 0 && tile_begin < tile_end) issue(tile_begin, 0);
+  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+    const int slot = it & 1;
+    int chunk, b, oy0, ox0;
+    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
+      cur_chunk = chunk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
+      if (cv_ok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int ts = a.flip ? 8 - t : t;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
+        }
+      }
+    }
+    // prefetch the next tile into the other buffer (free since the __syncthreads that ended the previous iteration)
+    if (tid == 0 && tile + 1 < tile_end) issue(tile + 1, slot ^ 1);
+    mbar_wait(&full[slot], (it >> 1) & 1);
+    H8* s_in = bufs[slot];
+    if (pro) {
+      dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
+      __syncthreads();
+    }
+    if (cv_ok) {
+#pragma unroll 2
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int oy = q / kTW, ox = q - oy * kTW;
+        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
+        const H8* base = s_in + static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          __half2 racc[4];
+          {
+            const H8 xv = base[off[ky * 3]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) racc[i] = __hmul2(xv.h[i], w2[ky * 3][i]);
+          }
+#pragma unroll
+          for (int kx = 1; kx < 3; ++kx) {
+            const H8 xv = base[off[ky * 3 + kx]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
+        if (a.out_scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], a.out_scale[cc + i], a.out_shift[cc + i]), a.out_act);
+        }
+        if (stats) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssqs[i] = fmaf(acc[i], acc[i], ssqs[i]); }
+        }
+        H8 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc) = o;
+      }
+    }
+    if (pro) fence_proxy_async();     // generic-proxy writes of the transform vs the TMA that will refill this buffer
+    __syncthreads();
+  }
+  if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
+}
+
+__global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
+  const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
+  H8* bufs[2] = {reinterpret_cast<H8*>(s_raw), reinterpret_cast<H8*>(s_raw + buf_stride)};
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
+  float* s_dw = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [9][64]
+  const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
+  const bool pro = a.in_scale != nullptr;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  float acc[9][8];
+  int off[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+  int cur_chunk = -1;
+  const __half* dy = reinterpret_cast<const __half*>(a.dy);
+
+  auto flush = [&](int chunk) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = acc[t][i];
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        acc[t][i] = x;
+      }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) s_dw[i] = 0.f;
+    __syncthreads();
+    if (lane < 8) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * 64 + v * 8 + i], acc[t][i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 9 * 64; i += 256) {
+      const int t = i >> 6, c = chunk * 64 + (i & 63);
+      if (c < a.C) atomicAdd(&a.dw[t * a.C + c], s_dw[i]);
+    }
+  };
+  auto issue = [&](int tile, int slot) {
+    int chunk, b, oy0, ox0;
+    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    mbar_expect_tx(&full[slot], tile_bytes);
+    tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
+  };
+
+  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
+  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
+  if (tid == 0 && tile_begin < tile_end) issue(tile_begin, 0);
+  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+    const int slot = it & 1;
+    int chunk, b, oy0, ox0;
+    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    const int c0 = chunk * 64, cc = c0 + v * 8;
+    const bool cv_ok = cc < a.C;
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0) flush(cur_chunk);
+      cur_chunk = chunk;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    }
+    if (tid == 0 && tile + 1 < tile_end) issue(tile + 1, slot ^ 1);
+    // the thread's four dy vectors are requested before waiting for the input tile
+    constexpr int NP = (kTH * kTW) / 32;
+    H8 g[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int q = (tid >> 3) + 32 * j;
+      const int oy = q / kTW, ox = q - oy * kTW;
+      if (cv_ok && oy0 + oy < a.Ho && ox0 + ox < a.Wo)
+        g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
+      }
+    }
+    mbar_wait(&full[slot], (it >> 1) & 1);
+    H8* s_in = bufs[slot];
+    if (pro) {
+      dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
+      __syncthreads();
+    }
+    if (cv_ok) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        __half2 p2[4];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const int q = (tid >> 3) + 32 * j;
+          const int oy = q / kTW, ox = q - oy * kTW;
+          const H8 xv = s_in[static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v + off[t]];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) p2[i] = j == 0 ? __hmul2(xv.h[i], g[j].h[i]) : __hfma2(xv.h[i], g[j].h[i], p2[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(p2[i]); acc[t][2 * i] += f.x; acc[t][2 * i + 1] += f.y; }
+      }
+    }
+    if (pro) fence_proxy_async();
+    __syncthreads();
+  }
+  if (cur_chunk >= 0) flush(cur_chunk);
+}
+
 static void fill_tile_geometry(DwTileArgs& a) {
   a.tiles_y = (a.Ho + kTH - 1) / kTH;
   a.tiles_x = (a.Wo + kTW - 1) / kTW;
@@ -1153,13 +1444,17 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024)
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
-    if (smem > 48 * 1024)
-      DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm_h = smem > 100 * 1024 ? 1 : 2;
+    const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
+    const size_t smem_t = 2 * tile_b + 16 + 128 * sizeof(float);
+    CUtensorMap tm;
+    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw, a.ih);
+    if (rc) return rc;
+    DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    const int per_sm_h = smem_t > 110 * 1024 ? 1 : 2;
     const int cap_h = num_sms() * per_sm_h;
-    dw_fwd_tiled_h_kernel<<<a.num_tiles < cap_h ? a.num_tiles : cap_h, 256, smem, st>>>(a);
+    dw_fwd_tma_h_kernel<<<a.num_tiles < cap_h ? a.num_tiles : cap_h, 256, smem_t, st>>>(tm, a);
     g_launches++;
-    return check_launch("dw_fwd_tiled_h_kernel");
+    return check_launch("dw_fwd_tma_h_kernel");
   }
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   const int cap = num_sms() * per_sm;
@@ -1179,11 +1474,15 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
   const int cap = num_sms();           // 1 CTA/SM (72 accumulators + staging need ~200 registers)
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
   if (std::is_same<T, __half>::value) {
-    if (smem > 48 * 1024)
-      DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dw_wgrad_tiled_h_kernel<<<grid, 256, smem, st>>>(a);
+    const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
+    const size_t smem_t = 2 * tile_b + 16 + 9 * 64 * sizeof(float);
+    CUtensorMap tm;
+    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw, a.ih);
+    if (rc) return rc;
+    DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    dw_wgrad_tma_h_kernel<<<grid, 256, smem_t, st>>>(tm, a);
     g_launches++;
-    return check_launch("dw_wgrad_tiled_h_kernel");
+    return check_launch("dw_wgrad_tma_h_kernel");
   }
   dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
   g_launches++;

@@ -497,6 +497,30 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t rows, ui
   return DLB_OK;
 }
 
+// NHWC activation tensor [B, H, W, C] as a 4D tensor map (dims innermost first: C, W, H, B), un-swizzled boxes
+// [1, box_h, box_w, box_c]; out-of-bounds coordinates (negative or past the edge) are zero-filled = conv padding
+int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w,
+                   int box_h) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled driver entry point unavailable"); return DLB_ERR_CUDA; }
+  const cuuint64_t es = dtype_size(dtype);
+  CUtensorMapDataType dt = dtype == DLB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                         : dtype == DLB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4D) failed (%d): B=%d H=%d W=%d C=%d box=%dx%dx%d", (int)r, B, H, W, C, box_h,
+                   box_w, box_c);
+    return DLB_ERR_CUDA;
+  }
+  return DLB_OK;
+}
+
 static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   GemmArgs g{};
   g.M = p->M; g.N = p->N; g.K = p->K;

@@ -84,3 +84,22 @@ ops.bn_bwd, ops.dw_conv_bwd, ops.pw_wgrad = bn_bwd, dw_bwd, pw_wgrad
 e.backward(ws, B, dropout=False)
 torch.cuda.synchronize()
 print("debug_bwd done:", cnt[0], "bn_bwd calls checked")
+
+# ---- forward comparison against the oracle (training-mode taps) and final gradient comparison
+from oracle import train as T
+W = N.random_mobilenetv2_weights(seed=11, head="conv_upsample")
+tap = {}
+Wd_ = {k: [t.double() for t in v] for k, v in W.items()}
+_, _, ctx = N.deeplabv3_forward(Wd_, torch.from_numpy(x).double(), training=True, tap=tap)
+for i in range(17):
+    name = f"expanded_conv_{i}_out" if i else "expanded_conv_out"
+    print(f"fwd x{i + 1} vs oracle: {rel(ws[f'x{i + 1}'].cpu(), tap[name]):.2e}")
+print("feat:", rel(ws["feat"].cpu(), tap["features"]), "logits:", rel(ws["logits"][..., :21].cpu(), tap["logits"]))
+loss, grads, _, _ = T.loss_and_grads(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw))
+for rec in e.layers:
+    for i, p in enumerate(rec.params):
+        if p.trainable_kind:
+            gref = grads[rec.name][i].reshape(p.shape)
+            er = rel(p.grad.cpu() / e.loss_scale, gref)
+            if er > 2e-3 and gref.abs().max() > 1e-9:
+                print(f"grad {rec.name}[{i}] vs oracle: {er:.2e} (|g| {gref.abs().max():.2e})")
