@@ -765,10 +765,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileAr
 // ---------------------------------------------------------------------------------------------
 int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w, int box_h);
 
-__device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int tile, int& chunk, int& b, int& oy0, int& ox0) {
-  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
-  chunk = tile / per_chunk;
-  int r = tile - chunk * per_chunk;
+__device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int r, int& b, int& oy0, int& ox0) {
   b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
   const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
   oy0 = ty * kTH; ox0 = tx * kTW;
@@ -849,20 +846,24 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
       atomicAdd(&a.stat_sqs[chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
     }
   };
-  auto issue = [&](int tile, int slot) {
-    int chunk, b, oy0, ox0;
-    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+  // CTA -> (channel chunk, spatial group): neighbouring CTAs work on the different 64-channel chunks of the SAME
+  // spatial tiles at the same time, so the 128-byte pieces of one pixel row are requested together (DRAM page
+  // locality), while a CTA keeps its chunk -- filter taps, statistics / gradient accumulators -- for its lifetime.
+  const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
+  const int n_sp = a.B * a.tiles_y * a.tiles_x;
+  auto issue = [&](int sp, int slot) {
+    int b, oy0, ox0;
+    dw_decode_tile(a, sp, b, oy0, ox0);
     mbar_expect_tx(&full[slot], tile_bytes);
     tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
-  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
-  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
-  if (tid == 0 && tile_begin < tile_end) issue(tile_begin, 0);
-  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+  if (grp >= ngrp) return;
+  if (tid == 0 && grp < n_sp) issue(grp, 0);
+  for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
     const int slot = it & 1;
-    int chunk, b, oy0, ox0;
-    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    int b, oy0, ox0;
+    dw_decode_tile(a, sp, b, oy0, ox0);
     const int c0 = chunk * 64, cc = c0 + v * 8;
     const bool cv_ok = cc < a.C;
     if (chunk != cur_chunk) {
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
       }
     }
     // prefetch the next tile into the other buffer (free since the __syncthreads that ended the previous iteration)
-    if (tid == 0 && tile + 1 < tile_end) issue(tile + 1, slot ^ 1);
+    if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
     mbar_wait(&full[slot], (it >> 1) & 1);
     H8* s_in = bufs[slot];
     if (pro) {
@@ -981,20 +982,24 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
       if (c < a.C) atomicAdd(&a.dw[t * a.C + c], s_dw[i]);
     }
   };
-  auto issue = [&](int tile, int slot) {
-    int chunk, b, oy0, ox0;
-    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+  // CTA -> (channel chunk, spatial group): neighbouring CTAs work on the different 64-channel chunks of the SAME
+  // spatial tiles at the same time, so the 128-byte pieces of one pixel row are requested together (DRAM page
+  // locality), while a CTA keeps its chunk -- filter taps, statistics / gradient accumulators -- for its lifetime.
+  const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
+  const int n_sp = a.B * a.tiles_y * a.tiles_x;
+  auto issue = [&](int sp, int slot) {
+    int b, oy0, ox0;
+    dw_decode_tile(a, sp, b, oy0, ox0);
     mbar_expect_tx(&full[slot], tile_bytes);
     tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
-  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
-  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
-  if (tid == 0 && tile_begin < tile_end) issue(tile_begin, 0);
-  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+  if (grp >= ngrp) return;
+  if (tid == 0 && grp < n_sp) issue(grp, 0);
+  for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
     const int slot = it & 1;
-    int chunk, b, oy0, ox0;
-    dw_decode_tile(a, tile, chunk, b, oy0, ox0);
+    int b, oy0, ox0;
+    dw_decode_tile(a, sp, b, oy0, ox0);
     const int c0 = chunk * 64, cc = c0 + v * 8;
     const bool cv_ok = cc < a.C;
     if (chunk != cur_chunk) {
@@ -1005,7 +1010,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
     }
-    if (tid == 0 && tile + 1 < tile_end) issue(tile + 1, slot ^ 1);
+    if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
     // the thread's four dy vectors are requested before waiting for the input tile
     constexpr int NP = (kTH * kTW) / 32;
     H8 g[NP];
@@ -1451,8 +1456,11 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
     if (rc) return rc;
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     const int per_sm_h = smem_t > 110 * 1024 ? 1 : 2;
-    const int cap_h = num_sms() * per_sm_h;
-    dw_fwd_tma_h_kernel<<<a.num_tiles < cap_h ? a.num_tiles : cap_h, 256, smem_t, st>>>(tm, a);
+    const int n_sp = a.B * a.tiles_y * a.tiles_x;
+    int ngrp = (num_sms() * per_sm_h) / a.chunks;
+    if (ngrp < 1) ngrp = 1;
+    if (ngrp > n_sp) ngrp = n_sp;
+    dw_fwd_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
     g_launches++;
     return check_launch("dw_fwd_tma_h_kernel");
   }
@@ -1480,7 +1488,11 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
     int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw, a.ih);
     if (rc) return rc;
     DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    dw_wgrad_tma_h_kernel<<<grid, 256, smem_t, st>>>(tm, a);
+    const int n_sp = a.B * a.tiles_y * a.tiles_x;
+    int ngrp = num_sms() / a.chunks;
+    if (ngrp < 1) ngrp = 1;
+    if (ngrp > n_sp) ngrp = n_sp;
+    dw_wgrad_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
     g_launches++;
     return check_launch("dw_wgrad_tma_h_kernel");
   }
