@@ -771,7 +771,20 @@ __device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int r, int& 
   oy0 = ty * kTH; ox0 = tx * kTW;
 }
 
-__device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, H8* s_in, int oy0, int ox0, int c0, bool cv_ok) {
+// Explicit shared-window accesses: the tile buffers are selected at run time (double buffer), which makes nvcc fall
+// back to generic 32-bit LD.E/ST.E (4 instructions and 4-way bank conflicts per 16-byte vector) -- ld/st.shared.v4 on a
+// 32-bit shared address keeps every tile access one LDS.128 / STS.128.
+__device__ __forceinline__ H8 lds_h8(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+  return *reinterpret_cast<H8*>(&u);
+}
+__device__ __forceinline__ void sts_h8(uint32_t saddr, const H8& o) {
+  const uint4 u = *reinterpret_cast<const uint4*>(&o);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+__device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_t s_in, int oy0, int ox0, int c0, bool cv_ok) {
   // in place: a = act(x * scale + shift) inside the image, exact zeros in the padding
   const int tid = threadIdx.x, v = tid & 7;
   const int cc = c0 + v * 8;
@@ -785,12 +798,15 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, H8* s_i
   const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
   const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
   const int npos = a.ih * a.iw;
-  for (int p = tid >> 3; p < npos; p += 32) {
-    const int py = p / a.iw, px = p - py * a.iw;
+  // (py, px) advance by 32 positions per step without a division
+  const int step_y = 32 / a.iw, step_x = 32 - step_y * a.iw;
+  int p = tid >> 3;
+  int py = p / a.iw, px = p - py * a.iw;
+  uint32_t addr = s_in + static_cast<uint32_t>(p * kCV + v) * 16u;
+  for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
     const int gy = gy0 + py, gx = gx0 + px;
-    H8 o;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-      o = s_in[static_cast<size_t>(p) * kCV + v];
+      H8 o = lds_h8(addr);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         __half2 z = __hfma2(o.h[i], sc2[i], sh2[i]);
@@ -798,11 +814,15 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, H8* s_i
         else if (a.in_act == DLB_ACT_RELU) z = __hmax2(z, zero2);
         o.h[i] = z;
       }
+      sts_h8(addr, o);
     } else {
+      H8 o;
 #pragma unroll
       for (int i = 0; i < 4; ++i) o.h[i] = zero2;
+      sts_h8(addr, o);
     }
-    s_in[static_cast<size_t>(p) * kCV + v] = o;
+    py += step_y; px += step_x;
+    if (px >= a.iw) { px -= a.iw; ++py; }
   }
 }
 
@@ -810,7 +830,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
-  H8* bufs[2] = {reinterpret_cast<H8*>(s_raw), reinterpret_cast<H8*>(s_raw + buf_stride)};
+  const uint32_t s_base = smem_u32(s_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
   float* s_stats = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [2][64]
   const int tid = threadIdx.x, v = tid & 7;
@@ -828,7 +848,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV * 16;
   int cur_chunk = -1;
   __half* y = reinterpret_cast<__half*>(a.y);
 
@@ -855,7 +875,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     int b, oy0, ox0;
     dw_decode_tile(a, sp, b, oy0, ox0);
     mbar_expect_tx(&full[slot], tile_bytes);
-    tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
+    tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
   if (grp >= ngrp) return;
@@ -883,7 +903,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     // prefetch the next tile into the other buffer (free since the __syncthreads that ended the previous iteration)
     if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
     mbar_wait(&full[slot], (it >> 1) & 1);
-    H8* s_in = bufs[slot];
+    const uint32_t s_in = s_base + slot * buf_stride;
     if (pro) {
       dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
       __syncthreads();
@@ -894,19 +914,19 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         const int q = (tid >> 3) + 32 * j;
         const int oy = q / kTW, ox = q - oy * kTW;
         if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
-        const H8* base = s_in + static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v;
+        const uint32_t base = s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           __half2 racc[4];
           {
-            const H8 xv = base[off[ky * 3]];
+            const H8 xv = lds_h8(base + off[ky * 3]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) racc[i] = __hmul2(xv.h[i], w2[ky * 3][i]);
           }
 #pragma unroll
           for (int kx = 1; kx < 3; ++kx) {
-            const H8 xv = base[off[ky * 3 + kx]];
+            const H8 xv = lds_h8(base + off[ky * 3 + kx]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
           }
@@ -937,7 +957,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
-  H8* bufs[2] = {reinterpret_cast<H8*>(s_raw), reinterpret_cast<H8*>(s_raw + buf_stride)};
+  const uint32_t s_base = smem_u32(s_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
   float* s_dw = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [9][64]
   const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
@@ -953,7 +973,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV * 16;
   int cur_chunk = -1;
   const __half* dy = reinterpret_cast<const __half*>(a.dy);
 
@@ -991,7 +1011,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
     int b, oy0, ox0;
     dw_decode_tile(a, sp, b, oy0, ox0);
     mbar_expect_tx(&full[slot], tile_bytes);
-    tma_load_4d(bufs[slot], &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
+    tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
   if (grp >= ngrp) return;
@@ -1026,7 +1046,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
       }
     }
     mbar_wait(&full[slot], (it >> 1) & 1);
-    H8* s_in = bufs[slot];
+    const uint32_t s_in = s_base + slot * buf_stride;
     if (pro) {
       dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
       __syncthreads();
@@ -1039,7 +1059,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
         for (int j = 0; j < NP; ++j) {
           const int q = (tid >> 3) + 32 * j;
           const int oy = q / kTW, ox = q - oy * kTW;
-          const H8 xv = s_in[static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v + off[t]];
+          const H8 xv = lds_h8(s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u + off[t]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) p2[i] = j == 0 ? __hmul2(xv.h[i], g[j].h[i]) : __hfma2(xv.h[i], g[j].h[i], p2[i]);
         }

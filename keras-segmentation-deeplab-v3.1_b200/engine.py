@@ -562,6 +562,7 @@ class Engine:
         HW = fh * fw
         wsp = ws["wgrad_ws"]
         ops.fill_zero(self.bn_red)
+        ops.fill_zero(self.grads)          # one memset: depthwise / stem gradients are accumulated with atomics
         first = self._first_trainable_index()
         # ---- head
         hc = self.head_conv
@@ -647,8 +648,6 @@ class Engine:
                        act=ACT_RELU6, red=dbn.red, dgamma=dbn.gamma.grad, dbeta=dbn.beta.grad)
             dwl = b["dw"]
             dw_grad = dwl.params[0].grad.view(3, 3, b["mid"]) if dwl.trainable else None
-            if dw_grad is not None:
-                ops.fill_zero(dw_grad)
             if b["bid"]:
                 ebn = b["expand_bn"]
                 stop_here = first > self._order(ebn.layer.name)
@@ -688,7 +687,6 @@ class Engine:
         ops.bn_bwd(ws["y_stem"], dx, dy_s, scale=sbn.scale, shift=sbn.shift, mean=sbn.mean, rstd=sbn.rstd,
                    act=ACT_RELU6, red=sbn.red, dgamma=sbn.gamma.grad, dbeta=sbn.beta.grad)
         if self.stem.trainable:
-            ops.fill_zero(self.stem.params[0].grad)
             ops.stem_conv_wgrad(ws["img"], dy_s, self.stem.params[0].grad)
 
     def _unshuffle_dlogits(self, ws):

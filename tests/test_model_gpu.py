@@ -238,7 +238,7 @@ def test_gradients_fp32_match_oracle_autograd():
             assert err < 0.2, (rec.name, i, err)               # a wrong index / missing term shows up as O(1)
             if rec.name in ("conv_upsample", "concat_projection", "concat_projection_BN", "aspp0"):
                 floor = rel(g32[rec.name][i].reshape(p.shape), gref)
-                assert rel(got, gref) < max(2e-3, 5 * floor), (rec.name, i)
+                assert rel(got, gref) < max(5e-3, 5 * floor), (rec.name, i)
     flat, ref = torch.cat(flat), torch.cat(ref)
     cos = (torch.dot(flat, ref) / (flat.norm() * ref.norm())).item()
     assert cos > 0.9999, cos
