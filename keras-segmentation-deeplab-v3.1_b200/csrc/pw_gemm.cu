@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmArgs g) {
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // round up to the 1024-byte swizzle-atom alignment by OFFSETTING the shared array (a uintptr_t round trip makes
+  // every later access a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,7 +83,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   float* s_shift = s_scale + npad;
   float* s_sum = s_shift + npad;
   float* s_sqs = s_sum + npad;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_sqs + npad) + 15) & ~uintptr_t(15));   // 8 warps x 4 KB
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_sqs + npad);   // 8 warps x 4 KB; 16-byte aligned (npad is a multiple of 16)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -172,6 +174,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int quad = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;           // which 64-column blocks
     const bool do_stats = g.stat_sum != nullptr;
+    const bool affine = g.col_scale != nullptr || g.col_shift != nullptr;
     const int red_col = reduce16_col_of_lane(lane);
     constexpr bool kStaged = sizeof(OutT) == 2;
     uint4* stg = reinterpret_cast<uint4*>(s_stage) + static_cast<size_t>(warp - 2) * 32 * 8;   // [32 rows][8 chunks of 16 B]
@@ -214,15 +217,38 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tmem_ld_wait();
             float v[2][16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int n0 = col_base + j + h * 16;
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(r[h][i]);
-                if (g.col_scale || g.col_shift) x = fmaf(x, s_scale[n0 + i], s_shift[n0 + i]);
-                if (rb && n0 + i < g.N) x += rb[n0 + i];
-                v[h][i] = (h == 0 || two) ? x : 0.f;
+              for (int i = 0; i < 16; ++i) v[h][i] = __uint_as_float(r[h][i]);
+            // kernel-uniform options are tested once per 32 columns, not per element
+            if (affine) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col_base + j + h * 16);
+                const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col_base + j + h * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 a4 = sc4[q], b4 = sh4[q];
+                  v[h][4 * q + 0] = fmaf(v[h][4 * q + 0], a4.x, b4.x);
+                  v[h][4 * q + 1] = fmaf(v[h][4 * q + 1], a4.y, b4.y);
+                  v[h][4 * q + 2] = fmaf(v[h][4 * q + 2], a4.z, b4.z);
+                  v[h][4 * q + 3] = fmaf(v[h][4 * q + 3], a4.w, b4.w);
+                }
               }
+            }
+            if (rb) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int n0 = col_base + j + h * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (n0 + i < g.N) v[h][i] += rb[n0 + i];
+              }
+            }
+            if (!two || (do_stats && !row_ok)) {
+              const bool all = do_stats && !row_ok;       // rows past M must not reach the statistics
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v[1][i] = 0.f; if (all) v[0][i] = 0.f; }
             }
             if (do_stats && !staged) {
               float s1[2][16], s2[2][16];
@@ -230,7 +256,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const float q = row_ok ? v[h][i] : 0.f;
+                  const float q = v[h][i];
                   s1[h][i] = q; s2[h][i] = q * q;
                 }
               const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
@@ -251,7 +277,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int c = 0; c < 4; ++c) {
                 float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = (do_stats && !row_ok) ? 0.f : v[c >> 1][(c & 1) * 8 + i];
+                for (int i = 0; i < 8; ++i) o[i] = v[c >> 1][(c & 1) * 8 + i];
                 uint4 pk;
                 Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
                 stg[lane * 8 + ((sub * 4 + c) ^ (lane & 7))] = pk;

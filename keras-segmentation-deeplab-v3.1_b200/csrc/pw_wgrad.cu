@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                    const WgArgs g) {
   extern __shared__ uint8_t smem_dyn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset, not a uintptr_t round trip: keeps LDS/STS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* tail = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
