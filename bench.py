@@ -220,7 +220,7 @@ def profile_eager_step(engine, ws, B):
             e0.record()
             r = f(*a, **k)
             e1.record()
-            recs.append((n, e0, e1, algo_bytes(n, a, k)))
+            recs.append((n, e0, e1, algo_bytes(n, a, k), [tuple(t.shape) for t in a[:3] if torch.is_tensor(t)]))
             return r
         return g
 
@@ -234,7 +234,12 @@ def profile_eager_step(engine, ws, B):
         for n in names:
             setattr(ops, n, orig[n])
     agg = {}
-    for n, e0, e1, b in recs:
+    if os.environ.get("DLB_CALL_LOG"):      # per-call list (name, us, algorithmic GB/s, leading tensor shapes) for profiles/
+        with open(os.environ["DLB_CALL_LOG"], "w") as f:
+            for n, e0, e1, b, shp in recs:
+                us = e0.elapsed_time(e1) * 1e3
+                f.write(json.dumps({"op": n, "us": round(us, 1), "gbs": round(b / max(us, 1e-3) / 1e3, 1), "shapes": shp}) + "\n")
+    for n, e0, e1, b, _ in recs:
         d = agg.setdefault(n, [0.0, 0, 0])
         d[0] += e0.elapsed_time(e1)
         d[1] += b

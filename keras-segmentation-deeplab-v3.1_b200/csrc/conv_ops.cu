@@ -244,6 +244,9 @@ struct DwTileArgs {
   const void* dy; float* dw;     // backward-weight mode
   int flip;
   int tiles_x, tiles_y, chunks, num_tiles, ih, iw;
+  // TMA kernels only: dilation-phase decomposition (sub = d: a tile is one phase of the d x d sub-sampled grids, read
+  // with TMA element strides, so the dilated conv is an undilated one in shared memory), smem dilation, NaN padding
+  int sub, sdil, nan_fill;
 };
 
 template <typename T>
@@ -763,12 +766,20 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileAr
 // one is being computed; the consumer-side BatchNorm+ReLU6 prologue is an in-place pass over the landed tile.
 // (The register-staged version above spends most of a tile's time waiting on its own loads: 2 CTAs/SM, no overlap.)
 // ---------------------------------------------------------------------------------------------
-int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w, int box_h);
+int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w, int box_h,
+                   int elem_stride, int nan_fill);
 
 __device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int r, int& b, int& oy0, int& ox0) {
-  b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
-  const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-  oy0 = ty * kTH; ox0 = tx * kTW;
+  // r = ((b * tiles_y + ty) * tiles_x + tx) * sub^2 + phase : the phases of one region are neighbours in the schedule,
+  // so CTAs running at the same time read one dense region between them.  Output pixel (i, j) of the tile is
+  // (oy0 + sub * i, ox0 + sub * j).
+  const int nph = a.sub * a.sub;
+  const int t = r / nph, ph = r - t * nph;
+  const int ry = ph / a.sub, rx = ph - ry * a.sub;
+  b = t / (a.tiles_y * a.tiles_x);
+  const int q = t - b * a.tiles_y * a.tiles_x;
+  const int ty = q / a.tiles_x, tx = q - ty * a.tiles_x;
+  oy0 = ry + a.sub * ty * kTH; ox0 = rx + a.sub * tx * kTW;
 }
 
 // Explicit shared-window accesses: the tile buffers are selected at run time (double buffer), which makes nvcc fall
@@ -796,15 +807,35 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
     sh2[i] = __floats2half2_rn(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
   }
   const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
-  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
   const int npos = a.ih * a.iw;
+  int p = tid >> 3;
+  uint32_t addr = s_in + static_cast<uint32_t>(p * kCV + v) * 16u;
+  if (a.nan_fill) {
+    // The tensor map fills out-of-image elements with NaN: fma keeps the NaN and max(NaN, 0) = 0 (PTX max returns the
+    // non-NaN operand), so ReLU / ReLU6 produce the exact zero padding without any coordinate test.
+    if (a.in_act == DLB_ACT_RELU6) {
+      for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
+        H8 o = lds_h8(addr);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.h[i] = __hmin2(__hmax2(__hfma2(o.h[i], sc2[i], sh2[i]), zero2), six2);
+        sts_h8(addr, o);
+      }
+    } else {
+      for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
+        H8 o = lds_h8(addr);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.h[i] = __hmax2(__hfma2(o.h[i], sc2[i], sh2[i]), zero2);
+        sts_h8(addr, o);
+      }
+    }
+    return;
+  }
+  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
   // (py, px) advance by 32 positions per step without a division
   const int step_y = 32 / a.iw, step_x = 32 - step_y * a.iw;
-  int p = tid >> 3;
   int py = p / a.iw, px = p - py * a.iw;
-  uint32_t addr = s_in + static_cast<uint32_t>(p * kCV + v) * 16u;
   for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
-    const int gy = gy0 + py, gx = gx0 + px;
+    const int gy = gy0 + py * a.sub, gx = gx0 + px * a.sub;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
       H8 o = lds_h8(addr);
 #pragma unroll
@@ -848,7 +879,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV * 16;
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.sdil * a.iw + kx * a.sdil) * kCV * 16;
   int cur_chunk = -1;
   __half* y = reinterpret_cast<__half*>(a.y);
 
@@ -856,7 +887,12 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     __syncthreads();
     if (tid < 128) s_stats[tid] = 0.f;
     __syncthreads();
-    if (chunk * 64 + v * 8 < a.C) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {        // the 4 lanes of a warp that share a channel vector are folded first
+      ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 8);  ssqs[i] += __shfl_xor_sync(0xffffffffu, ssqs[i], 8);
+      ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16); ssqs[i] += __shfl_xor_sync(0xffffffffu, ssqs[i], 16);
+    }
+    if ((tid & 31) < 8 && chunk * 64 + v * 8 < a.C) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
     }
@@ -870,7 +906,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   // spatial tiles at the same time, so the 128-byte pieces of one pixel row are requested together (DRAM page
   // locality), while a CTA keeps its chunk -- filter taps, statistics / gradient accumulators -- for its lifetime.
   const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
-  const int n_sp = a.B * a.tiles_y * a.tiles_x;
+  const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
   auto issue = [&](int sp, int slot) {
     int b, oy0, ox0;
     dw_decode_tile(a, sp, b, oy0, ox0);
@@ -913,7 +949,8 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
       for (int j = 0; j < (kTH * kTW) / 32; ++j) {
         const int q = (tid >> 3) + 32 * j;
         const int oy = q / kTW, ox = q - oy * kTW;
-        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
+        const int gy = oy0 + oy * a.sub, gx = ox0 + ox * a.sub;
+        if (gy >= a.Ho || gx >= a.Wo) continue;
         const uint32_t base = s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -944,7 +981,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         H8 o;
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc) = o;
+        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc) = o;
       }
     }
     if (pro) fence_proxy_async();     // generic-proxy writes of the transform vs the TMA that will refill this buffer
@@ -973,7 +1010,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV * 16;
+    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.sdil * a.iw + kx * a.sdil) * kCV * 16;
   int cur_chunk = -1;
   const __half* dy = reinterpret_cast<const __half*>(a.dy);
 
@@ -1006,7 +1043,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   // spatial tiles at the same time, so the 128-byte pieces of one pixel row are requested together (DRAM page
   // locality), while a CTA keeps its chunk -- filter taps, statistics / gradient accumulators -- for its lifetime.
   const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
-  const int n_sp = a.B * a.tiles_y * a.tiles_x;
+  const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
   auto issue = [&](int sp, int slot) {
     int b, oy0, ox0;
     dw_decode_tile(a, sp, b, oy0, ox0);
@@ -1038,8 +1075,9 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
     for (int j = 0; j < NP; ++j) {
       const int q = (tid >> 3) + 32 * j;
       const int oy = q / kTW, ox = q - oy * kTW;
-      if (cv_ok && oy0 + oy < a.Ho && ox0 + ox < a.Wo)
-        g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
+      const int gy = oy0 + oy * a.sub, gx = ox0 + ox * a.sub;
+      if (cv_ok && gy < a.Ho && gx < a.Wo)
+        g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc);
       else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
@@ -1073,7 +1111,22 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   if (cur_chunk >= 0) flush(cur_chunk);
 }
 
+// Geometry of the TMA kernels: stride-1 dilated layers (rate 2..8) are decomposed into their d x d phases.
+static void fill_tma_geometry(DwTileArgs& a) {
+  const bool decomp = a.stride == 1 && a.dil > 1 && a.dil <= 8;
+  a.sub = decomp ? a.dil : 1;
+  a.sdil = decomp ? 1 : a.dil;
+  a.ih = (kTH - 1) * a.stride + 2 * a.sdil + 1;
+  a.iw = (kTW - 1) * a.stride + 2 * a.sdil + 1;
+  const int hs = (a.Ho + a.sub - 1) / a.sub, ws = (a.Wo + a.sub - 1) / a.sub;
+  a.tiles_y = (hs + kTH - 1) / kTH;
+  a.tiles_x = (ws + kTW - 1) / kTW;
+  a.chunks = (a.C + 63) / 64;
+  a.nan_fill = (a.in_scale != nullptr && (a.in_act == DLB_ACT_RELU6 || a.in_act == DLB_ACT_RELU)) ? 1 : 0;
+}
+
 static void fill_tile_geometry(DwTileArgs& a) {
+  a.sub = 1; a.sdil = a.dil; a.nan_fill = 0;
   a.tiles_y = (a.Ho + kTH - 1) / kTH;
   a.tiles_x = (a.Wo + kTW - 1) / kTW;
   a.chunks = (a.C + 63) / 64;
@@ -1469,14 +1522,15 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024)
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+    fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
     const size_t smem_t = 2 * tile_b + 16 + 128 * sizeof(float);
     CUtensorMap tm;
-    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw, a.ih);
+    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     const int per_sm_h = smem_t > 110 * 1024 ? 1 : 2;
-    const int n_sp = a.B * a.tiles_y * a.tiles_x;
+    const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
     int ngrp = (num_sms() * per_sm_h) / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;
@@ -1502,13 +1556,14 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
   const int cap = num_sms();           // 1 CTA/SM (72 accumulators + staging need ~200 registers)
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
   if (std::is_same<T, __half>::value) {
+    fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
     const size_t smem_t = 2 * tile_b + 16 + 9 * 64 * sizeof(float);
     CUtensorMap tm;
-    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw, a.ih);
+    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;
     DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    const int n_sp = a.B * a.tiles_y * a.tiles_x;
+    const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
     int ngrp = num_sms() / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;

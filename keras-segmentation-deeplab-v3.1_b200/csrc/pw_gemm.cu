@@ -526,7 +526,7 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t rows, ui
 // NHWC activation tensor [B, H, W, C] as a 4D tensor map (dims innermost first: C, W, H, B), un-swizzled boxes
 // [1, box_h, box_w, box_c]; out-of-bounds coordinates (negative or past the edge) are zero-filled = conv padding
 int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_c, int box_w,
-                   int box_h) {
+                   int box_h, int elem_stride, int nan_fill) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled driver entry point unavailable"); return DLB_ERR_CUDA; }
   const cuuint64_t es = dtype_size(dtype);
@@ -536,9 +536,11 @@ int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, i
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // spatial element strides > 1 read every elem_stride-th pixel (box = pixels * stride, see cuTensorMapEncodeTiled)
+  cuuint32_t estr[4] = {1, (cuuint32_t)elem_stride, (cuuint32_t)elem_stride, 1};
   CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled(4D) failed (%d): B=%d H=%d W=%d C=%d box=%dx%dx%d", (int)r, B, H, W, C, box_h,
                    box_w, box_c);

@@ -178,7 +178,9 @@ def _dw_ref(x, w, stride, dil, in_scale=None, in_shift=None, in_act=0):
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
 @pytest.mark.parametrize("H,W,C,stride,dil", [(32, 32, 96, 1, 1), (32, 48, 144, 2, 1), (33, 31, 32, 2, 1),
                                                (16, 16, 384, 1, 2), (16, 16, 960, 1, 4), (24, 24, 64, 1, 12),
-                                               (8, 8, 2048, 1, 36)])
+                                               (8, 8, 2048, 1, 36),
+                                               # ragged sizes through the dilation-phase decomposition of the TMA kernels
+                                               (35, 29, 96, 1, 2), (30, 44, 64, 1, 4), (41, 37, 72, 1, 3)])
 def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(H * W + C)
