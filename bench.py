@@ -152,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ roofline probe
@@ -304,7 +304,7 @@ def main():
         for _ in range(args.warmup + args.steps):
             e.train_step(xd, yd, swd, use_graph=False)
         torch.cuda.synchronize()
-        print(json.dumps({"profile_eager_steps": args.warmup + args.steps}))
+        _emit({"profile_eager_steps": args.warmup + args.steps})
         return
 
     # ---- device-resident arm
@@ -405,8 +405,29 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+def _emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (NCCL's
+    version banner, library chatter) was diverted to stderr by `_divert_stdout`."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _divert_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 if __name__ == "__main__":
-    main()
+    _divert_stdout()
+    try:
+        main()
+    finally:
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
