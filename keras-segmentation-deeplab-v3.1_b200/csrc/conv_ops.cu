@@ -1111,6 +1111,101 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   if (cur_chunk >= 0) flush(cur_chunk);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward-data of the stride-2 3x3 depthwise conv (fp16): with u = iy + pad_t, v = ix + pad_l the transposed conv splits
+// by parity -- the 2x2 block (u, v) in {2m, 2m+1} x {2n, 2n+1} only needs dy[m-1..m, n-1..n]:
+//   dx[2m  ,2n  ] = dy[m,n] w00 + dy[m-1,n] w20 + dy[m,n-1] w02 + dy[m-1,n-1] w22
+//   dx[2m  ,2n+1] = dy[m,n] w01 + dy[m-1,n] w21
+//   dx[2m+1,2n  ] = dy[m,n] w10 + dy[m,n-1] w12
+//   dx[2m+1,2n+1] = dy[m,n] w11
+// One TMA box (kTH+1) x (kTW+1) x 64 channels of dy (zero fill outside) per tile of kTH x kTW cells, double-buffered.
+// ---------------------------------------------------------------------------------------------
+struct DwS2Args {
+  int B, H, W, C, Ho, Wo, pad_t, pad_l;
+  const float* w; void* dx;
+  int tiles_x, tiles_y, chunks;
+};
+
+__global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwS2Args a) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  constexpr int IH = kTH + 1, IW = kTW + 1;
+  constexpr uint32_t tile_bytes = IH * IW * kCV * 16;
+  constexpr uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
+  const uint32_t s_base = smem_u32(s_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
+  const int tid = threadIdx.x, v = tid & 7;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
+  const int n_sp = a.B * a.tiles_y * a.tiles_x;
+  const int cc = chunk * 64 + v * 8;
+  const bool cv_ok = cc < a.C;
+  __half2 w2[9][4];
+  if (cv_ok) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[t * a.C + cc + 2 * i], a.w[t * a.C + cc + 2 * i + 1]);
+  }
+  auto decode = [&](int sp, int& b, int& m0, int& n0) {
+    b = sp / (a.tiles_y * a.tiles_x);
+    const int q = sp - b * a.tiles_y * a.tiles_x;
+    const int ty = q / a.tiles_x;
+    m0 = ty * kTH; n0 = (q - ty * a.tiles_x) * kTW;
+  };
+  auto issue = [&](int sp, int slot) {
+    int b, m0, n0;
+    decode(sp, b, m0, n0);
+    mbar_expect_tx(&full[slot], tile_bytes);
+    tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, n0 - 1, m0 - 1, b);
+  };
+  if (grp >= ngrp) return;
+  if (tid == 0 && grp < n_sp) issue(grp, 0);
+  __half* dx = reinterpret_cast<__half*>(a.dx);
+  for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
+    const int slot = it & 1;
+    int b, m0, n0;
+    decode(sp, b, m0, n0);
+    if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
+    mbar_wait(&full[slot], (it >> 1) & 1);
+    const uint32_t s_in = s_base + slot * buf_stride;
+    if (cv_ok) {
+#pragma unroll 2
+      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
+        const int q = (tid >> 3) + 32 * j;
+        const int cm = q / kTW, cn = q - cm * kTW;          // cell (m0 + cm, n0 + cn); smem position (cm + 1, cn + 1)
+        const uint32_t base = s_in + static_cast<uint32_t>(((cm + 1) * IW + cn + 1) * kCV + v) * 16u;
+        const H8 d11 = lds_h8(base);                                     // dy[m, n]
+        const H8 d01 = lds_h8(base - IW * kCV * 16);                     // dy[m-1, n]
+        const H8 d10 = lds_h8(base - kCV * 16);                          // dy[m, n-1]
+        const H8 d00 = lds_h8(base - (IW + 1) * kCV * 16);               // dy[m-1, n-1]
+        H8 o00, o01, o10, o11;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o00.h[i] = __hfma2(d00.h[i], w2[8][i], __hfma2(d10.h[i], w2[2][i], __hfma2(d01.h[i], w2[6][i], __hmul2(d11.h[i], w2[0][i]))));
+          o01.h[i] = __hfma2(d01.h[i], w2[7][i], __hmul2(d11.h[i], w2[1][i]));
+          o10.h[i] = __hfma2(d10.h[i], w2[5][i], __hmul2(d11.h[i], w2[3][i]));
+          o11.h[i] = __hmul2(d11.h[i], w2[4][i]);
+        }
+        const int iy0 = 2 * (m0 + cm) - a.pad_t, ix0 = 2 * (n0 + cn) - a.pad_l;
+        const bool y0 = iy0 >= 0 && iy0 < a.H, y1 = iy0 + 1 >= 0 && iy0 + 1 < a.H;
+        const bool x0 = ix0 >= 0 && ix0 < a.W, x1 = ix0 + 1 >= 0 && ix0 + 1 < a.W;
+        __half* p = dx + ((static_cast<long long>(b) * a.H + iy0) * a.W + ix0) * a.C + cc;
+        const long long rs = static_cast<long long>(a.W) * a.C;
+        if (y0 && x0) *reinterpret_cast<H8*>(p) = o00;
+        if (y0 && x1) *reinterpret_cast<H8*>(p + a.C) = o01;
+        if (y1 && x0) *reinterpret_cast<H8*>(p + rs) = o10;
+        if (y1 && x1) *reinterpret_cast<H8*>(p + rs + a.C) = o11;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Geometry of the TMA kernels: stride-1 dilated layers (rate 2..8) are decomposed into their d x d phases.
 static void fill_tma_geometry(DwTileArgs& a) {
   const bool decomp = a.stride == 1 && a.dil > 1 && a.dil <= 8;
@@ -1614,6 +1709,27 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
       if (p->dtype == DLB_F16) rc = launch_dw_tiled<__half>(a, st);
       else if (p->dtype == DLB_BF16) rc = launch_dw_tiled<__nv_bfloat16>(a, st);
       else rc = launch_dw_tiled<float>(a, st);
+      if (rc) return rc;
+    } else if (p->stride == 2 && p->dilation == 1 && p->dtype == DLB_F16) {
+      DwS2Args a{};
+      a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
+      a.pad_t = p->pad_top; a.pad_l = p->pad_left; a.w = p->w; a.dx = p->dx;
+      // cells m = 0 .. floor((H - 1 + pad_t) / 2)
+      const int cells_y = (p->H - 1 + p->pad_top) / 2 + 1, cells_x = (p->W - 1 + p->pad_left) / 2 + 1;
+      a.tiles_y = (cells_y + kTH - 1) / kTH; a.tiles_x = (cells_x + kTW - 1) / kTW;
+      a.chunks = (p->C + 63) / 64;
+      CUtensorMap tm;
+      int rc = make_tmap_nhwc(&tm, DLB_F16, p->dy, p->B, p->Ho, p->Wo, p->C, 64, kTW + 1, kTH + 1, 1, 0);
+      if (rc) return rc;
+      const size_t smem_t = 2 * ((static_cast<size_t>(kTH + 1) * (kTW + 1) * kCV * 16 + 127) & ~size_t(127)) + 16;
+      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_data_s2_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      const int n_sp = a.B * a.tiles_y * a.tiles_x;
+      int ngrp = (num_sms() * 2) / a.chunks;
+      if (ngrp < 1) ngrp = 1;
+      if (ngrp > n_sp) ngrp = n_sp;
+      dw_bwd_data_s2_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+      g_launches++;
+      rc = check_launch("dw_bwd_data_s2_tma_h_kernel");
       if (rc) return rc;
     } else {
       DLB_REQUIRE(p->C / 8 <= 256, "dw_conv_bwd: C <= 2048 for the strided backward-data kernel");
