@@ -1256,10 +1256,10 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemArgs a) {
   T* y = reinterpret_cast<T*>(a.y);
   for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + tid; pix < a.npix;
        pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wo = static_cast<int>(pix % a.Wo);
-    const long long t1 = pix / a.Wo;
-    const int ho = static_cast<int>(t1 % a.Ho);
-    const int b = static_cast<int>(t1 / a.Ho);
+    const int hw_ = a.Ho * a.Wo;
+    const int b = static_cast<int>(pix / hw_);
+    const int r_ = static_cast<int>(pix - static_cast<long long>(b) * hw_);
+    const int ho = r_ / a.Wo, wo = r_ - ho * a.Wo;
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
@@ -1333,20 +1333,25 @@ __global__ void __launch_bounds__(224) stem_wgrad_kernel(int B, int H, int W, in
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long long p0 = static_cast<long long>(blockIdx.x) * PIX; p0 < npix; p0 += static_cast<long long>(gridDim.x) * PIX) {
     __syncthreads();
-    for (int i = tid; i < PIX * 28; i += 224) {
-      const int p = i / 28, t = i - p * 28;
-      const long long pix = p0 + p;
-      float v = 0.f;
-      if (pix < npix && t < 27) {
-        const int wo = static_cast<int>(pix % Wo);
-        const long long t1 = pix / Wo;
-        const int ho = static_cast<int>(t1 % Ho);
-        const int b = static_cast<int>(t1 / Ho);
-        const int kk = t / 3, ci = t - kk * 3, ky = kk / 3, kx = kk - ky * 3;
-        const int h = ho * 2 - pad_t + ky, w = wo * 2 - pad_l + kx;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = x[((static_cast<size_t>(b) * H + h) * W + w) * 3 + ci] / 127.5f - 1.f;
+    // patch matrix: thread -> (pixel p = i / 28, tap t); the slab's pixel coordinates come from ONE 32-bit decode of
+    // its first pixel (64-bit div/mod per element cost a third of the kernel)
+    {
+      const int hw = Ho * Wo;
+      const int b0 = static_cast<int>(p0 / hw);
+      const int r0 = static_cast<int>(p0 - static_cast<long long>(b0) * hw);
+      for (int i = tid; i < PIX * 28; i += 224) {
+        const int p = i / 28, t = i - p * 28;
+        float v = 0.f;
+        if (p0 + p < npix && t < 27) {
+          int r = r0 + p, b = b0;
+          if (r >= hw) { r -= hw; ++b; }           // PIX <= Ho*Wo: at most one image boundary inside a slab
+          const int ho = r / Wo, wo = r - ho * Wo;
+          const int kk = t / 3, ci = t - kk * 3, ky = kk / 3, kx = kk - ky * 3;
+          const int h = ho * 2 - pad_t + ky, w = wo * 2 - pad_l + kx;
+          if (h >= 0 && h < H && w >= 0 && w < W) v = x[((static_cast<size_t>(b) * H + h) * W + w) * 3 + ci] / 127.5f - 1.f;
+        }
+        s_x[p][t] = v;
       }
-      s_x[p][t] = v;
     }
     for (int i = tid; i < PIX * 4; i += 224) {
       const int p = i >> 2, c8 = (i & 3) * 8;
@@ -1815,6 +1820,7 @@ extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, con
   const int pt = (Ho - 1) * 2 + 3 - H, pl = (Wo - 1) * 2 + 3 - W;
   const int pad_t = (pt > 0 ? pt : 0) / 2, pad_l = (pl > 0 ? pl : 0) / 2;
   const long long npix = static_cast<long long>(B) * Ho * Wo;
+  DLB_REQUIRE(Ho * Wo >= 64, "stem_conv_wgrad: output map %dx%d smaller than one 64-pixel slab", Ho, Wo);
   const int grid = pick_grid((npix + 63) / 64, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == DLB_F16)

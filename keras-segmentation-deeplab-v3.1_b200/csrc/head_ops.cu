@@ -90,10 +90,12 @@ struct CeArgs {
 };
 
 template <int C, int S>
-__global__ void __launch_bounds__(256) resize_softmax_ce_kernel(const CeArgs a) {
+__global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs a) {
   constexpr int TILE = 64 / S >= 8 ? 8 : 64 / S;      // low-res cells per tile side (8 for S=8, 8 for S=4 -> 32px)
   constexpr int TP = TILE + 1;
-  constexpr int PX = TILE * S;                        // output pixels per tile side
+  constexpr int PX = TILE * S;                        // output pixels per tile side (64 or 32)
+  constexpr int RG = 256 / PX;                        // thread = (pixel column, row group); a row group owns cell rows
+  static_assert(TILE % RG == 0 && S <= 32 && (S & (S - 1)) == 0, "tile / thread mapping");
   __shared__ float s_log[TP * TP * C];
   __shared__ float s_grad[TP * TP * C];
   __shared__ float s_loss[8];
@@ -111,75 +113,84 @@ __global__ void __launch_bounds__(256) resize_softmax_ce_kernel(const CeArgs a) 
   __syncthreads();
   const float gs = *a.grad_scale;
   float loss_acc = 0.f;
-  // each warp walks rows of the tile; a lane owns one output pixel of a 32-pixel row segment
-  constexpr int SEGS = (PX + 31) / 32;
-  for (int rs = warp; rs < PX * SEGS; rs += 8) {
-    const int ry = rs / SEGS, seg = rs - ry * SEGS;
-    const int lx = seg * 32 + lane;                 // pixel x inside the tile
-    const int Y = ty0 * S + ry, X = tx0 * S + lx;
-    const bool ok = lx < PX && Y < a.H && X < a.W;
-    // local (tile) source coordinates; src = dst / S exactly, hi clamps at the image edge
-    const int cy0 = ry / S; const float fy = static_cast<float>(ry % S) / static_cast<float>(S);
-    const int cx0 = lx / S; const float fx = static_cast<float>(lx % S) / static_cast<float>(S);
+  // A thread walks the S pixels of one pixel column inside one cell row.  The column's two source columns and its fx
+  // are fixed, so the x-lerped logits (top / bottom rows) are computed once, the transposed resize is accumulated
+  // in registers over the S rows (weights 1-fy / fy), and only then folded over the S lanes that share the source
+  // columns -- 4 shared-memory atomics per class and cell instead of 4 per class and pixel group.
+  const int lx = tid % PX, rg = tid / PX;
+  const int X = tx0 * S + lx;
+  const int cx0 = lx / S; const float fx = static_cast<float>(lx % S) / static_cast<float>(S);
+  const int cx1 = (tx0 + cx0 + 1 <= a.w - 1) ? cx0 + 1 : cx0;
+  for (int cy0 = rg; cy0 < TILE; cy0 += RG) {
     const int cy1 = (ty0 + cy0 + 1 <= a.h - 1) ? cy0 + 1 : cy0;
-    const int cx1 = (tx0 + cx0 + 1 <= a.w - 1) ? cx0 + 1 : cx0;
-    float g[C];
-    const float wy0 = 1.f - fy, wy1 = fy;   // identical for all lanes of the row
-    if (ok) {
+    const bool col_ok = X < a.W && ty0 + cy0 < a.h;
+    float top[C], dlt[C], acc0[C], acc1[C];
+    {
       const float* tl = &s_log[(cy0 * TP + cx0) * C];
       const float* tr = &s_log[(cy0 * TP + cx1) * C];
       const float* bl = &s_log[(cy1 * TP + cx0) * C];
       const float* br = &s_log[(cy1 * TP + cx1) * C];
-      float mx = -INFINITY; int am = 0;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float top = tl[c] + (tr[c] - tl[c]) * fx;
-        const float bot = bl[c] + (br[c] - bl[c]) * fx;
-        g[c] = top + (bot - top) * fy;
-        if (g[c] > mx) { mx = g[c]; am = c; }
+        top[c] = tl[c] + (tr[c] - tl[c]) * fx;
+        dlt[c] = (bl[c] + (br[c] - bl[c]) * fx) - top[c];
+        acc0[c] = 0.f; acc1[c] = 0.f;
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) { g[c] = expf(g[c] - mx); sum += g[c]; }
-      const float inv = 1.f / sum;
-      const size_t pix = (static_cast<size_t>(b) * a.H + Y) * a.W + X;
-      if (a.argmax) a.argmax[pix] = static_cast<uint8_t>(am);
-      const int label = static_cast<int>(a.labels[pix]);
-      const float sw = a.sample_w ? a.sample_w[pix] : 1.f;
-      float py = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) { g[c] *= inv; if (c == label) py = g[c]; }
-      const bool valid = label >= 0 && label < C;
-      // Keras: p = clip(p, 1e-7, 1 - 1e-7); loss = -log p[y]; the clip has zero gradient outside its range
-      const bool in_range = valid && py >= 1e-7f && py <= 1.f - 1e-7f;
-      if (valid) loss_acc += sw * -logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f));
-      const float k = in_range ? sw * gs : 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) g[c] = k * (g[c] - (c == label ? 1.f : 0.f));
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) g[c] = 0.f;
     }
-    // transposed resize: pixel contributes (1-fx) to column cx0 and fx to cx1; the S lanes of a group share them
+    if (col_ok) {
+#pragma unroll 1
+      for (int r = 0; r < S; ++r) {
+        const int Y = (ty0 + cy0) * S + r;
+        const float fy = static_cast<float>(r) / static_cast<float>(S);
+        float g[C];
+        float mx = -INFINITY; int am = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          g[c] = top[c] + dlt[c] * fy;
+          if (g[c] > mx) { mx = g[c]; am = c; }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { g[c] = expf(g[c] - mx); sum += g[c]; }
+        const float inv = 1.f / sum;
+        const size_t pix = (static_cast<size_t>(b) * a.H + Y) * a.W + X;
+        if (a.argmax) a.argmax[pix] = static_cast<uint8_t>(am);
+        const int label = static_cast<int>(a.labels[pix]);
+        const float sw = a.sample_w ? a.sample_w[pix] : 1.f;
+        float py = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { g[c] *= inv; if (c == label) py = g[c]; }
+        const bool valid = label >= 0 && label < C;
+        // Keras: p = clip(p, 1e-7, 1 - 1e-7); loss = -log p[y]; the clip has zero gradient outside its range
+        const bool in_range = valid && py >= 1e-7f && py <= 1.f - 1e-7f;
+        if (valid) loss_acc += sw * -logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f));
+        const float k = in_range ? sw * gs : 0.f;
+        const float k0 = k * (1.f - fy), k1 = k * fy;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float d = g[c] - (c == label ? 1.f : 0.f);
+          acc0[c] = fmaf(k0, d, acc0[c]);
+          acc1[c] = fmaf(k1, d, acc1[c]);
+        }
+      }
+    }
+    // fold over the S lanes of the cell (same cx0 / cx1), split by the x weights
     const bool leader = (lane % S) == 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      float ga = g[c] * (1.f - fx), gb = g[c] * fx;
+      float v00 = acc0[c] * (1.f - fx), v01 = acc0[c] * fx, v10 = acc1[c] * (1.f - fx), v11 = acc1[c] * fx;
 #pragma unroll
       for (int o = S / 2; o > 0; o >>= 1) {
-        ga += __shfl_xor_sync(0xffffffffu, ga, o);
-        gb += __shfl_xor_sync(0xffffffffu, gb, o);
+        v00 += __shfl_xor_sync(0xffffffffu, v00, o);
+        v01 += __shfl_xor_sync(0xffffffffu, v01, o);
+        v10 += __shfl_xor_sync(0xffffffffu, v10, o);
+        v11 += __shfl_xor_sync(0xffffffffu, v11, o);
       }
-      if (leader && lx < PX) {
-        const float w0 = wy0, w1 = wy1;
-        if (ga != 0.f) {
-          atomicAdd(&s_grad[(cy0 * TP + cx0) * C + c], ga * w0);
-          if (w1 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx0) * C + c], ga * w1);
-        }
-        if (gb != 0.f) {
-          atomicAdd(&s_grad[(cy0 * TP + cx1) * C + c], gb * w0);
-          if (w1 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx1) * C + c], gb * w1);
-        }
+      if (leader) {
+        if (v00 != 0.f) atomicAdd(&s_grad[(cy0 * TP + cx0) * C + c], v00);
+        if (v01 != 0.f) atomicAdd(&s_grad[(cy0 * TP + cx1) * C + c], v01);
+        if (v10 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx0) * C + c], v10);
+        if (v11 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx1) * C + c], v11);
       }
     }
   }

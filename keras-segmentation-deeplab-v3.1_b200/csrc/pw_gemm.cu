@@ -56,6 +56,7 @@ struct GemmArgs {
   int k_elems_per_block, umma_k;   // 64/16 for 16-bit inputs
   uint32_t idesc;
   uint32_t stage_bytes;
+  int alt_tiles;   // N <= 64: the two epilogue warp sets take alternate M tiles (one accumulator stage each)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
@@ -89,7 +90,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? kEpiThreads / 64 : kEpiThreads / 32); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -200,11 +201,12 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
         const int as = it % g.acc_stages;
         const uint32_t aphase = (it / g.acc_stages) & 1;
+        if (g.alt_tiles && as != half) continue;     // narrow outputs: this warp set owns accumulator stage `half`
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const int gcols = chunks * g.chunk_n;
         const int col_base = grp * group_rows;
-        for (int j64 = half * 64; j64 < gcols; j64 += 128) {
+        for (int j64 = g.alt_tiles ? 0 : half * 64; j64 < gcols; j64 += 128) {
 #pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             const int j = j64 + sub * 32;
@@ -570,6 +572,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.n_groups = (g.n_chunks + g.chunks_per_group - 1) / g.chunks_per_group;
   g.acc_cols = g.chunks_per_group * g.chunk_n;
   g.acc_stages = g.acc_cols <= 256 ? 2 : 1;
+  g.alt_tiles = (g.n_groups == 1 && g.acc_cols <= 64 && g.acc_stages == 2) ? 1 : 0;
   g.k_elems_per_block = 64; g.umma_k = 16;
   g.num_k_blocks = (p->K + 63) / 64;
   g.num_m_tiles = (p->M + kBlockM - 1) / kBlockM;
