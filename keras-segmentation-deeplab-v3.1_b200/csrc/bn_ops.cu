@@ -161,11 +161,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
 // fp16 specialisation of the reduce pass: packed half2 arithmetic, 4-row partial sums on half2 folded into fp32
 // accumulators (the generic kernel is instruction-issue bound: ~13 instructions per element, 1.7 TB/s)
 struct __align__(16) BH8 { __half2 h[4]; };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
-  extern __shared__ float s_red[];   // [2*C]
+  extern __shared__ float s_red[];   // [rpb][2*C] per-row-group partial sums (no shared atomics: they were a 32-way
+                                     // CAS contention, a third of the kernel on the narrow project BNs)
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
-  __syncthreads();
   if (tid < a.rpb * a.cv) {
     const int r_in = tid / a.cv;
     const int c0 = (tid - r_in * a.cv) * 8;
@@ -183,7 +183,15 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
     const __half* da = reinterpret_cast<const __half*>(a.da);
     const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
     constexpr int U = 4;
+    const bool pf = (c0 & 63) == 0;      // one lane per 128-byte line warms L2 for the next iteration
     for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+      if (pf) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long rn = r0 + (U + u) * rstride;
+          if (rn < a.M) { prefetch_l2(x + rn * a.C + c0); prefetch_l2(da + rn * a.C + c0); }
+        }
+      }
       BH8 xv[U], gv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -215,11 +223,18 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
         s1[2 * k] += f1.x; s1[2 * k + 1] += f1.y; s2[2 * k] += f2.x; s2[2 * k + 1] += f2.y;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&s_red[c0 + k], s1[k]); atomicAdd(&s_red[a.C + c0 + k], s2[k]); }
+    float* row = s_red + static_cast<size_t>(r_in) * 2 * a.C;
+    *reinterpret_cast<float4*>(row + c0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(row + c0 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+    *reinterpret_cast<float4*>(row + a.C + c0) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    *reinterpret_cast<float4*>(row + a.C + c0 + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
   }
   __syncthreads();
-  for (int i = tid; i < 2 * a.C; i += blockDim.x) atomicAdd(&a.red[i], static_cast<double>(s_red[i]));
+  for (int i = tid; i < 2 * a.C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < a.rpb; ++r) t += s_red[static_cast<size_t>(r) * 2 * a.C + i];
+    atomicAdd(&a.red[i], static_cast<double>(t));
+  }
 }
 
 template <typename T>
@@ -313,6 +328,13 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
   constexpr int U = 4;
   for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
     BH8 xv[U], gv[U];
+    if ((c0 & 63) == 0) {                // one lane per 128-byte line warms L2 for the next iteration
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rn = r0 + (U + u) * rstride;
+        if (rn < a.M) { prefetch_l2(x + rn * a.C + c0); prefetch_l2(da + rn * a.C + c0); }
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * rstride;
@@ -484,7 +506,8 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   const size_t smem = 2 * p->C * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_reduce_h_kernel<<<grid, 256, smem, st>>>(a);
+  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f)
+    bn_bwd_reduce_h_kernel<<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);       // [rpb][2C] <= 16 KB
   else if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
   else bn_bwd_reduce_kernel<float><<<grid, 256, smem, st>>>(a);
