@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
 // fp16 specialisation of the reduce pass: packed half2 arithmetic, 4-row partial sums on half2 folded into fp32
 // accumulators (the generic kernel is instruction-issue bound: ~13 instructions per element, 1.7 TB/s)
 struct __align__(16) BH8 { __half2 h[4]; };
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
   extern __shared__ float s_red[];   // [rpb][2*C] per-row-group partial sums (no shared atomics: they were a 32-way
                                      // CAS contention, a third of the kernel on the narrow project BNs)
@@ -183,15 +183,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
     const __half* da = reinterpret_cast<const __half*>(a.da);
     const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
     constexpr int U = 4;
-    const bool pf = (c0 & 63) == 0;      // one lane per 128-byte line warms L2 for the next iteration
     for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
-      if (pf) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const long long rn = r0 + (U + u) * rstride;
-          if (rn < a.M) { prefetch_l2(x + rn * a.C + c0); prefetch_l2(da + rn * a.C + c0); }
-        }
-      }
       BH8 xv[U], gv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -328,13 +320,6 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
   constexpr int U = 4;
   for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
     BH8 xv[U], gv[U];
-    if ((c0 & 63) == 0) {                // one lane per 128-byte line warms L2 for the next iteration
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long rn = r0 + (U + u) * rstride;
-        if (rn < a.M) { prefetch_l2(x + rn * a.C + c0); prefetch_l2(da + rn * a.C + c0); }
-      }
-    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * rstride;
