@@ -57,7 +57,8 @@ struct ApplyArgs {
   const float* scale; const float* shift; int act; float drop_rate; uint64_t seed; const long long* seed_dev;
 };
 
-// thread = fixed 8-channel vector (scale/shift in registers), rows strided over the grid, 4 rows in flight
+// thread = fixed 8-channel vector (scale/shift in registers); a CTA iteration covers U * rpb CONSECUTIVE rows (one
+// contiguous block of memory), 4 rows in flight per thread
 template <typename T>
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const ApplyArgs a) {
   const T* x = reinterpret_cast<const T*>(a.x);
@@ -76,11 +77,11 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const ApplyArgs a) {
   const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
   const long long rstride = static_cast<long long>(gridDim.x) * rpb;
   constexpr int U = 4;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * rpb + r_in; r0 < M; r0 += rstride * U) {
+  for (long long r0 = static_cast<long long>(blockIdx.x) * rpb * U + r_in; r0 < M; r0 += rstride * U) {
     float v[U][8], rr[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * rpb;
       if (r < M) {
         Vec8<T>::ld(x + r * a.C + c0, v[u]);
         if (res) Vec8<T>::ld(res + r * a.C + c0, rr[u]);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const ApplyArgs a) {
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * rpb;
       if (r >= M) continue;
       const long long e0 = r * a.C + c0;
 #pragma unroll
@@ -129,16 +130,16 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
     const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
     const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
     constexpr int U = 4;
-    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
       float xv[U][8], gv[U][8];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long r = r0 + u * rstride;
+        const long long r = r0 + u * a.rpb;
         if (r < a.M) { Vec8<T>::ld(x + r * a.C + c0, xv[u]); Vec8<T>::ld(da + r * a.C + c0, gv[u]); }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long r = r0 + u * rstride;
+        const long long r = r0 + u * a.rpb;
         if (r >= a.M) continue;
         const long long e0 = r * a.C + c0;
 #pragma unroll
@@ -161,6 +162,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
 // fp16 specialisation of the reduce pass: packed half2 arithmetic, 4-row partial sums on half2 folded into fp32
 // accumulators (the generic kernel is instruction-issue bound: ~13 instructions per element, 1.7 TB/s)
 struct __align__(16) BH8 { __half2 h[4]; };
+// 16-byte global accesses go through uint4: nvcc scalarises a copy of the half2[4] struct into four 32-bit LDG/STG
+__device__ __forceinline__ BH8 ldg_bh8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<BH8*>(&u); }
+__device__ __forceinline__ void stg_bh8(void* p, const BH8& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
 
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
   extern __shared__ float s_red[];   // [rpb][2*C] per-row-group partial sums (no shared atomics: they were a 32-way
@@ -183,14 +187,14 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
     const __half* da = reinterpret_cast<const __half*>(a.da);
     const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
     constexpr int U = 4;
-    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+    for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
       BH8 xv[U], gv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long r = r0 + u * rstride;
+        const long long r = r0 + u * a.rpb;
         if (r < a.M) {
-          xv[u] = *reinterpret_cast<const BH8*>(x + r * a.C + c0);
-          gv[u] = *reinterpret_cast<const BH8*>(da + r * a.C + c0);
+          xv[u] = ldg_bh8(x + r * a.C + c0);
+          gv[u] = ldg_bh8(da + r * a.C + c0);
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) { xv[u].h[k] = zero2; gv[u].h[k] = zero2; }
@@ -257,16 +261,16 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
   const uint64_t seed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
   const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
   constexpr int U = 4;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
     float xv[U][8], gv[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * a.rpb;
       if (r < a.M) { Vec8<T>::ld(x + r * a.C + c0, xv[u]); Vec8<T>::ld(da + r * a.C + c0, gv[u]); }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * a.rpb;
       if (r >= a.M) continue;
       const long long e0 = r * a.C + c0;
       float o[8];
@@ -318,19 +322,19 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
   __half* dx = reinterpret_cast<__half*>(a.dx);
   const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
   constexpr int U = 4;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb + r_in; r0 < a.M; r0 += rstride * U) {
+  for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
     BH8 xv[U], gv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * a.rpb;
       if (r < a.M) {
-        xv[u] = *reinterpret_cast<const BH8*>(x + r * a.C + c0);
-        gv[u] = *reinterpret_cast<const BH8*>(da + r * a.C + c0);
+        xv[u] = ldg_bh8(x + r * a.C + c0);
+        gv[u] = ldg_bh8(da + r * a.C + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * rstride;
+      const long long r = r0 + u * a.rpb;
       if (r >= a.M) continue;
       BH8 o;
 #pragma unroll
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
         const float o1 = sc[2 * k + 1] * (dzf.y - k1[2 * k + 1] - xh.y * k2[2 * k + 1]);
         o.h[k] = __floats2half2_rn(o0, o1);
       }
-      *reinterpret_cast<BH8*>(dx + r * a.C + c0) = o;
+      stg_bh8(dx + r * a.C + c0, o);
     }
   }
 }

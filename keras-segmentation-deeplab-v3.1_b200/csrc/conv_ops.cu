@@ -503,6 +503,9 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs
 // registers instead of 72 floats, and tap offsets are precomputed: ~4x fewer instructions per output.
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) H8 { __half2 h[4]; };
+// 16-byte global accesses go through uint4: nvcc scalarises a copy of the half2[4] struct into four 32-bit LDG/STG
+__device__ __forceinline__ H8 ldg_h8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<H8*>(&u); }
+__device__ __forceinline__ void stg_h8(void* p, const H8& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
 
 __device__ __forceinline__ void dw_stage_input_h(const DwTileArgs& a, H8* s_in, int b, int oy0, int ox0, int c0, bool cv_ok) {
   const int tid = threadIdx.x, v = tid & 7;
@@ -530,7 +533,7 @@ __device__ __forceinline__ void dw_stage_input_h(const DwTileArgs& a, H8* s_in, 
       const int py = p / a.iw, px = p - py * a.iw;
       const int gy = gy0 + py, gx = gx0 + px;
       inb[u] = p < npos && cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-      if (inb[u]) raw[u] = *reinterpret_cast<const H8*>(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc);
+      if (inb[u]) raw[u] = ldg_h8(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_h_kernel(const DwTileArgs
         H8 o;
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc) = o;
+        stg_h8(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, o);
       }
     }
   }
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileAr
         const int q = (tid >> 3) + 32 * j;
         const int oy = q / kTW, ox = q - oy * kTW;
         ok[j] = oy0 + oy < a.Ho && ox0 + ox < a.Wo;
-        if (ok[j]) g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
+        if (ok[j]) g[j] = ldg_h8(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
         else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
@@ -981,7 +984,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         H8 o;
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        *reinterpret_cast<H8*>(y + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc) = o;
+        stg_h8(y + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc, o);
       }
     }
     if (pro) fence_proxy_async();     // generic-proxy writes of the transform vs the TMA that will refill this buffer
@@ -1077,7 +1080,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
       const int oy = q / kTW, ox = q - oy * kTW;
       const int gy = oy0 + oy * a.sub, gx = ox0 + ox * a.sub;
       if (cv_ok && gy < a.Ho && gx < a.Wo)
-        g[j] = *reinterpret_cast<const H8*>(dy + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc);
+        g[j] = ldg_h8(dy + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc);
       else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
@@ -1196,10 +1199,10 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
         const bool x0 = ix0 >= 0 && ix0 < a.W, x1 = ix0 + 1 >= 0 && ix0 + 1 < a.W;
         __half* p = dx + ((static_cast<long long>(b) * a.H + iy0) * a.W + ix0) * a.C + cc;
         const long long rs = static_cast<long long>(a.W) * a.C;
-        if (y0 && x0) *reinterpret_cast<H8*>(p) = o00;
-        if (y0 && x1) *reinterpret_cast<H8*>(p + a.C) = o01;
-        if (y1 && x0) *reinterpret_cast<H8*>(p + rs) = o10;
-        if (y1 && x1) *reinterpret_cast<H8*>(p + rs + a.C) = o11;
+        if (y0 && x0) stg_h8(p, o00);
+        if (y0 && x1) stg_h8(p + a.C, o01);
+        if (y1 && x0) stg_h8(p + rs, o10);
+        if (y1 && x1) stg_h8(p + rs + a.C, o11);
       }
     }
     __syncthreads();
