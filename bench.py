@@ -371,12 +371,19 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     name, (ms_k, bytes_k, n_k) = top
     achieved = bytes_k / (ms_k * 1e-3) / 1e9
-    traffic = None
+    # achieved = algorithmic bytes per launch / average launch duration (= family bytes / family time of the step);
+    # traffic = DRAM bytes per launch: the family's ncu-measured DRAM/algorithmic ratio (profiles/) x bytes per launch
+    traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get(name)
+        ent = json.load(open(tr_path)).get(name)
+        if ent:
+            traffic = ent["dram_over_algorithmic"] * bytes_k / n_k
+            traffic_src = ent["source"]
     roofline = {"bound": "hbm", "kernel": name, "launches_per_step": n_k, "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": bytes_k / n_k, "avg_launch_us": ms_k * 1e3 / n_k,
+                "peak_source": peak_src,
                 "share_of_step": ms_k / tot_ms,
                 "per_family_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
                 "per_family_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[0] > 0 and v[1] > 0}}
