@@ -161,11 +161,25 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) 
 
 // fp16 specialisation of the reduce pass: packed half2 arithmetic, 4-row partial sums on half2 folded into fp32
 // accumulators (the generic kernel is instruction-issue bound: ~13 instructions per element, 1.7 TB/s)
-struct __align__(16) BH8 { __half2 h[4]; };
+template <typename T> struct BP2;
+template <> struct BP2<__half> {
+  using t = __half2;
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ t bcast(float a) { return __float2half2_rn(a); }
+  static __device__ __forceinline__ float2 unpack(t v) { return __half22float2(v); }
+};
+template <> struct BP2<__nv_bfloat16> {
+  using t = __nv_bfloat162;
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ t bcast(float a) { return __float2bfloat162_rn(a); }
+  static __device__ __forceinline__ float2 unpack(t v) { return __bfloat1622float2(v); }
+};
+template <typename T> struct __align__(16) BV8 { typename BP2<T>::t h[4]; };
 // 16-byte global accesses go through uint4: nvcc scalarises a copy of the half2[4] struct into four 32-bit LDG/STG
-__device__ __forceinline__ BH8 ldg_bh8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<BH8*>(&u); }
-__device__ __forceinline__ void stg_bh8(void* p, const BH8& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
+template <typename T> __device__ __forceinline__ BV8<T> ldg_bh8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<BV8<T>*>(&u); }
+template <typename T> __device__ __forceinline__ void stg_bh8(void* p, const BV8<T>& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
 
+template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
   extern __shared__ float s_red[];   // [rpb][2*C] per-row-group partial sums (no shared atomics: they were a 32-way
                                      // CAS contention, a third of the kernel on the narrow project BNs)
@@ -173,28 +187,28 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
   if (tid < a.rpb * a.cv) {
     const int r_in = tid / a.cv;
     const int c0 = (tid - r_in * a.cv) * 8;
-    __half2 sc2[4], sh2[4], mu2[4], rs2[4];
+    typename BP2<T>::t sc2[4], sh2[4], mu2[4], rs2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      sc2[k] = __floats2half2_rn(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
-      sh2[k] = __floats2half2_rn(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
-      mu2[k] = __floats2half2_rn(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
-      rs2[k] = __floats2half2_rn(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
+      sc2[k] = BP2<T>::pack(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
+      sh2[k] = BP2<T>::pack(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
+      mu2[k] = BP2<T>::pack(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
+      rs2[k] = BP2<T>::pack(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
     }
-    const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+    const typename BP2<T>::t zero2 = BP2<T>::bcast(0.f), six2 = BP2<T>::bcast(6.f);
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const __half* x = reinterpret_cast<const __half*>(a.x);
-    const __half* da = reinterpret_cast<const __half*>(a.da);
+    const T* x = reinterpret_cast<const T*>(a.x);
+    const T* da = reinterpret_cast<const T*>(a.da);
     const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
     constexpr int U = 4;
     for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
-      BH8 xv[U], gv[U];
+      BV8<T> xv[U], gv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long r = r0 + u * a.rpb;
         if (r < a.M) {
-          xv[u] = ldg_bh8(x + r * a.C + c0);
-          gv[u] = ldg_bh8(da + r * a.C + c0);
+          xv[u] = ldg_bh8<T>(x + r * a.C + c0);
+          gv[u] = ldg_bh8<T>(da + r * a.C + c0);
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) { xv[u].h[k] = zero2; gv[u].h[k] = zero2; }
@@ -202,20 +216,20 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        __half2 p1 = zero2, p2 = zero2;
+        typename BP2<T>::t p1 = zero2, p2 = zero2;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          __half2 dz = gv[u].h[k];
+          typename BP2<T>::t dz = gv[u].h[k];
           if (a.act != DLB_ACT_NONE) {
-            const __half2 z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
-            __half2 m = __hgt2(z, zero2);
+            const typename BP2<T>::t z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
+            typename BP2<T>::t m = __hgt2(z, zero2);
             if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
             dz = __hmul2(dz, m);
           }
           p1 = __hadd2(p1, dz);
           p2 = __hfma2(dz, __hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]), p2);
         }
-        const float2 f1 = __half22float2(p1), f2 = __half22float2(p2);
+        const float2 f1 = BP2<T>::unpack(p1), f2 = BP2<T>::unpack(p2);
         s1[2 * k] += f1.x; s1[2 * k + 1] += f1.y; s2[2 * k] += f2.x; s2[2 * k + 1] += f2.y;
       }
     }
@@ -289,6 +303,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
 
 // fp16 specialisation of the apply pass: mask and x-hat on packed half2, the projection
 // dz - mean(dz) - xhat * mean(dz * xhat) in fp32 (the mean terms are far below one fp16 ulp of dz)
+template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a) {
   const int tid = threadIdx.x;
   if (blockIdx.x == 0) {
@@ -300,15 +315,15 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
   if (tid >= a.rpb * a.cv) return;
   const int r_in = tid / a.cv;
   const int c0 = (tid - r_in * a.cv) * 8;
-  __half2 sc2[4], sh2[4], mu2[4], rs2[4];
+  typename BP2<T>::t sc2[4], sh2[4], mu2[4], rs2[4];
   float sc[8], k1[8], k2[8];
   const float invM = 1.f / static_cast<float>(a.M);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    sc2[k] = __floats2half2_rn(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
-    sh2[k] = __floats2half2_rn(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
-    mu2[k] = __floats2half2_rn(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
-    rs2[k] = __floats2half2_rn(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
+    sc2[k] = BP2<T>::pack(a.scale[c0 + 2 * k], a.scale[c0 + 2 * k + 1]);
+    sh2[k] = BP2<T>::pack(a.shift[c0 + 2 * k], a.shift[c0 + 2 * k + 1]);
+    mu2[k] = BP2<T>::pack(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
+    rs2[k] = BP2<T>::pack(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -316,41 +331,41 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a)
     k1[k] = a.frozen ? 0.f : static_cast<float>(a.red[c0 + k]) * invM;
     k2[k] = a.frozen ? 0.f : static_cast<float>(a.red[a.C + c0 + k]) * invM;
   }
-  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
-  const __half* x = reinterpret_cast<const __half*>(a.x);
-  const __half* da = reinterpret_cast<const __half*>(a.da);
-  __half* dx = reinterpret_cast<__half*>(a.dx);
+  const typename BP2<T>::t zero2 = BP2<T>::bcast(0.f), six2 = BP2<T>::bcast(6.f);
+  const T* x = reinterpret_cast<const T*>(a.x);
+  const T* da = reinterpret_cast<const T*>(a.da);
+  T* dx = reinterpret_cast<T*>(a.dx);
   const long long rstride = static_cast<long long>(gridDim.x) * a.rpb;
   constexpr int U = 4;
   for (long long r0 = static_cast<long long>(blockIdx.x) * a.rpb * U + r_in; r0 < a.M; r0 += rstride * U) {
-    BH8 xv[U], gv[U];
+    BV8<T> xv[U], gv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * a.rpb;
       if (r < a.M) {
-        xv[u] = ldg_bh8(x + r * a.C + c0);
-        gv[u] = ldg_bh8(da + r * a.C + c0);
+        xv[u] = ldg_bh8<T>(x + r * a.C + c0);
+        gv[u] = ldg_bh8<T>(da + r * a.C + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * a.rpb;
       if (r >= a.M) continue;
-      BH8 o;
+      BV8<T> o;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        __half2 dz = gv[u].h[k];
+        typename BP2<T>::t dz = gv[u].h[k];
         if (a.act != DLB_ACT_NONE) {
-          const __half2 z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
-          __half2 m = __hgt2(z, zero2);
+          const typename BP2<T>::t z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
+          typename BP2<T>::t m = __hgt2(z, zero2);
           if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
           dz = __hmul2(dz, m);
         }
-        const float2 dzf = __half22float2(dz);
-        const float2 xh = __half22float2(__hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]));
+        const float2 dzf = BP2<T>::unpack(dz);
+        const float2 xh = BP2<T>::unpack(__hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]));
         const float o0 = sc[2 * k] * (dzf.x - k1[2 * k] - xh.x * k2[2 * k]);
         const float o1 = sc[2 * k + 1] * (dzf.y - k1[2 * k + 1] - xh.y * k2[2 * k + 1]);
-        o.h[k] = __floats2half2_rn(o0, o1);
+        o.h[k] = BP2<T>::pack(o0, o1);
       }
       stg_bh8(dx + r * a.C + c0, o);
     }
@@ -496,7 +511,9 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   const size_t smem = 2 * p->C * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16 && p->drop_rate <= 0.f)
-    bn_bwd_reduce_h_kernel<<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);       // [rpb][2C] <= 16 KB
+    bn_bwd_reduce_h_kernel<__half><<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);       // [rpb][2C] <= 16 KB
+  else if (p->dtype == DLB_BF16 && p->drop_rate <= 0.f)
+    bn_bwd_reduce_h_kernel<__nv_bfloat16><<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);
   else if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
   else bn_bwd_reduce_kernel<float><<<grid, 256, smem, st>>>(a);
@@ -513,7 +530,8 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   long long cap = static_cast<long long>(num_sms()) * 6;
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<<<grid, 256, 0, st>>>(a);
+  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<__half><<<grid, 256, 0, st>>>(a);
+  else if (p->dtype == DLB_BF16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
   else if (p->dtype == DLB_BF16) bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(a);

@@ -502,266 +502,25 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs
 // 3-tap row sums run on packed half2 (HFMA2 / HMNMX2), rows are added in fp32, filter taps are 36 half2
 // registers instead of 72 floats, and tap offsets are precomputed: ~4x fewer instructions per output.
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) H8 { __half2 h[4]; };
+// 16-bit pair traits: the TMA depthwise kernels are written once for __half and __nv_bfloat16 (packed HFMA2 /
+// HFMA2.BF16; the arithmetic intrinsics are overloaded for both pair types)
+template <typename T> struct P2;
+template <> struct P2<__half> {
+  using t = __half2;
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ t bcast(float a) { return __float2half2_rn(a); }
+  static __device__ __forceinline__ float2 unpack(t v) { return __half22float2(v); }
+};
+template <> struct P2<__nv_bfloat16> {
+  using t = __nv_bfloat162;
+  static __device__ __forceinline__ t pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ t bcast(float a) { return __float2bfloat162_rn(a); }
+  static __device__ __forceinline__ float2 unpack(t v) { return __bfloat1622float2(v); }
+};
+template <typename T> struct __align__(16) V8 { typename P2<T>::t h[4]; };
 // 16-byte global accesses go through uint4: nvcc scalarises a copy of the half2[4] struct into four 32-bit LDG/STG
-__device__ __forceinline__ H8 ldg_h8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<H8*>(&u); }
-__device__ __forceinline__ void stg_h8(void* p, const H8& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
-
-__device__ __forceinline__ void dw_stage_input_h(const DwTileArgs& a, H8* s_in, int b, int oy0, int ox0, int c0, bool cv_ok) {
-  const int tid = threadIdx.x, v = tid & 7;
-  const int cc = c0 + v * 8;
-  __half2 sc2[4], sh2[4];
-  const bool pro = a.in_scale != nullptr;
-  if (pro && cv_ok) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      sc2[i] = __floats2half2_rn(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
-      sh2[i] = __floats2half2_rn(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
-    }
-  }
-  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
-  const __half* x = reinterpret_cast<const __half*>(a.x);
-  const int gy0 = oy0 * a.stride - a.pad_t, gx0 = ox0 * a.stride - a.pad_l;
-  const int npos = a.ih * a.iw;
-  constexpr int U = 4;
-  for (int p0 = tid >> 3; p0 < npos; p0 += 32 * U) {
-    H8 raw[U];
-    bool inb[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + 32 * u;
-      const int py = p / a.iw, px = p - py * a.iw;
-      const int gy = gy0 + py, gx = gx0 + px;
-      inb[u] = p < npos && cv_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-      if (inb[u]) raw[u] = ldg_h8(x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * a.C + cc);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + 32 * u;
-      if (p >= npos) continue;
-      H8 o;
-      if (inb[u]) {
-        o = raw[u];
-        if (pro) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __half2 z = __hfma2(o.h[i], sc2[i], sh2[i]);
-            if (a.in_act == DLB_ACT_RELU6) z = __hmin2(__hmax2(z, zero2), six2);
-            else if (a.in_act == DLB_ACT_RELU) z = __hmax2(z, zero2);
-            o.h[i] = z;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o.h[i] = zero2;
-      }
-      s_in[static_cast<size_t>(p) * kCV + v] = o;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256, 2) dw_fwd_tiled_h_kernel(const DwTileArgs a) {
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  H8* s_in = reinterpret_cast<H8*>(s_raw);
-  float* s_stats = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * sizeof(H8));   // [2][64]
-  const int tid = threadIdx.x, v = tid & 7;
-  const bool stats = a.stat_sum != nullptr;
-  __half2 w2[9][4];
-  float ssum[8], ssqs[8];
-  int off[9];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
-  int cur_chunk = -1;
-  __half* y = reinterpret_cast<__half*>(a.y);
-  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
-
-  auto flush_stats = [&](int chunk) {
-    __syncthreads();
-    if (tid < 128) s_stats[tid] = 0.f;
-    __syncthreads();
-    if (chunk * 64 + v * 8 < a.C) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { atomicAdd(&s_stats[v * 8 + i], ssum[i]); atomicAdd(&s_stats[64 + v * 8 + i], ssqs[i]); }
-    }
-    __syncthreads();
-    if (tid < 64 && chunk * 64 + tid < a.C) {
-      atomicAdd(&a.stat_sum[chunk * 64 + tid], static_cast<double>(s_stats[tid]));
-      atomicAdd(&a.stat_sqs[chunk * 64 + tid], static_cast<double>(s_stats[64 + tid]));
-    }
-  };
-
-  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
-  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
-  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
-  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int chunk = tile / per_chunk;
-    int r = tile - chunk * per_chunk;
-    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
-    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-    const int c0 = chunk * 64, cc = c0 + v * 8;
-    const bool cv_ok = cc < a.C;
-    if (chunk != cur_chunk) {
-      if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
-      cur_chunk = chunk;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
-      if (cv_ok) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int ts = a.flip ? 8 - t : t;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
-        }
-      }
-    }
-    const int oy0 = ty * kTH, ox0 = tx * kTW;
-    __syncthreads();
-    dw_stage_input_h(a, s_in, b, oy0, ox0, c0, cv_ok);
-    __syncthreads();
-    if (cv_ok) {
-#pragma unroll 2
-      for (int j = 0; j < (kTH * kTW) / 32; ++j) {
-        const int q = (tid >> 3) + 32 * j;
-        const int oy = q / kTW, ox = q - oy * kTW;
-        if (oy0 + oy >= a.Ho || ox0 + ox >= a.Wo) continue;
-        const H8* base = s_in + static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          __half2 racc[4];
-          {
-            const H8 xv = base[off[ky * 3]];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) racc[i] = __hmul2(xv.h[i], w2[ky * 3][i]);
-          }
-#pragma unroll
-          for (int kx = 1; kx < 3; ++kx) {
-            const H8 xv = base[off[ky * 3 + kx]];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
-        }
-        if (a.out_scale) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], a.out_scale[cc + i], a.out_shift[cc + i]), a.out_act);
-        }
-        if (stats) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssqs[i] = fmaf(acc[i], acc[i], ssqs[i]); }
-        }
-        H8 o;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        stg_h8(y + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc, o);
-      }
-    }
-  }
-  if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
-}
-
-__global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_h_kernel(const DwTileArgs a) {
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  H8* s_in = reinterpret_cast<H8*>(s_raw);
-  float* s_dw = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * sizeof(H8));   // [9][64]
-  const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
-  float acc[9][8];
-  int off[9];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.dil * a.iw + kx * a.dil) * kCV;
-  int cur_chunk = -1;
-  const __half* dy = reinterpret_cast<const __half*>(a.dy);
-  const int per_chunk = a.B * a.tiles_y * a.tiles_x;
-
-  auto flush = [&](int chunk) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float x = acc[t][i];
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
-        acc[t][i] = x;
-      }
-    __syncthreads();
-    for (int i = tid; i < 9 * 64; i += 256) s_dw[i] = 0.f;
-    __syncthreads();
-    if (lane < 8) {
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * 64 + v * 8 + i], acc[t][i]);
-    }
-    __syncthreads();
-    for (int i = tid; i < 9 * 64; i += 256) {
-      const int t = i >> 6, c = chunk * 64 + (i & 63);
-      if (c < a.C) atomicAdd(&a.dw[t * a.C + c], s_dw[i]);
-    }
-  };
-
-  // contiguous tile range per CTA (chunk-major order): the channel chunk -- filter registers, statistics /
-  // gradient accumulators -- changes at most a couple of times per CTA instead of on almost every tile
-  const int tile_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * a.num_tiles / gridDim.x);
-  const int tile_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * a.num_tiles / gridDim.x);
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int chunk = tile / per_chunk;
-    int r = tile - chunk * per_chunk;
-    const int b = r / (a.tiles_y * a.tiles_x); r -= b * a.tiles_y * a.tiles_x;
-    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-    const int c0 = chunk * 64, cc = c0 + v * 8;
-    const bool cv_ok = cc < a.C;
-    if (chunk != cur_chunk) {
-      if (cur_chunk >= 0) flush(cur_chunk);
-      cur_chunk = chunk;
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-    }
-    const int oy0 = ty * kTH, ox0 = tx * kTW;
-    __syncthreads();
-    dw_stage_input_h(a, s_in, b, oy0, ox0, c0, cv_ok);
-    __syncthreads();
-    if (cv_ok) {
-      constexpr int NP = (kTH * kTW) / 32;
-      H8 g[NP];
-      bool ok[NP];
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const int q = (tid >> 3) + 32 * j;
-        const int oy = q / kTW, ox = q - oy * kTW;
-        ok[j] = oy0 + oy < a.Ho && ox0 + ox < a.Wo;
-        if (ok[j]) g[j] = ldg_h8(dy + ((static_cast<size_t>(b) * a.Ho + oy0 + oy) * a.Wo + ox0 + ox) * a.C + cc);
-        else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
-        }
-      }
-      // products of the thread's 4 pixels are summed on packed half2, then folded into the fp32 accumulators
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        __half2 p2[4];
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const int q = (tid >> 3) + 32 * j;
-          const int oy = q / kTW, ox = q - oy * kTW;
-          const H8 xv = s_in[static_cast<size_t>(oy * a.stride * a.iw + ox * a.stride) * kCV + v + off[t]];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) p2[i] = j == 0 ? __hmul2(xv.h[i], g[j].h[i]) : __hfma2(xv.h[i], g[j].h[i], p2[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(p2[i]); acc[t][2 * i] += f.x; acc[t][2 * i + 1] += f.y; }
-      }
-    }
-  }
-  if (cur_chunk >= 0) flush(cur_chunk);
-}
+template <typename T> __device__ __forceinline__ V8<T> ldg_h8(const void* p) { uint4 u = *reinterpret_cast<const uint4*>(p); return *reinterpret_cast<V8<T>*>(&u); }
+template <typename T> __device__ __forceinline__ void stg_h8(void* p, const V8<T>& o) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&o); }
 
 // ---------------------------------------------------------------------------------------------
 // TMA-staged, double-buffered fp16 depthwise kernels.  One cp.async.bulk.tensor (4D box [ih, iw, 64 ch], zero fill
@@ -788,28 +547,29 @@ __device__ __forceinline__ void dw_decode_tile(const DwTileArgs& a, int r, int& 
 // Explicit shared-window accesses: the tile buffers are selected at run time (double buffer), which makes nvcc fall
 // back to generic 32-bit LD.E/ST.E (4 instructions and 4-way bank conflicts per 16-byte vector) -- ld/st.shared.v4 on a
 // 32-bit shared address keeps every tile access one LDS.128 / STS.128.
-__device__ __forceinline__ H8 lds_h8(uint32_t saddr) {
+template <typename T> __device__ __forceinline__ V8<T> lds_h8(uint32_t saddr) {
   uint4 u;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
-  return *reinterpret_cast<H8*>(&u);
+  return *reinterpret_cast<V8<T>*>(&u);
 }
-__device__ __forceinline__ void sts_h8(uint32_t saddr, const H8& o) {
+template <typename T> __device__ __forceinline__ void sts_h8(uint32_t saddr, const V8<T>& o) {
   const uint4 u = *reinterpret_cast<const uint4*>(&o);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
+template <typename T>
 __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_t s_in, int oy0, int ox0, int c0, bool cv_ok) {
   // in place: a = act(x * scale + shift) inside the image, exact zeros in the padding
   const int tid = threadIdx.x, v = tid & 7;
   const int cc = c0 + v * 8;
   if (!cv_ok) return;
-  __half2 sc2[4], sh2[4];
+  typename P2<T>::t sc2[4], sh2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    sc2[i] = __floats2half2_rn(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
-    sh2[i] = __floats2half2_rn(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
+    sc2[i] = P2<T>::pack(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
+    sh2[i] = P2<T>::pack(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
   }
-  const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
+  const typename P2<T>::t zero2 = P2<T>::bcast(0.f), six2 = P2<T>::bcast(6.f);
   const int npos = a.ih * a.iw;
   int p = tid >> 3;
   uint32_t addr = s_in + static_cast<uint32_t>(p * kCV + v) * 16u;
@@ -818,14 +578,14 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
     // non-NaN operand), so ReLU / ReLU6 produce the exact zero padding without any coordinate test.
     if (a.in_act == DLB_ACT_RELU6) {
       for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
-        H8 o = lds_h8(addr);
+        V8<T> o = lds_h8<T>(addr);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.h[i] = __hmin2(__hmax2(__hfma2(o.h[i], sc2[i], sh2[i]), zero2), six2);
         sts_h8(addr, o);
       }
     } else {
       for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
-        H8 o = lds_h8(addr);
+        V8<T> o = lds_h8<T>(addr);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.h[i] = __hmax2(__hfma2(o.h[i], sc2[i], sh2[i]), zero2);
         sts_h8(addr, o);
@@ -840,17 +600,17 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
   for (; p < npos; p += 32, addr += 32u * kCV * 16u) {
     const int gy = gy0 + py * a.sub, gx = gx0 + px * a.sub;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-      H8 o = lds_h8(addr);
+      V8<T> o = lds_h8<T>(addr);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        __half2 z = __hfma2(o.h[i], sc2[i], sh2[i]);
+        typename P2<T>::t z = __hfma2(o.h[i], sc2[i], sh2[i]);
         if (a.in_act == DLB_ACT_RELU6) z = __hmin2(__hmax2(z, zero2), six2);
         else if (a.in_act == DLB_ACT_RELU) z = __hmax2(z, zero2);
         o.h[i] = z;
       }
       sts_h8(addr, o);
     } else {
-      H8 o;
+      V8<T> o;
 #pragma unroll
       for (int i = 0; i < 4; ++i) o.h[i] = zero2;
       sts_h8(addr, o);
@@ -860,9 +620,10 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
   extern __shared__ __align__(128) uint8_t s_raw[];
-  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
+  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
   const uint32_t s_base = smem_u32(s_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
@@ -876,7 +637,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     mbar_fence_init();
   }
   __syncthreads();
-  __half2 w2[9][4];
+  typename P2<T>::t w2[9][4];
   float ssum[8], ssqs[8];
   int off[9];
 #pragma unroll
@@ -884,7 +645,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.sdil * a.iw + kx * a.sdil) * kCV * 16;
   int cur_chunk = -1;
-  __half* y = reinterpret_cast<__half*>(a.y);
+  T* y = reinterpret_cast<T*>(a.y);
 
   auto flush_stats = [&](int chunk) {
     __syncthreads();
@@ -935,7 +696,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         for (int t = 0; t < 9; ++t) {
           const int ts = a.flip ? 8 - t : t;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
+          for (int i = 0; i < 4; ++i) w2[t][i] = P2<T>::pack(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
         }
       }
     }
@@ -944,7 +705,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     mbar_wait(&full[slot], (it >> 1) & 1);
     const uint32_t s_in = s_base + slot * buf_stride;
     if (pro) {
-      dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
+      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok);
       __syncthreads();
     }
     if (cv_ok) {
@@ -958,20 +719,20 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          __half2 racc[4];
+          typename P2<T>::t racc[4];
           {
-            const H8 xv = lds_h8(base + off[ky * 3]);
+            const V8<T> xv = lds_h8<T>(base + off[ky * 3]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) racc[i] = __hmul2(xv.h[i], w2[ky * 3][i]);
           }
 #pragma unroll
           for (int kx = 1; kx < 3; ++kx) {
-            const H8 xv = lds_h8(base + off[ky * 3 + kx]);
+            const V8<T> xv = lds_h8<T>(base + off[ky * 3 + kx]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+          for (int i = 0; i < 4; ++i) { const float2 f = P2<T>::unpack(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
         }
         if (a.out_scale) {
 #pragma unroll
@@ -981,9 +742,9 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssqs[i] = fmaf(acc[i], acc[i], ssqs[i]); }
         }
-        H8 o;
+        V8<T> o;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o.h[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) o.h[i] = P2<T>::pack(acc[2 * i], acc[2 * i + 1]);
         stg_h8(y + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc, o);
       }
     }
@@ -993,9 +754,10 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
   extern __shared__ __align__(128) uint8_t s_raw[];
-  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(H8);
+  const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
   const uint32_t s_base = smem_u32(s_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
@@ -1015,7 +777,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) off[ky * 3 + kx] = (ky * a.sdil * a.iw + kx * a.sdil) * kCV * 16;
   int cur_chunk = -1;
-  const __half* dy = reinterpret_cast<const __half*>(a.dy);
+  const T* dy = reinterpret_cast<const T*>(a.dy);
 
   auto flush = [&](int chunk) {
 #pragma unroll
@@ -1073,39 +835,39 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
     if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
     // the thread's four dy vectors are requested before waiting for the input tile
     constexpr int NP = (kTH * kTW) / 32;
-    H8 g[NP];
+    V8<T> g[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const int q = (tid >> 3) + 32 * j;
       const int oy = q / kTW, ox = q - oy * kTW;
       const int gy = oy0 + oy * a.sub, gx = ox0 + ox * a.sub;
       if (cv_ok && gy < a.Ho && gx < a.Wo)
-        g[j] = ldg_h8(dy + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc);
+        g[j] = ldg_h8<T>(dy + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc);
       else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g[j].h[i] = __float2half2_rn(0.f);
+        for (int i = 0; i < 4; ++i) g[j].h[i] = P2<T>::bcast(0.f);
       }
     }
     mbar_wait(&full[slot], (it >> 1) & 1);
     const uint32_t s_in = s_base + slot * buf_stride;
     if (pro) {
-      dw_transform_tile_h(a, s_in, oy0, ox0, c0, cv_ok);
+      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok);
       __syncthreads();
     }
     if (cv_ok) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        __half2 p2[4];
+        typename P2<T>::t p2[4];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           const int q = (tid >> 3) + 32 * j;
           const int oy = q / kTW, ox = q - oy * kTW;
-          const H8 xv = lds_h8(s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u + off[t]);
+          const V8<T> xv = lds_h8<T>(s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u + off[t]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) p2[i] = j == 0 ? __hmul2(xv.h[i], g[j].h[i]) : __hfma2(xv.h[i], g[j].h[i], p2[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(p2[i]); acc[t][2 * i] += f.x; acc[t][2 * i + 1] += f.y; }
+        for (int i = 0; i < 4; ++i) { const float2 f = P2<T>::unpack(p2[i]); acc[t][2 * i] += f.x; acc[t][2 * i + 1] += f.y; }
       }
     }
     if (pro) fence_proxy_async();
@@ -1129,6 +891,7 @@ struct DwS2Args {
   int tiles_x, tiles_y, chunks;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwS2Args a) {
   extern __shared__ __align__(128) uint8_t s_raw[];
   constexpr int IH = kTH + 1, IW = kTW + 1;
@@ -1147,12 +910,12 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
   const int n_sp = a.B * a.tiles_y * a.tiles_x;
   const int cc = chunk * 64 + v * 8;
   const bool cv_ok = cc < a.C;
-  __half2 w2[9][4];
+  typename P2<T>::t w2[9][4];
   if (cv_ok) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w2[t][i] = __floats2half2_rn(a.w[t * a.C + cc + 2 * i], a.w[t * a.C + cc + 2 * i + 1]);
+      for (int i = 0; i < 4; ++i) w2[t][i] = P2<T>::pack(a.w[t * a.C + cc + 2 * i], a.w[t * a.C + cc + 2 * i + 1]);
   }
   auto decode = [&](int sp, int& b, int& m0, int& n0) {
     b = sp / (a.tiles_y * a.tiles_x);
@@ -1168,7 +931,7 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
   };
   if (grp >= ngrp) return;
   if (tid == 0 && grp < n_sp) issue(grp, 0);
-  __half* dx = reinterpret_cast<__half*>(a.dx);
+  T* dx = reinterpret_cast<T*>(a.dx);
   for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
     const int slot = it & 1;
     int b, m0, n0;
@@ -1182,11 +945,11 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
         const int q = (tid >> 3) + 32 * j;
         const int cm = q / kTW, cn = q - cm * kTW;          // cell (m0 + cm, n0 + cn); smem position (cm + 1, cn + 1)
         const uint32_t base = s_in + static_cast<uint32_t>(((cm + 1) * IW + cn + 1) * kCV + v) * 16u;
-        const H8 d11 = lds_h8(base);                                     // dy[m, n]
-        const H8 d01 = lds_h8(base - IW * kCV * 16);                     // dy[m-1, n]
-        const H8 d10 = lds_h8(base - kCV * 16);                          // dy[m, n-1]
-        const H8 d00 = lds_h8(base - (IW + 1) * kCV * 16);               // dy[m-1, n-1]
-        H8 o00, o01, o10, o11;
+        const V8<T> d11 = lds_h8<T>(base);                                     // dy[m, n]
+        const V8<T> d01 = lds_h8<T>(base - IW * kCV * 16);                     // dy[m-1, n]
+        const V8<T> d10 = lds_h8<T>(base - kCV * 16);                          // dy[m, n-1]
+        const V8<T> d00 = lds_h8<T>(base - (IW + 1) * kCV * 16);               // dy[m-1, n-1]
+        V8<T> o00, o01, o10, o11;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           o00.h[i] = __hfma2(d00.h[i], w2[8][i], __hfma2(d10.h[i], w2[2][i], __hfma2(d01.h[i], w2[6][i], __hmul2(d11.h[i], w2[0][i]))));
@@ -1197,7 +960,7 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
         const int iy0 = 2 * (m0 + cm) - a.pad_t, ix0 = 2 * (n0 + cn) - a.pad_l;
         const bool y0 = iy0 >= 0 && iy0 < a.H, y1 = iy0 + 1 >= 0 && iy0 + 1 < a.H;
         const bool x0 = ix0 >= 0 && ix0 < a.W, x1 = ix0 + 1 >= 0 && ix0 + 1 < a.W;
-        __half* p = dx + ((static_cast<long long>(b) * a.H + iy0) * a.W + ix0) * a.C + cc;
+        T* p = dx + ((static_cast<long long>(b) * a.H + iy0) * a.W + ix0) * a.C + cc;
         const long long rs = static_cast<long long>(a.W) * a.C;
         if (y0 && x0) stg_h8(p, o00);
         if (y0 && x1) stg_h8(p + a.C, o01);
@@ -1624,29 +1387,31 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
   DLB_REQUIRE(smem <= 200 * 1024, "dw_conv: dilation %d needs a %zu-byte tile (> 200 KB)", a.dil, smem);
   if (smem > 48 * 1024)
     DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+  if constexpr (sizeof(T) == 2) {     // fp16 and bf16 take the TMA kernels
+    constexpr int kDt = std::is_same<T, __half>::value ? DLB_F16 : DLB_BF16;
     fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
     const size_t smem_t = 2 * tile_b + 16 + 128 * sizeof(float);
     CUtensorMap tm;
-    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
+    int rc = make_tmap_nhwc(&tm, kDt, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;
-    DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    DLB_CUDA(cudaFuncSetAttribute(dw_fwd_tma_h_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     const int per_sm_h = smem_t > 110 * 1024 ? 1 : 2;
     const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
     int ngrp = (num_sms() * per_sm_h) / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;
-    dw_fwd_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+    dw_fwd_tma_h_kernel<T><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
     g_launches++;
     return check_launch("dw_fwd_tma_h_kernel");
+  } else {
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;
+    const int cap = num_sms() * per_sm;
+    const int grid = a.num_tiles < cap ? a.num_tiles : cap;
+    dw_fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+    g_launches++;
+    return check_launch("dw_fwd_tiled_kernel");
   }
-  const int per_sm = smem > 100 * 1024 ? 1 : 2;
-  const int cap = num_sms() * per_sm;
-  const int grid = a.num_tiles < cap ? a.num_tiles : cap;
-  dw_fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
-  g_launches++;
-  return check_launch("dw_fwd_tiled_kernel");
 }
 
 template <typename T>
@@ -1658,25 +1423,27 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
     DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cap = num_sms();           // 1 CTA/SM (72 accumulators + staging need ~200 registers)
   const int grid = a.num_tiles < cap ? a.num_tiles : cap;
-  if (std::is_same<T, __half>::value) {
+  if constexpr (sizeof(T) == 2) {
+    constexpr int kDt = std::is_same<T, __half>::value ? DLB_F16 : DLB_BF16;
     fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
     const size_t smem_t = 2 * tile_b + 16 + 9 * 64 * sizeof(float);
     CUtensorMap tm;
-    int rc = make_tmap_nhwc(&tm, DLB_F16, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
+    int rc = make_tmap_nhwc(&tm, kDt, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;
-    DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    DLB_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_h_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
     int ngrp = num_sms() / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;
-    dw_wgrad_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+    dw_wgrad_tma_h_kernel<T><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
     g_launches++;
     return check_launch("dw_wgrad_tma_h_kernel");
+  } else {
+    dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+    g_launches++;
+    return check_launch("dw_wgrad_tiled_kernel");
   }
-  dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
-  g_launches++;
-  return check_launch("dw_wgrad_tiled_kernel");
 }
 
 extern "C" int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream) {
@@ -1718,7 +1485,7 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
       else if (p->dtype == DLB_BF16) rc = launch_dw_tiled<__nv_bfloat16>(a, st);
       else rc = launch_dw_tiled<float>(a, st);
       if (rc) return rc;
-    } else if (p->stride == 2 && p->dilation == 1 && p->dtype == DLB_F16) {
+    } else if (p->stride == 2 && p->dilation == 1 && (p->dtype == DLB_F16 || p->dtype == DLB_BF16)) {
       DwS2Args a{};
       a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.Ho = p->Ho; a.Wo = p->Wo;
       a.pad_t = p->pad_top; a.pad_l = p->pad_left; a.w = p->w; a.dx = p->dx;
@@ -1727,15 +1494,17 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
       a.tiles_y = (cells_y + kTH - 1) / kTH; a.tiles_x = (cells_x + kTW - 1) / kTW;
       a.chunks = (p->C + 63) / 64;
       CUtensorMap tm;
-      int rc = make_tmap_nhwc(&tm, DLB_F16, p->dy, p->B, p->Ho, p->Wo, p->C, 64, kTW + 1, kTH + 1, 1, 0);
+      int rc = make_tmap_nhwc(&tm, p->dtype, p->dy, p->B, p->Ho, p->Wo, p->C, 64, kTW + 1, kTH + 1, 1, 0);
       if (rc) return rc;
       const size_t smem_t = 2 * ((static_cast<size_t>(kTH + 1) * (kTW + 1) * kCV * 16 + 127) & ~size_t(127)) + 16;
-      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_data_s2_tma_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_data_s2_tma_h_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      DLB_CUDA(cudaFuncSetAttribute(dw_bwd_data_s2_tma_h_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       const int n_sp = a.B * a.tiles_y * a.tiles_x;
       int ngrp = (num_sms() * 2) / a.chunks;
       if (ngrp < 1) ngrp = 1;
       if (ngrp > n_sp) ngrp = n_sp;
-      dw_bwd_data_s2_tma_h_kernel<<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+      if (p->dtype == DLB_F16) dw_bwd_data_s2_tma_h_kernel<__half><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+      else dw_bwd_data_s2_tma_h_kernel<__nv_bfloat16><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
       g_launches++;
       rc = check_launch("dw_bwd_data_s2_tma_h_kernel");
       if (rc) return rc;

@@ -175,7 +175,7 @@ def _dw_ref(x, w, stride, dil, in_scale=None, in_shift=None, in_act=0):
     return y.permute(0, 2, 3, 1).contiguous(), (Ho, Wo, pt, pl)
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("H,W,C,stride,dil", [(32, 32, 96, 1, 1), (32, 48, 144, 2, 1), (33, 31, 32, 2, 1),
                                                (16, 16, 384, 1, 2), (16, 16, 960, 1, 4), (24, 24, 64, 1, 12),
                                                (8, 8, 2048, 1, 36),
@@ -197,12 +197,13 @@ def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
     ssqs = torch.zeros(C, device="cuda", dtype=torch.float64)
     ops.dw_conv_fwd(x, w, y, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc, in_shift=ish,
                     in_act=2, stat_sum=ssum, stat_sqs=ssqs)
-    # fp16: the prologue and the 3-tap row sums run on packed half2 (rows are added in fp32)
-    tol = 8e-3 if dtype == torch.float16 else 1e-5
+    # 16 bit: the prologue and the 3-tap row sums run on packed half2 / bfloat162 (rows are added in fp32)
+    tol = {torch.float16: 8e-3, torch.bfloat16: 5e-2, torch.float32: 1e-5}[dtype]
+    stol = {torch.float16: 2e-3, torch.bfloat16: 1e-2, torch.float32: 1e-4}[dtype]
     assert rel_err(y, ref) < tol
     yr = y.double()
-    assert rel_err(ssum, yr.sum((0, 1, 2))) < (2e-3 if dtype == torch.float16 else 1e-4)
-    assert rel_err(ssqs, (yr * yr).sum((0, 1, 2))) < (2e-3 if dtype == torch.float16 else 1e-4)
+    assert rel_err(ssum, yr.sum((0, 1, 2))) < stol
+    assert rel_err(ssqs, (yr * yr).sum((0, 1, 2))) < stol
     # backward: gradient w.r.t. the *activated* input a and w.r.t. the weights
     dy = torch.randn(B, Ho, Wo, C, device="cuda", generator=g).to(dtype)
     a = (x.float() * isc + ish).clamp(0, 6).requires_grad_(True)
@@ -213,7 +214,7 @@ def test_dw_conv_fwd_bwd(H, W, C, stride, dil, dtype):
     ops.dw_conv_bwd(x, dy, w, dx=dx, dw=dw, stride=stride, dilation=dil, pad_top=pt, pad_left=pl, in_scale=isc,
                     in_shift=ish, in_act=2)
     assert rel_err(dx, ga) < tol
-    assert rel_err(dw, gw) < (5e-3 if dtype == torch.float16 else 1e-3)
+    assert rel_err(dw, gw) < {torch.float16: 5e-3, torch.bfloat16: 3e-2, torch.float32: 1e-3}[dtype]
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
@@ -243,7 +244,7 @@ def test_stem_conv(H, W, dtype):
     assert rel_err(dw, gw) < 1e-4
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
 def test_bn_train_fwd_bwd(dtype):
     """finalize + apply (+residual) and the two-pass backward vs autograd through F.batch_norm."""
     ops = _ops()
@@ -266,7 +267,7 @@ def test_bn_train_fwd_bwd(dtype):
     ref = z.clamp(0, 6) + res.float()
     y = torch.empty_like(x)
     ops.bn_act_apply(x, y, scale=scale, shift=shift, act=2, res=res)
-    tol = 3e-3 if dtype == torch.float16 else 2e-5
+    tol = {torch.float16: 3e-3, torch.bfloat16: 2e-2, torch.float32: 2e-5}[dtype]
     assert rel_err(y, ref) < tol
     var_u = x.float().var(0, unbiased=True)
     assert rel_err(mv, 0.999 + 0.001 * var_u) < 1e-5
@@ -277,15 +278,16 @@ def test_bn_train_fwd_bwd(dtype):
     dx = torch.empty_like(x)
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_bwd(x, da, dx, scale=scale, shift=shift, mean=mean, rstd=rstd, act=2, red=red, dgamma=dgamma, dbeta=dbeta)
-    if dtype == torch.float16:
-        # the fp16 kernels evaluate the ReLU6 mask on packed half2: an element whose pre-activation lies within one
-        # fp16 ulp of 0 or 6 may flip, so compare in the L2 norm instead of the max norm
-        assert ((dx.float() - gx).norm() / gx.norm()).item() < 1e-2
+    if dtype != torch.float32:
+        # the 16-bit kernels evaluate the ReLU6 mask on packed pairs: an element whose pre-activation lies within one
+        # ulp of 0 or 6 may flip, so compare in the L2 norm instead of the max norm
+        assert ((dx.float() - gx).norm() / gx.norm()).item() < (1e-2 if dtype == torch.float16 else 5e-2)
     else:
         assert rel_err(dx, gx) < 1e-4
-    # fp16: the reduce pass runs on packed half2 with 4-row partial sums (x-hat from fp16 mean / rstd)
-    assert rel_err(dgamma, gg) < (2e-2 if dtype == torch.float16 else 1e-3)
-    assert rel_err(dbeta, gb) < (2e-2 if dtype == torch.float16 else 1e-3)
+    # 16 bit: the reduce pass runs on packed pairs with 4-row partial sums (x-hat from 16-bit mean / rstd)
+    rtol = {torch.float16: 2e-2, torch.bfloat16: 8e-2, torch.float32: 1e-3}[dtype]
+    assert rel_err(dgamma, gg) < rtol
+    assert rel_err(dbeta, gb) < rtol
 
 
 def test_dropout_apply_and_bwd_consistent():
