@@ -211,7 +211,7 @@ def profile_eager_step(engine, ws, B):
 
     names = ["pw_gemm", "pw_wgrad", "dw_conv_fwd", "dw_conv_bwd", "bn_act_apply", "bn_bwd", "stem_conv_fwd",
              "stem_conv_wgrad", "resize_softmax_ce", "global_avgpool_fwd", "global_avgpool_bwd", "adam_step", "cast",
-             "bn_finalize", "cast_weight", "small_gemm", "ce_grad_scale", "fill_zero"]
+             "bn_finalize", "cast_weight", "cast_weights_batched", "small_gemm", "ce_grad_scale", "fill_zero"]
     orig = {n: getattr(ops, n) for n in names}
 
     def wrap(n, f):

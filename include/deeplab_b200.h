@@ -75,7 +75,8 @@ typedef struct {
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
 
 /* Weight gradient of a 1x1 convolution: dW[K, N] (+)= A[M, K]^T * dY[M, N]  (fp32 out, ld = N).
- * tcgen05 with MN-major operands for 16-bit dtypes; SIMT for f32.  beta = 0 overwrites, 1 accumulates. */
+ * tcgen05 with MN-major operands for 16-bit dtypes; SIMT for f32.  beta = 0 overwrites, 1 accumulates (only 0 / 1).
+ * Split-M partial tiles are added into dW with fp32 reductions in L2, so the last bits depend on the arrival order. */
 typedef struct {
   int M, N, K;
   int dtype;
@@ -84,7 +85,7 @@ typedef struct {
   float* dW;      int ldw;
   float* dbias;             /* [N] column sums of dY, or NULL */
   float beta;
-  void* workspace;          /* split-M partials (tensor-core path), >= dlb_pw_wgrad_workspace_bytes() */
+  void* workspace;          /* unused since the partials are reduced in L2 (dlb_pw_wgrad_workspace_bytes() = 0); may be NULL */
   int64_t workspace_bytes;
 } dlb_pw_wgrad_params;
 int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream);
@@ -250,6 +251,11 @@ int dlb_adam_step(int64_t n, float* param, const float* grad, float* m, float* v
                   float beta1, float beta2, float eps, float decay, float grad_mult, void* stream);
 /* fp32 [K, N] master weight -> 16-bit W[K,N] and Wt[N,K] copies used by the GEMMs (either may be NULL) */
 int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_kn, void* w_nk, void* stream);
+/* The same for every 1x1 layer of the model in ONE launch (after each optimizer step).  `table` is a DEVICE array of
+ * n_entries x 8 int64: { w (const float*), w_kn (void* or 0), w_nk (void* or 0), K, N, ld_kn (row pitch of w_kn in
+ * elements, >= N), dtype (DLB_F16 / DLB_BF16 / DLB_F32) of the copies, first flat element index of the entry };
+ * total = sum of K*N. */
+int dlb_cast_weights_batched(int n_entries, const int64_t* table, int64_t total, void* stream);
 int dlb_cast(int64_t n, int src_dtype, const void* src, int dst_dtype, void* dst, void* stream);
 int dlb_fill_zero(void* p, int64_t bytes, void* stream);
 

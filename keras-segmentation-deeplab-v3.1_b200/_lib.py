@@ -102,7 +102,7 @@ EXPORTS = [
     "dlb_stem_conv_wgrad", "dlb_bn_finalize", "dlb_bn_fold", "dlb_bn_act_apply", "dlb_bn_bwd_reduce",
     "dlb_bn_bwd_apply", "dlb_global_avgpool_fwd", "dlb_global_avgpool_bwd", "dlb_small_gemm",
     "dlb_resize_softmax_fwd", "dlb_resize_softmax_ce", "dlb_ce_grad_scale", "dlb_phase_shift", "dlb_adam_step",
-    "dlb_cast_weight", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
+    "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
 ]
 
@@ -134,6 +134,7 @@ def lib() -> C.CDLL:
         L.dlb_adam_step.argtypes = [i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp]
         L.dlb_cast_weight.argtypes = [i32, i32, vp, i32, vp, vp, vp]
         L.dlb_cast.argtypes = [i64, i32, vp, i32, vp, vp]
+        L.dlb_cast_weights_batched.argtypes = [i32, vp, i64, vp]
         L.dlb_fill_zero.argtypes = [vp, i64, vp]
         L.dlb_confusion.argtypes = [i32, i64, i32, vp, vp, vp, vp]
         L.dlb_stem_conv_wgrad.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]

@@ -67,6 +67,35 @@ __global__ void cast_weight_kernel(int K, int N, const float* __restrict__ w, T*
   if (w_nk) Act<T>::st(&w_nk[static_cast<size_t>(n) * K + k], v);
 }
 
+// one launch for all layers: entry found by binary search over the prefix of flat element counts
+__global__ void __launch_bounds__(256) cast_weights_batched_kernel(int n_entries, const long long* __restrict__ tab, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab[mid * 8 + 7] <= i) lo = mid; else hi = mid - 1;
+    }
+    const long long* e = tab + lo * 8;
+    const float* w = reinterpret_cast<const float*>(e[0]);
+    const int K = static_cast<int>(e[3]), N = static_cast<int>(e[4]), ld = static_cast<int>(e[5]), dt = static_cast<int>(e[6]);
+    const int j = static_cast<int>(i - e[7]);
+    const int k = j / N, n = j - k * N;
+    const float v = w[j];
+    const size_t o_kn = static_cast<size_t>(k) * ld + n, o_nk = static_cast<size_t>(n) * K + k;
+    if (dt == DLB_F16) {
+      if (e[1]) reinterpret_cast<__half*>(e[1])[o_kn] = __float2half_rn(v);
+      if (e[2]) reinterpret_cast<__half*>(e[2])[o_nk] = __float2half_rn(v);
+    } else if (dt == DLB_BF16) {
+      if (e[1]) reinterpret_cast<__nv_bfloat16*>(e[1])[o_kn] = __float2bfloat16_rn(v);
+      if (e[2]) reinterpret_cast<__nv_bfloat16*>(e[2])[o_nk] = __float2bfloat16_rn(v);
+    } else {
+      if (e[1]) reinterpret_cast<float*>(e[1])[o_kn] = v;
+      if (e[2]) reinterpret_cast<float*>(e[2])[o_nk] = v;
+    }
+  }
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(long long n, const S* __restrict__ s, D* __restrict__ d) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -112,6 +141,17 @@ extern "C" int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_
   else cast_weight_kernel<float><<<grid, 256, 0, st>>>(K, N, w, (float*)w_kn, (float*)w_nk);
   g_launches++;
   return check_launch("cast_weight_kernel");
+}
+
+extern "C" int dlb_cast_weights_batched(int n_entries, const int64_t* table, int64_t total, void* stream) {
+  DLB_REQUIRE(n_entries > 0 && table && total > 0, "cast_weights_batched: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  cast_weights_batched_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(
+      n_entries, reinterpret_cast<const long long*>(table), total);
+  g_launches++;
+  return check_launch("cast_weights_batched_kernel");
 }
 
 extern "C" int dlb_cast(int64_t n, int src_dtype, const void* src, int dst_dtype, void* dst, void* stream) {

@@ -25,6 +25,7 @@ import torch
 
 from . import ops
 from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6
+from ._lib import _DT as L_DT
 
 # (expansion, stride, block_id, skip, rate, out_channels)   deeplabv3p.py:327-367 with alpha = 1
 MNV2_BLOCKS = [
@@ -220,9 +221,21 @@ class Engine:
                     d["nk32"] = torch.empty(N, K, device=dev, dtype=torch.float32)
                 if rec is self.head_conv and N % 8:
                     # dgrad reads W[K, N] as a [K, ld] matrix through TMA: pad the pitch to 32 (16-byte rule)
-                    d["kn_tmp"] = d["kn"]
                     d["kn"] = torch.zeros(K, self.ldl, device=dev, dtype=self.dtype)
                 self.wcopies[rec.name] = d
+        # descriptor table of the batched master -> copy cast (one launch after every optimizer step)
+        rows, start = [], 0
+        for rec in self.layers:
+            if rec.name in self.wcopies:
+                d, K, N = self.wcopies[rec.name], rec.cin, rec.cout
+                wp = rec.params[0].data.data_ptr()
+                rows.append([wp, d["kn"].data_ptr(), d["nk"].data_ptr(), K, N, d["kn"].shape[1], L_DT[self.dtype], start])
+                start += K * N
+                if "nk32" in d:
+                    rows.append([wp, 0, d["nk32"].data_ptr(), K, N, N, L_DT[torch.float32], start])
+                    start += K * N
+        self._cast_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self._cast_total = start
         # Subpixel: GEMM columns are stored permuted (jj, i, k) so the fused phase-shift store is contiguous
         self.sub_perm = self.sub_perm_inv = None
         if self.head == "subpixel":
@@ -287,17 +300,7 @@ class Engine:
 
     def refresh_weight_copies(self):
         """fp32 master -> 16-bit [K,N] / [N,K] GEMM operands (after load / set_weights / optimizer step)."""
-        for rec in self.layers:
-            if rec.name in self.wcopies:
-                d = self.wcopies[rec.name]
-                w = rec.params[0].data
-                if "kn_tmp" in d:
-                    ops.cast_weight(w, rec.cin, rec.cout, d["kn_tmp"], d["nk"])
-                    d["kn"][:, :rec.cout].copy_(d["kn_tmp"])
-                else:
-                    ops.cast_weight(w, rec.cin, rec.cout, d["kn"], d["nk"])
-                if "nk32" in d:
-                    ops.cast_weight(w, rec.cin, rec.cout, None, d["nk32"])
+        ops.cast_weights_batched(self._cast_table, self._cast_total)
         self._weights_dirty = False
 
     # ------------------------------------------------------------------------------------------------
@@ -359,8 +362,6 @@ class Engine:
             ws["wcount"] = torch.zeros(1, device=dev, dtype=torch.float64)
             ws["loss_sum"] = torch.zeros(1, device=dev, dtype=torch.float64)
             ws["argmax"] = torch.empty(B, self.H * self.W, device=dev, dtype=torch.uint8)
-            maxkn = max(rec.cin * rec.cout for rec in self.layers if rec.kind == "conv" and rec.kh == 1)
-            ws["wgrad_ws"] = torch.empty(2 * 148 * maxkn + 64, device=dev)
             if self.head == "subpixel":
                 ws["logits"] = E(B, self.H, self.W, self.n_out, dtype=torch.float32)
                 ws["dlogits"] = E(B, self.H, self.W, self.n_out, dtype=torch.float32)
@@ -560,7 +561,6 @@ class Engine:
         geo = ws["geo"]
         fh, fw = self.fh, self.fw
         HW = fh * fw
-        wsp = ws["wgrad_ws"]
         ops.fill_zero(self.bn_red)
         ops.fill_zero(self.grads)          # one memset: depthwise / stem gradients are accumulated with atomics
         first = self._first_trainable_index()
@@ -576,7 +576,7 @@ class Engine:
             dl = ops.cast(ws["dlogits"], ws["dlogits_lo"])
         if hc.trainable:
             ops.pw_wgrad(ws["feat"], dl, hc.params[0].grad.view(256, -1), N=hc.cout, dbias=hc.params[1].grad,
-                         workspace=wsp)
+                         beta=1.0)
         if first > self._order("concat_projection_BN"):
             return
         d_feat = ops.pw_gemm(dl, hw["kn"], g256a, K=hc.cout if self.head == "subpixel" else self.ldl, N=256)
@@ -590,7 +590,7 @@ class Engine:
         wcp = self.wcopies["concat_projection"]
         gW = cp.params[0].grad.view(512, 256)
         if cp.trainable:
-            ops.pw_wgrad(ws["a_a0"], dy_cp, gW[256:], workspace=wsp)
+            ops.pw_wgrad(ws["a_a0"], dy_cp, gW[256:], beta=1.0)
         # per-image bias gradient = column sums of dy_cp per image
         ops.global_avgpool_fwd(dy_cp, ws["d_rowbias"])
         if cp.trainable:
@@ -603,7 +603,7 @@ class Engine:
                            act=ACT_RELU, red=abn.red, dgamma=abn.gamma.grad, dbeta=abn.beta.grad)
         x16 = ws["x17"]
         if self.aspp0.trainable:
-            ops.pw_wgrad(x16, dy_a0, self.aspp0.params[0].grad.view(320, 256), workspace=wsp)
+            ops.pw_wgrad(x16, dy_a0, self.aspp0.params[0].grad.view(320, 256), beta=1.0)
         # ---- image pooling branch
         ops.small_gemm(ws["d_rowbias"], cp.params[0].data.view(512, 256), ws["d_b4"], M=B, N=256, K=256, transB=True,
                        alpha=float(HW))
@@ -638,7 +638,7 @@ class Engine:
                        act=ACT_NONE, red=pbn.red, dgamma=pbn.gamma.grad, dbeta=pbn.beta.grad)
             pj = b["project"]
             if pj.trainable:
-                ops.pw_wgrad(ws[f"a_d{i}"], dy_p, pj.params[0].grad.view(b["mid"], b["cout"]), workspace=wsp)
+                ops.pw_wgrad(ws[f"a_d{i}"], dy_p, pj.params[0].grad.view(b["mid"], b["cout"]), beta=1.0)
             if first > self._order(b["dw_bn"].layer.name):
                 return
             da_d = nview(gw[0], B, g["ho"], g["wo"], b["mid"])
@@ -662,7 +662,7 @@ class Engine:
                            act=ACT_RELU6, red=ebn.red, dgamma=ebn.gamma.grad, dbeta=ebn.beta.grad)
                 ex = b["expand"]
                 if ex.trainable:
-                    ops.pw_wgrad(xin, dy_e, ex.params[0].grad.view(b["cin"], b["mid"]), workspace=wsp)
+                    ops.pw_wgrad(xin, dy_e, ex.params[0].grad.view(b["cin"], b["mid"]), beta=1.0)
                 prev_bn = self.blocks[i - 1]["project_bn"].layer.name if i > 0 else "Conv_BN"
                 if first > self._order(prev_bn):
                     return

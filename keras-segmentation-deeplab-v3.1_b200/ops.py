@@ -259,6 +259,12 @@ def cast_weight(w: torch.Tensor, K: int, N: int, w_kn=None, w_nk=None):
             "cast_weight")
 
 
+def cast_weights_batched(table: torch.Tensor, total: int):
+    """All 1x1-layer weight copies in one launch; `table` = device int64 [n, 8] (see dlb_cast_weights_batched)."""
+    L.check(L.lib().dlb_cast_weights_batched(table.shape[0], table.data_ptr(), total, L.stream_ptr()),
+            "cast_weights_batched")
+
+
 def cast(src: torch.Tensor, dst: torch.Tensor):
     L.check(L.lib().dlb_cast(src.numel(), L.dt(src), src.data_ptr(), L.dt(dst), dst.data_ptr(), L.stream_ptr()), "cast")
     return dst
