@@ -159,6 +159,36 @@ int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int ldo, int d
 int dlb_aspp_dw3_fwd(int B, int H, int W, int C, int dtype, const void* x, const float* const* w, const int* rates,
                      const float* const* scale, const float* const* shift, void* const* y, void* stream);
 
+/* Fused separable-conv branches (tcgen05): for every branch i
+ *     out[i][m, 0:N] = pw_act( (dw_act( dw3x3_{rate[i]}(x) * dw_scale + dw_shift ) @ w_pw[i]^T) * pw_scale[i] + pw_shift[i] )
+ * in ONE kernel -- the depthwise result is produced in shared memory as the tensor-core A operand and never written.
+ * Replaces the spatial ASPP branches aspp0 (rate 0 = plain 1x1, no depthwise stage) and aspp1..3 = SepConv_BN(x, 256,
+ * rate=atrous_rates[i], depth_activation=True, epsilon=1e-5) (deeplabv3p.py:385-399, SepConv_BN :47-84; stride 1,
+ * TF 'same' zero padding) and, with one branch, decoder_conv0/1 (:426-429), BatchNorms folded (inference).
+ * x: [B,H,W,C] NHWC f16/bf16, W <= 128, C % 8 == 0.  w_pw[i]: [N, C] (C contiguous), N in {64,128,192,256}.
+ * out[i]: rows of pitch ldc (a channel slice of the concat buffer).  dw_pack: dlb_sepconv_pack_dw() output for the
+ * branches with rate > 0, in branch order. */
+typedef struct {
+  int B, H, W, C, N;
+  int dtype;
+  int n_branches;             /* 1..4 */
+  int rates[4];               /* 0 = pointwise-only branch */
+  const void* x;
+  const void* w_pw[4];
+  const void* dw_pack;
+  const float* pw_scale[4];   /* [N] folded pointwise BN (NULL = 1) */
+  const float* pw_shift[4];   /* [N] (NULL = 0) */
+  void* out[4];
+  int ldc;
+  int dw_act, pw_act;         /* dlb_act after the depthwise BN / pointwise BN */
+} dlb_sepconv_fused_params;
+int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* stream);
+/* Packs depthwise kernels w_dw[i] [3,3,C] fp32 + folded BN scale/shift[i] [C] into the per-64-channel-chunk blocks the
+ * fused kernel bulk-copies to shared memory (16-bit taps, fp32 affine); pack holds dlb_sepconv_pack_bytes() bytes. */
+int64_t dlb_sepconv_pack_bytes(int C, int n_branches);
+int dlb_sepconv_pack_dw(int C, int dtype, int n_branches, const float* const* w_dw, const float* const* scale,
+                        const float* const* shift, void* pack, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * BatchNormalization (deeplabv3p.py:76,80,178,189,197,322,379,386,408), training mode = batch statistics.
  * ------------------------------------------------------------------------------------------------- */

@@ -88,6 +88,14 @@ class SoftmaxCeParams(C.Structure):
     ]
 
 
+class SepconvFusedParams(C.Structure):
+    _fields_ = [
+        ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("N", i32), ("dtype", i32), ("n_branches", i32),
+        ("rates", i32 * 4), ("x", vp), ("w_pw", vp * 4), ("dw_pack", vp), ("pw_scale", vp * 4), ("pw_shift", vp * 4),
+        ("out", vp * 4), ("ldc", i32), ("dw_act", i32), ("pw_act", i32),
+    ]
+
+
 class CrfConfig(C.Structure):
     _fields_ = [
         ("H", i32), ("W", i32), ("M", i32), ("iters", i32), ("sxy_gauss", f32), ("compat_gauss", f32),
@@ -104,6 +112,7 @@ EXPORTS = [
     "dlb_resize_softmax_fwd", "dlb_resize_softmax_ce", "dlb_ce_grad_scale", "dlb_phase_shift", "dlb_adam_step",
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
+    "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw",
 ]
 
 _lib = None
@@ -143,6 +152,10 @@ def lib() -> C.CDLL:
         L.dlb_subsample.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp]
         L.dlb_resize_bilinear.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
         L.dlb_aspp_dw3_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.dlb_sepconv_pack_bytes.restype = i64
+        L.dlb_sepconv_pack_bytes.argtypes = [i32, i32]
+        L.dlb_sepconv_pack_dw.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
+        L.dlb_sepconv_fused_fwd.argtypes = [vp, vp]
         L.dlb_crf_workspace_bytes.argtypes = [vp]
         L.dlb_crf_inference.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
         for name in ("dlb_pw_gemm", "dlb_pw_wgrad", "dlb_dw_conv_fwd", "dlb_dw_conv_bwd", "dlb_stem_conv_fwd",

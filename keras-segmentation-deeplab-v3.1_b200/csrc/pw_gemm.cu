@@ -551,6 +551,27 @@ int make_tmap_nhwc(CUtensorMap* map, int dtype, const void* ptr, int B, int H, i
   return DLB_OK;
 }
 
+// NHWC activation tensor as a 4D tensor map with 128-byte swizzled boxes [1, box_h, box_w, 64 channels]: a landed box
+// is pixel-major rows of 128 B = directly a K-major SWIZZLE_128B tcgen05 operand tile (sepconv_fused.cu); coordinates
+// outside the image (and channels past C) are zero-filled.
+int make_tmap_nhwc_sw128(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled driver entry point unavailable"); return DLB_ERR_CUDA; }
+  const cuuint64_t es = 2;
+  CUtensorMapDataType dt = dtype == DLB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4D sw128) failed (%d): B=%d H=%d W=%d C=%d box=%dx%d", (int)r, B, H, W, C, box_h, box_w);
+    return DLB_ERR_CUDA;
+  }
+  return DLB_OK;
+}
+
 static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   GemmArgs g{};
   g.M = p->M; g.N = p->N; g.K = p->K;

@@ -315,3 +315,43 @@ def aspp_dw3_fwd(x: torch.Tensor, ws, rates, scales, shifts, ys):
     L.check(L.lib().dlb_aspp_dw3_fwd(B, H, W_, C_, L.dt(x), x.data_ptr(), wv, rt, sc, sh, yv, L.stream_ptr()),
             "aspp_dw3_fwd")
     return ys
+
+
+def sepconv_pack_dw(ws, scales, shifts, dtype: torch.dtype) -> torch.Tensor:
+    """Pack depthwise kernels [3,3,C] + folded BN (scale, shift) of the rate>0 branches for sepconv_fused_fwd."""
+    n = len(ws)
+    C_ = ws[0].shape[2]
+    L.require_cuda(*ws, *scales, *shifts)
+    nbytes = L.lib().dlb_sepconv_pack_bytes(C_, n)
+    pack = torch.empty(nbytes, dtype=torch.uint8, device=ws[0].device)
+    PN = C.c_void_p * n
+    L.check(L.lib().dlb_sepconv_pack_dw(C_, L._DT[dtype], n, PN(*[t.data_ptr() for t in ws]),
+                                        PN(*[t.data_ptr() for t in scales]), PN(*[t.data_ptr() for t in shifts]),
+                                        pack.data_ptr(), L.stream_ptr()), "sepconv_pack_dw")
+    return pack
+
+
+def sepconv_fused_fwd(x: torch.Tensor, rates, w_pws, dw_pack, pw_scales, pw_shifts, outs, dw_act=L.ACT_RELU,
+                      pw_act=L.ACT_RELU):
+    """Fused [atrous depthwise 3x3 + BN + act] -> [1x1 + BN + act] branches sharing the input x (rate 0 = plain 1x1).
+
+    x [B,H,W,C] f16/bf16; w_pws[i] [N,C]; outs[i]: [B,H,W,N] views (channel slices of a concat buffer are fine)."""
+    B, H, W_, C_ = x.shape
+    n = len(rates)
+    L.require_cuda(x, *w_pws, *outs)
+    p = L.SepconvFusedParams()
+    p.B, p.H, p.W, p.C, p.N = B, H, W_, C_, w_pws[0].shape[0]
+    p.dtype, p.n_branches = L.dt(x), n
+    for i in range(n):
+        assert x.is_contiguous() and w_pws[i].is_contiguous() and w_pws[i].shape[1] == C_ and outs[i].stride(3) == 1
+        p.rates[i] = int(rates[i])
+        p.w_pw[i] = w_pws[i].data_ptr()
+        p.pw_scale[i] = L.ptr(pw_scales[i])
+        p.pw_shift[i] = L.ptr(pw_shifts[i])
+        p.out[i] = outs[i].data_ptr()
+    p.x = x.data_ptr()
+    p.dw_pack = L.ptr(dw_pack)
+    p.ldc = outs[0].stride(2)
+    p.dw_act, p.pw_act = dw_act, pw_act
+    L.check(L.lib().dlb_sepconv_fused_fwd(C.byref(p), L.stream_ptr()), "sepconv_fused_fwd")
+    return outs

@@ -39,7 +39,9 @@ class XceptionEngine(Engine):
         super().__init__(input_shape=(H, W, 3), classes=classes, head="bare", compute_dtype=compute_dtype, device=device,
                          seed=seed)
         self.scale = 4
-        self.fused_aspp = True
+        self.fused_aspp = True          # (layer-wise path) one pass over x for the three atrous depthwise convs
+        self.fused_sepconv = True       # 16-bit: ASPP branches / decoder SepConvs as ONE tcgen05 kernel each
+        self._packs: Dict = {}
         self._bufs: Dict = {}
         self._ones = torch.ones(2048, device=self.device)
         self._zeros = torch.zeros(2048, device=self.device)
@@ -153,6 +155,15 @@ class XceptionEngine(Engine):
                     col_shift=pwbn.fshift, act=ACT_RELU if depth_activation else ACT_NONE, residual=residual)
         return z
 
+    def _dw_pack(self, tag, seps):
+        """Packed depthwise taps + folded BN of `seps` for the fused kernel (rebuilt whenever the BNs are re-folded)."""
+        pk = self._packs.get(tag)
+        if pk is None:
+            pk = ops.sepconv_pack_dw([s_["dw"].params[0].data for s_ in seps], [s_["dw_bn"].fscale for s_ in seps],
+                                     [s_["dw_bn"].fshift for s_ in seps], self.dtype)
+            self._packs[tag] = pk
+        return pk
+
     def _xception_block(self, x, blk):
         """_xception_block (deeplabv3p.py:119-155)."""
         B, H, W, C = x.shape
@@ -186,6 +197,7 @@ class XceptionEngine(Engine):
         if getattr(self, "_fold_dirty", True) or getattr(self, "_fold_ws", None) is not ws:
             self._fold_all(ws)
             self._fold_dirty, self._fold_ws = False, ws
+            self._packs = {}
         H, W = self.H, self.W
         x = self._buf("stem", B, H // 2, W // 2, 32)
         ops.stem_conv_fwd(img, self.stem.params[0].data, x, out_scale=self.stem_bn.fscale, out_shift=self.stem_bn.fshift,
@@ -212,9 +224,21 @@ class XceptionEngine(Engine):
         ops.pw_gemm(b4, wcp["nk32"], rowbias, K=256, col_scale=cbn.fscale)
         cat = self._buf("aspp_cat", B, fh, fw, 1024)
         bn0 = self.aspp0_bn
-        ops.pw_gemm(x, self.wcopies["aspp0"]["nk"], cat[..., 0:256], N=256, n_store=256, col_scale=bn0.fscale,
-                    col_shift=bn0.fshift, act=ACT_RELU)
-        if self.fused_aspp and fh * fw * 32 <= 200 * 1024:
+        fused = self.fused_sepconv and self.dtype != torch.float32
+        if fused and fw <= 128:
+            # aspp0 + aspp1..3 in one launch: x is read once, the depthwise results stay in shared memory
+            # (dlb_sepconv_fused_fwd; deeplabv3p.py:385-399)
+            pw_bns = [bn0] + [s_["pw_bn"] for s_ in self.aspp]
+            ops.sepconv_fused_fwd(x, [0] + list(self.atrous),
+                                  [self.wcopies["aspp0"]["nk"]] + [self.wcopies[s_["pw"].name]["nk"] for s_ in self.aspp],
+                                  self._dw_pack("aspp", self.aspp), [b_.fscale for b_ in pw_bns],
+                                  [b_.fshift for b_ in pw_bns], [cat[..., 256 * i:256 * (i + 1)] for i in range(4)])
+        else:
+            ops.pw_gemm(x, self.wcopies["aspp0"]["nk"], cat[..., 0:256], N=256, n_store=256, col_scale=bn0.fscale,
+                        col_shift=bn0.fshift, act=ACT_RELU)
+        if fused and fw <= 128:
+            pass
+        elif self.fused_aspp and fh * fw * 32 <= 200 * 1024:
             # fused atrous depthwise stage: x is read once for the three rates (dlb_aspp_dw3_fwd)
             dws = [self._buf(f"aspp{i + 1}/dw", B, fh, fw, 2048) for i in range(3)]
             ops.aspp_dw3_fwd(x, [s_["dw"].params[0].data for s_ in self.aspp], list(self.atrous),
@@ -236,8 +260,17 @@ class XceptionEngine(Engine):
         fbn = self.feature_projection0_bn
         ops.pw_gemm(skip1, self.wcopies["feature_projection0"]["nk"], dcat[..., 256:304], N=48, n_store=48,
                     col_scale=fbn.fscale, col_shift=fbn.fshift, act=ACT_RELU)
-        d = self._sepconv("decoder_conv0", dcat, self.decoder[0], 1, 1, True)
-        d = self._sepconv("decoder_conv1", d, self.decoder[1], 1, 1, True)
+        if fused and dw_ <= 128:
+            # decoder_conv0/1 (deeplabv3p.py:426-429): depthwise 3x3 + BN + ReLU + 1x1 + BN + ReLU, one kernel each
+            d = dcat
+            for i, sep in enumerate(self.decoder):
+                o = self._buf(f"decoder_conv{i}/pw", B, dh, dw_, 256)
+                ops.sepconv_fused_fwd(d, [1], [self.wcopies[sep["pw"].name]["nk"]], self._dw_pack(f"dec{i}", [sep]),
+                                      [sep["pw_bn"].fscale], [sep["pw_bn"].fshift], [o])
+                d = o
+        else:
+            d = self._sepconv("decoder_conv0", dcat, self.decoder[0], 1, 1, True)
+            d = self._sepconv("decoder_conv1", d, self.decoder[1], 1, 1, True)
         # ---- head
         hw = self.wcopies[self.head_conv.name]
         ops.pw_gemm(d, hw["nk"], ws["logits"], col_shift=self.head_conv.params[1].data, n_store=self.ldl)
