@@ -37,11 +37,13 @@ int make_tmap_2d(CUtensorMap* map, int dtype, const void* ptr, uint64_t rows, ui
 int make_tmap_nhwc_sw128(CUtensorMap* map, int dtype, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
 
 constexpr int kFMaxBr = 4;
-constexpr int kFThreads = 448;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-13 depthwise
 constexpr int kFDwWarps = 8;
+constexpr int kFThreads = 192 + 32 * kFDwWarps;   // warp 0 TMA + scheduler, warp 1 MMA, warps 2-5 epilogue, then the depthwise warps
 constexpr int kFDwThread0 = 192;
+constexpr int kFDwSlots = kFDwWarps * 4;          // pixels per pass (8 lanes = the 8 channel vectors of one pixel)
+constexpr int kFDwIter = 128 / kFDwSlots;
 constexpr int kFGroupBytes = 16384;     // 128 pixels x 64 channels x 2 B
-constexpr int kFPackBytes = 1664;       // 9 taps x 64 ch x 2 B + 64 scale + 64 shift (fp32)
+constexpr int kFPackBytes = 1408;       // (9 taps + BN scale + BN shift) x 64 ch x 2 B
 constexpr int kFInStage = 3 * kFGroupBytes + 2048;
 constexpr int kFStages = 2;
 constexpr int kFABytes = 16384;
@@ -52,7 +54,9 @@ constexpr int kFOffB = kFOffA + kFStages * kFABytes;
 constexpr int kFOffStg = kFOffB + kFStages * kFBBytes;
 constexpr int kFOffPw = kFOffStg + 4 * kFStageTile;
 constexpr int kFOffBar = kFOffPw + kFMaxBr * 512 * 4;
-constexpr int kFSmem = 1024 + kFOffBar + 256;
+constexpr int kFSmem = 1024 + kFOffBar + 512;
+constexpr int kFRing = 4;               // scheduler ring depth
+constexpr int kFConsumers = 1 + 4 + kFDwWarps;   // MMA thread + epilogue warps + depthwise warps read every ticket
 
 struct WMaps { CUtensorMap m[kFMaxBr]; };
 
@@ -61,53 +65,49 @@ struct FusedArgs {
   int TH, tiles_y, n_items, nk, n_br;
   int rate[kFMaxBr];
   int pack_idx[kFMaxBr];
+  int br_order[kFMaxBr];          // branches by descending cost (tickets are handed out longest-first inside an image)
   const uint8_t* pack;
   const float* pw_scale[kFMaxBr];
   const float* pw_shift[kFMaxBr];
   void* out[kFMaxBr];
   int ldc, dw_act, pw_act;
   uint32_t idesc;
+  unsigned int* ticket;           // zeroed by the host before every launch
 };
+
+__device__ unsigned int g_sepconv_ticket;
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-  uint4 u;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
-  return u;
-}
-__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& u) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
-}
 
 template <typename T> struct H2;
 template <> struct H2<__half> {
   using t = __half2;
   static __device__ __forceinline__ t pack(float a, float b) { return __floats2half2_rn(a, b); }
-  static __device__ __forceinline__ float2 unpack(t v) { return __half22float2(v); }
   static __device__ __forceinline__ t zero() { return __float2half2_rn(0.f); }
 };
 template <> struct H2<__nv_bfloat16> {
   using t = __nv_bfloat162;
   static __device__ __forceinline__ t pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
-  static __device__ __forceinline__ float2 unpack(t v) { return __bfloat1622float2(v); }
   static __device__ __forceinline__ t zero() { return __float2bfloat162_rn(0.f); }
 };
 
+// work item (ticket) = (image, tile of TH rows, branch); inside an image the expensive branches come first
 struct ItemGeom {
   int br, b, y0, d;
   bool g0, g2;      // row groups y0-d.. / y0+d.. intersect the image
 };
 __device__ __forceinline__ ItemGeom decode_item(const FusedArgs& a, int item) {
   ItemGeom g;
-  g.br = item % a.n_br;
-  const int t = item / a.n_br;
-  const int ty = t % a.tiles_y;
-  g.b = t / a.tiles_y;
-  g.y0 = ty * a.TH;
+  const int per_img = a.tiles_y * a.n_br;
+  g.b = item / per_img;
+  const int idx = item - g.b * per_img;
+  const int rank = idx / a.tiles_y;
+  g.br = a.br_order[rank];
+  g.y0 = (idx - rank * a.tiles_y) * a.TH;
   g.d = a.rate[g.br];
   g.g0 = g.d > 0 && g.y0 - g.d + a.TH - 1 >= 0;
   g.g2 = g.d > 0 && g.y0 + g.d < a.H;
@@ -124,15 +124,18 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const int lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFOffBar);
-  uint64_t* in_full = bars;            // [2]
+  uint64_t* in_full = bars;            // [2]  TMA -> depthwise warps
   uint64_t* in_empty = bars + 2;       // [2]
-  uint64_t* a_full = bars + 4;         // [2]
+  uint64_t* a_full = bars + 4;         // [2]  depthwise warps -> MMA
   uint64_t* a_empty = bars + 6;        // [2]
-  uint64_t* b_full = bars + 8;         // [2]
+  uint64_t* b_full = bars + 8;         // [2]  TMA -> MMA (pointwise weights)
   uint64_t* b_empty = bars + 10;       // [2]
-  uint64_t* t_full = bars + 12;        // [2]
-  uint64_t* t_empty = bars + 14;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* t_full = bars + 12;        // [2]  accumulator stage complete -> epilogue
+  uint64_t* t_empty = bars + 14;       // [2]  accumulator stage drained -> MMA
+  uint64_t* q_full = bars + 16;        // [4]  scheduler ring
+  uint64_t* q_empty = bars + 20;       // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  volatile int* q_item = reinterpret_cast<volatile int*>(bars + 25);   // [4]
   float* s_pw = reinterpret_cast<float*>(smem + kFOffPw);     // [branch][scale 256 | shift 256]
 
   if (warp == 0 && lane == 0) {
@@ -144,6 +147,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       mbar_init(&b_full[i], 1);   mbar_init(&b_empty[i], 1);
       mbar_init(&t_full[i], 1);   mbar_init(&t_empty[i], 4);
     }
+    for (int i = 0; i < kFRing; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], kFConsumers); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -160,11 +164,30 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t box_bytes = static_cast<uint32_t>(a.TH) * a.W * 128u;
 
+  // Dynamic tile scheduler: the producer thread draws tickets from a global counter and publishes them in a 4-deep
+  // shared-memory ring; every consumer role reads ticket n from slot n % 4.  -1 ends the kernel.  (A static stride
+  // gave CTA c the same branch every round -- 148 % 4 == 0 -- and a 40 % idle tail.)
+  auto next_item = [&](int n) -> int {
+    const int slot = n & (kFRing - 1);
+    mbar_wait(&q_full[slot], (n / kFRing) & 1);
+    const int item = q_item[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&q_empty[slot]);
+    return item;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== scheduler + TMA producer =====================
       int st = 0; uint32_t ph = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (int n = 0;; ++n) {
+        const int slot = n & (kFRing - 1);
+        mbar_wait(&q_empty[slot], ((n / kFRing) & 1) ^ 1);
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        const int item = t < static_cast<unsigned int>(a.n_items) ? static_cast<int>(t) : -1;
+        q_item[slot] = item;
+        mbar_arrive(&q_full[slot]);
+        if (item < 0) break;
         const ItemGeom g = decode_item(a, item);
         const uint32_t in_bytes = box_bytes * (1u + (g.g0 ? 1u : 0u) + (g.g2 ? 1u : 0u)) + (g.d > 0 ? kFPackBytes : 0u);
         const uint8_t* pk = a.pack + static_cast<size_t>(g.d > 0 ? a.pack_idx[g.br] : 0) * a.nk * kFPackBytes;
@@ -187,11 +210,14 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (lane == 0) {
       // ===================== MMA issuer =====================
       int st = 0; uint32_t ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&t_empty[as], aph ^ 1);
+      for (int n = 0;; ++n) {
+        const int slot = n & (kFRing - 1);
+        mbar_wait(&q_full[slot], (n / kFRing) & 1);
+        const int item = q_item[slot];
+        mbar_arrive(&q_empty[slot]);
+        if (item < 0) break;
+        const int as = n & 1;
+        mbar_wait(&t_empty[as], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
         for (int kc = 0; kc < a.nk; ++kc) {
@@ -216,17 +242,17 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ===================== epilogue warps (2..5) =====================
     const int quad = warp & 3;
     uint4* stg = reinterpret_cast<uint4*>(smem + kFOffStg) + static_cast<size_t>(warp - 2) * 32 * 8;
-    int it = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+    for (int n = 0;; ++n) {
+      const int item = next_item(n);
+      if (item < 0) break;
       const ItemGeom g = decode_item(a, item);
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
+      const int as = n & 1;
       const long long m0 = (static_cast<long long>(g.b) * a.H + g.y0) * a.W;
       const int rows_valid = min(a.TH, a.H - g.y0) * a.W;
       const float* sc = s_pw + g.br * 512;
       const float* sh = sc + 256;
       T* out = reinterpret_cast<T*>(a.out[g.br]);
-      mbar_wait(&t_full[as], aph);
+      mbar_wait(&t_full[as], (n >> 1) & 1);
       tc_fence_after();
       for (int j64 = 0; j64 < a.N; j64 += 64) {
 #pragma unroll 1
@@ -268,103 +294,94 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       if (lane == 0) mbar_arrive(&t_empty[as]);
     }
   } else {
-    // ===================== depthwise producers (warps 6..13) =====================
+    // ===================== depthwise producers =====================
+    // Everything that depends only on (pixel, rate) -- the three swizzled tap-column offsets and their validity -- is
+    // computed once per item; the chunk loop is loads + packed HFMA2 only.  The 9 taps are three independent 16-bit
+    // row chains (HFMA2), summed, then BN affine + activation on packed 16-bit (the result is rounded to 16 bit for
+    // the tensor core anyway).
     using P = typename H2<T>::t;
     const int td = threadIdx.x - kFDwThread0;
     const int cv = td & 7;          // 8-channel vector inside the 64-channel chunk
-    const int slot = td >> 3;       // 0..31
+    const int slot = td >> 3;       // 0..kFDwSlots-1
     const int n_px = a.TH * a.W;
+    const P zero2 = H2<T>::zero();
+    const P hi2 = H2<T>::pack(a.dw_act == DLB_ACT_RELU6 ? 6.f : 65000.f, a.dw_act == DLB_ACT_RELU6 ? 6.f : 65000.f);
     int st = 0; uint32_t ph = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    for (int n = 0;; ++n) {
+      const int item = next_item(n);
+      if (item < 0) break;
       const ItemGeom g = decode_item(a, item);
-      int prow[4], pcol[4];
+      uint32_t offC[kFDwIter], offL[kFDwIter], offR[kFDwIter];
+      bool vp[kFDwIter], vl[kFDwIter], vr[kFDwIter];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = slot + 32 * i;
-        prow[i] = p / a.W;
-        pcol[i] = p - prow[i] * a.W;
+      for (int i = 0; i < kFDwIter; ++i) {
+        const int p = slot + kFDwSlots * i;
+        const int row = p / a.W, x = p - row * a.W;
+        vp[i] = p < n_px;
+        vl[i] = vp[i] && x - g.d >= 0;
+        vr[i] = vp[i] && x + g.d < a.W;
+        const int ql = vl[i] ? p - g.d : p, qr = vr[i] ? p + g.d : p;
+        offC[i] = static_cast<uint32_t>(p) * 128u + (static_cast<uint32_t>(cv ^ (p & 7)) << 4);
+        offL[i] = static_cast<uint32_t>(ql) * 128u + (static_cast<uint32_t>(cv ^ (ql & 7)) << 4);
+        offR[i] = static_cast<uint32_t>(qr) * 128u + (static_cast<uint32_t>(cv ^ (qr & 7)) << 4);
       }
       for (int kc = 0; kc < a.nk; ++kc) {
         mbar_wait(&in_full[st], ph);
-        const uint32_t sin = s0 + st * kFInStage;
-        const uint32_t sa = s0 + kFOffA + st * kFABytes;
+        const uint8_t* sin = smem + st * kFInStage;
+        uint8_t* sa = smem + kFOffA + st * kFABytes;
         if (g.d == 0) {
           mbar_wait(&a_empty[st], ph ^ 1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int p = slot + 32 * i;
-            if (p < n_px) {
-              const uint32_t off = static_cast<uint32_t>(p) * 128u + (static_cast<uint32_t>(cv ^ (p & 7)) << 4);
-              sts128(sa + off, lds128(sin + kFGroupBytes + off));
-            }
-          }
+          for (int i = 0; i < kFDwIter; ++i)
+            if (vp[i]) *reinterpret_cast<uint4*>(sa + offC[i]) = *reinterpret_cast<const uint4*>(sin + kFGroupBytes + offC[i]);
         } else {
-          P w2[9][4];
-          float scl[8], shf[8];
+          P w2[9][4], scl[4], shf[4];
           {
-            const uint32_t sp = sin + 3 * kFGroupBytes;
+            const uint8_t* sp = sin + 3 * kFGroupBytes + cv * 16;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const uint4 u = lds128(sp + t * 128 + cv * 16);
+              const uint4 u = *reinterpret_cast<const uint4*>(sp + t * 128);
               const P* h = reinterpret_cast<const P*>(&u);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) w2[t][i] = h[i];
+              for (int j = 0; j < 4; ++j) w2[t][j] = h[j];
             }
-            const uint4 s_a = lds128(sp + 1152 + cv * 32), s_b = lds128(sp + 1152 + cv * 32 + 16);
-            const uint4 h_a = lds128(sp + 1408 + cv * 32), h_b = lds128(sp + 1408 + cv * 32 + 16);
-            scl[0] = __uint_as_float(s_a.x); scl[1] = __uint_as_float(s_a.y); scl[2] = __uint_as_float(s_a.z); scl[3] = __uint_as_float(s_a.w);
-            scl[4] = __uint_as_float(s_b.x); scl[5] = __uint_as_float(s_b.y); scl[6] = __uint_as_float(s_b.z); scl[7] = __uint_as_float(s_b.w);
-            shf[0] = __uint_as_float(h_a.x); shf[1] = __uint_as_float(h_a.y); shf[2] = __uint_as_float(h_a.z); shf[3] = __uint_as_float(h_a.w);
-            shf[4] = __uint_as_float(h_b.x); shf[5] = __uint_as_float(h_b.y); shf[6] = __uint_as_float(h_b.z); shf[7] = __uint_as_float(h_b.w);
+            const uint4 us = *reinterpret_cast<const uint4*>(sp + 9 * 128), uh = *reinterpret_cast<const uint4*>(sp + 10 * 128);
+            const P* hs = reinterpret_cast<const P*>(&us);
+            const P* hh = reinterpret_cast<const P*>(&uh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { scl[j] = hs[j]; shf[j] = hh[j]; }
           }
           mbar_wait(&a_empty[st], ph ^ 1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int p = slot + 32 * i;
-            if (p >= n_px) continue;
-            const int x = pcol[i];
-            const int qrow = prow[i] * a.W;
-            const bool xl = x - g.d >= 0, xr = x + g.d < a.W;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int i = 0; i < kFDwIter; ++i) {
+            if (!vp[i]) continue;
+            P racc[3][4];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-              if ((ky == 0 && !g.g0) || (ky == 2 && !g.g2)) continue;
-              const uint32_t gb = sin + ky * kFGroupBytes;
-              P racc[4];
-              {
-                const int q = qrow + x;
-                const uint4 u = lds128(gb + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(cv ^ (q & 7)) << 4));
-                const P* h = reinterpret_cast<const P*>(&u);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) racc[j] = __hmul2(h[j], w2[ky * 3 + 1][j]);
-              }
-              if (xl) {
-                const int q = qrow + x - g.d;
-                const uint4 u = lds128(gb + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(cv ^ (q & 7)) << 4));
-                const P* h = reinterpret_cast<const P*>(&u);
+              for (int j = 0; j < 4; ++j) racc[ky][j] = zero2;
+              if ((ky == 0 && !g.g0) || (ky == 2 && !g.g2)) continue;      // item-uniform
+              const uint8_t* gb = sin + ky * kFGroupBytes;
+              const uint4 uc = *reinterpret_cast<const uint4*>(gb + offC[i]);
+              uint4 ul = make_uint4(0u, 0u, 0u, 0u), ur = make_uint4(0u, 0u, 0u, 0u);
+              if (vl[i]) ul = *reinterpret_cast<const uint4*>(gb + offL[i]);
+              if (vr[i]) ur = *reinterpret_cast<const uint4*>(gb + offR[i]);
+              const P* hc = reinterpret_cast<const P*>(&uc);
+              const P* hl = reinterpret_cast<const P*>(&ul);
+              const P* hr = reinterpret_cast<const P*>(&ur);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) racc[j] = __hfma2(h[j], w2[ky * 3][j], racc[j]);
-              }
-              if (xr) {
-                const int q = qrow + x + g.d;
-                const uint4 u = lds128(gb + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(cv ^ (q & 7)) << 4));
-                const P* h = reinterpret_cast<const P*>(&u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) racc[j] = __hfma2(h[j], w2[ky * 3 + 2][j], racc[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = H2<T>::unpack(racc[j]);
-                acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
-              }
+              for (int j = 0; j < 4; ++j)
+                racc[ky][j] = __hfma2(hr[j], w2[ky * 3 + 2][j], __hfma2(hl[j], w2[ky * 3][j], __hmul2(hc[j], w2[ky * 3 + 1][j])));
             }
             uint4 o;
             P* oh = reinterpret_cast<P*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              oh[j] = H2<T>::pack(apply_act(fmaf(acc[2 * j], scl[2 * j], shf[2 * j]), a.dw_act),
-                                  apply_act(fmaf(acc[2 * j + 1], scl[2 * j + 1], shf[2 * j + 1]), a.dw_act));
-            sts128(sa + static_cast<uint32_t>(p) * 128u + (static_cast<uint32_t>(cv ^ (p & 7)) << 4), o);
+            for (int j = 0; j < 4; ++j) {
+              P v = __hfma2(__hadd2(__hadd2(racc[0][j], racc[2][j]), racc[1][j]), scl[j], shf[j]);
+              if (a.dw_act != DLB_ACT_NONE) v = __hmin2(__hmax2(v, zero2), hi2);
+              oh[j] = v;
+            }
+            *reinterpret_cast<uint4*>(sa + offC[i]) = o;
           }
         }
         fence_proxy_async();      // generic-proxy writes of the A tile -> visible to tcgen05.mma (async proxy)
@@ -380,18 +397,16 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// packed per-(branch, 64-channel chunk) depthwise parameters: [9 taps][64 ch] 16-bit | scale[64] f32 | shift[64] f32
+// packed per-(branch, 64-channel chunk) depthwise parameters, all 16-bit: [9 taps][64 ch] | scale[64] | shift[64]
 template <typename T>
 __global__ void aspp_pack_kernel(int C, int nk, const float* w, const float* scale, const float* shift, uint8_t* pack) {
   const int kc = blockIdx.x, ch = threadIdx.x;     // 64 threads
   const int c = kc * 64 + ch;
   uint8_t* dst = pack + static_cast<size_t>(kc) * kFPackBytes;
   T* wt = reinterpret_cast<T*>(dst);
-  float* sc = reinterpret_cast<float*>(dst + 1152);
-  float* sh = reinterpret_cast<float*>(dst + 1408);
   for (int t = 0; t < 9; ++t) Act<T>::st(&wt[t * 64 + ch], c < C ? w[t * C + c] : 0.f);
-  sc[ch] = (c < C) ? (scale ? scale[c] : 1.f) : 0.f;
-  sh[ch] = (c < C && shift) ? shift[c] : 0.f;
+  Act<T>::st(&wt[9 * 64 + ch], (c < C) ? (scale ? scale[c] : 1.f) : 0.f);
+  Act<T>::st(&wt[10 * 64 + ch], (c < C && shift) ? shift[c] : 0.f);
 }
 
 }  // namespace dlb
@@ -456,12 +471,25 @@ extern "C" int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* st
     if (rc) return rc;
   }
   DLB_REQUIRE(n_dw == 0 || p->dw_pack, "sepconv_fused_fwd: dw_pack missing");
+  // longest-first ticket order inside an image: small positive rates keep the most taps inside the map, rate 0 has none
+  for (int i = 0; i < a.n_br; ++i) a.br_order[i] = i;
+  for (int i = 1; i < a.n_br; ++i)
+    for (int j = i; j > 0; --j) {
+      const int ra = a.rate[a.br_order[j - 1]], rb = a.rate[a.br_order[j]];
+      const bool swap = (ra == 0 && rb != 0) || (ra != 0 && rb != 0 && rb < ra);
+      if (!swap) break;
+      const int t = a.br_order[j]; a.br_order[j] = a.br_order[j - 1]; a.br_order[j - 1] = t;
+    }
   DLB_REQUIRE((reinterpret_cast<uintptr_t>(p->dw_pack) & 15) == 0, "sepconv_fused_fwd: dw_pack must be 16-byte aligned");
   CUtensorMap tx;
   int rc = make_tmap_nhwc_sw128(&tx, p->dtype, p->x, p->B, p->H, p->W, p->C, p->W, a.TH);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+  // dynamic tile scheduler: one device counter, zeroed in stream order before every launch (a memset node under graph
+  // capture); launches of this kernel must therefore not overlap on different streams
+  DLB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.ticket), g_sepconv_ticket));
+  DLB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), st));
   if (p->dtype == DLB_F16) {
     DLB_CUDA(cudaFuncSetAttribute(sepconv_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
     sepconv_fused_kernel<__half><<<grid, kFThreads, kFSmem, st>>>(tx, wm, a);
