@@ -374,10 +374,18 @@ class Model:
         slots = getattr(self, "_slots", None)
         pending = None
 
+        # read-backs go through their own stream into pinned host buffers: a `.cpu()` on the main stream would be
+        # ordered behind the step that was just enqueued and make the host wait for step i+1 instead of step i (the
+        # next batch's host->device copy would then start too late to overlap anything).
+        d2h = getattr(self, "_d2h_stream", None)
+        if d2h is None:
+            d2h = self._d2h_stream = torch.cuda.Stream()
+
         def finish(p):
-            vals = torch.stack([p["loss"][0], p["wcount"][0]]).cpu().numpy()
+            p["done"].synchronize()
+            vals = p["h_vals"].numpy()
             loss = float(vals[0] / vals[1]) if vals[1] > 0 else float("nan")
-            jac, acc = _metrics_from_confusion(p["conf"].cpu().numpy(), e.n_out)
+            jac, acc = _metrics_from_confusion(p["h_conf"].numpy().copy(), e.n_out)
             return [loss, jac, acc]
 
         for i, batch in enumerate(batches):
@@ -412,7 +420,21 @@ class Model:
             ws = e.workspace(B, True)
             conf = torch.zeros(B, e.n_out + 1, e.n_out, device=dev, dtype=torch.int64)
             ops.confusion(ws["labels"], ws["argmax"], e.n_out, conf)
-            cur = dict(loss=loss_sum.clone(), wcount=wcount.clone(), conf=conf)
+            vals = torch.stack([loss_sum[0].double(), wcount[0].double()])
+            hb = getattr(self, "_host_bufs", None)
+            if hb is None or hb[0]["h_conf"].shape != conf.shape:
+                hb = self._host_bufs = [dict(h_vals=torch.empty(2, dtype=torch.float64).pin_memory(),
+                                             h_conf=torch.empty(conf.shape, dtype=torch.int64).pin_memory()) for _ in range(2)]
+            cur = dict(hb[i % 2], done=torch.cuda.Event())
+            produced = torch.cuda.Event()
+            produced.record(main)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(produced)
+                cur["h_vals"].copy_(vals, non_blocking=True)
+                cur["h_conf"].copy_(conf, non_blocking=True)
+                cur["done"].record(d2h)
+            vals.record_stream(d2h)
+            conf.record_stream(d2h)
             if pending is not None:
                 yield finish(pending)
             pending = cur
