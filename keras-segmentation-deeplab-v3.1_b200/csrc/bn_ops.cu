@@ -3,12 +3,15 @@
 // Reference sites: BatchNormalization deeplabv3p.py:76,80,178,189,197,322,379,386,408 ; relu6 Lambda :181,192,325 ;
 // Add :202 ; Dropout :410 ; AveragePooling2D :375.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace dlb {
 
 extern std::atomic<long long> g_launches;
+// DLB_BN_STREAM=0 selects the register-staged BatchNorm streaming kernels (A/B measurements)
+static const bool g_bn_stream = [] { const char* e = getenv("DLB_BN_STREAM"); return !(e && e[0] == '0'); }();
 
 __global__ void bn_finalize_kernel(int C, double count, double* sum, double* sqs, const float* gamma,
                                    const float* beta, float eps, float momentum, float* moving_mean,
@@ -440,6 +443,232 @@ __global__ void small_gemm_kernel(int M, int N, int K, const float* A, int lda, 
   *c = alpha * acc + (beta != 0.f ? beta * *c : 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy pipelined versions of the three BatchNorm streaming kernels (16-bit storage, no dropout).
+//
+// The register-staged kernels above top out at 50-60 % of the HBM copy bandwidth: ncu shows every warp parked on the
+// long scoreboard with a third of the warp slots filled (80 registers x 256 threads) -- too few bytes in flight.
+// Here one producer thread streams whole row blocks (rows are contiguous in NHWC: R rows = R*C*2 bytes in ONE
+// cp.async.bulk) into a ring of shared-memory stages, ~190 KB in flight per SM at no register cost, and 16 consumer
+// warps read them back with conflict-free LDS.128 (thread = fixed 8-channel vector, so the per-channel constants stay
+// in registers); results go straight out with coalesced 16-byte stores.
+//   mode 0: y = act(x*scale+shift) (+res)                  (bn_act_apply;   in: x [, res]   out: y)
+//   mode 1: red += sum dz, sum dz*xhat                     (bn_bwd_reduce;  in: x, da)
+//   mode 2: dx = scale*(dz - mean(dz) - xhat*mean(dz*xhat)) (bn_bwd_apply;   in: x, da      out: dx)
+// ---------------------------------------------------------------------------------------------
+constexpr int kSConsumers = 480;      // 15 consumer warps + 1 producer warp = 512 threads -> 128 registers each
+constexpr int kSThreads = kSConsumers + 32;
+constexpr int kSMaxStages = 8;
+
+struct StreamArgs {
+  long long M; int C, cv, rpb;          // rows, channels, channel vectors, rows per consumer pass
+  int U, rows_per_stage, n_stages, n_in;
+  uint32_t slot_bytes;                  // bytes reserved per tensor per stage (128-byte multiple)
+  const void* in0; const void* in1; void* out;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  int act, frozen;
+  double* red; float* dgamma; float* dbeta;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T, int kMode>
+__global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  using P = typename BP2<T>::t;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t stage_bytes = a.slot_bytes * a.n_in;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + static_cast<size_t>(a.n_stages) * stage_bytes);
+  uint64_t* empty = full + kSMaxStages;
+  if (tid == 0) {
+    for (int i = 0; i < a.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSConsumers / 32); }
+    mbar_fence_init();
+  }
+  if (kMode == 2 && blockIdx.x == 0) {
+    for (int c = tid; c < a.C; c += kSThreads) {
+      if (a.dbeta) a.dbeta[c] = static_cast<float>(a.red[c]);
+      if (a.dgamma) a.dgamma[c] = static_cast<float>(a.red[a.C + c]);
+    }
+  }
+  __syncthreads();
+  const long long n_blk = (a.M + a.rows_per_stage - 1) / a.rows_per_stage;
+  const size_t row_bytes = static_cast<size_t>(a.C) * sizeof(T);
+
+  if (warp == kSConsumers / 32) {
+    if (lane == 0) {
+      // ===================== producer =====================
+      int st = 0; uint32_t ph = 0;
+      for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const long long r0 = blk * a.rows_per_stage;
+        const long long rows = a.M - r0 < a.rows_per_stage ? a.M - r0 : a.rows_per_stage;
+        const uint32_t bytes = static_cast<uint32_t>(rows * row_bytes);
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], bytes * a.n_in);
+        const uint32_t dst = smem_u32(s_raw) + st * stage_bytes;
+        bulk_g2s(dst, static_cast<const uint8_t*>(a.in0) + r0 * row_bytes, bytes, &full[st]);
+        if (a.n_in > 1) bulk_g2s(dst + a.slot_bytes, static_cast<const uint8_t*>(a.in1) + r0 * row_bytes, bytes, &full[st]);
+        if (++st == a.n_stages) { st = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const bool active = tid < a.rpb * a.cv;
+  const int r_in = active ? tid / a.cv : 0;
+  const int c0 = active ? (tid - r_in * a.cv) * 8 : 0;
+  // per-channel constants of this thread's 8 channels
+  float sc[8], sh[8], k1[8], k2[8];
+  P sc2[4], sh2[4], mu2[4], rs2[4];
+  const float invM = 1.f / static_cast<float>(a.M);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = a.scale ? a.scale[c0 + k] : 1.f;
+    sh[k] = a.scale ? a.shift[c0 + k] : 0.f;
+    k1[k] = (kMode == 2 && !a.frozen) ? static_cast<float>(a.red[c0 + k]) * invM : 0.f;
+    k2[k] = (kMode == 2 && !a.frozen) ? static_cast<float>(a.red[a.C + c0 + k]) * invM : 0.f;
+  }
+  if (kMode != 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sc2[k] = BP2<T>::pack(sc[2 * k], sc[2 * k + 1]);
+      sh2[k] = BP2<T>::pack(sh[2 * k], sh[2 * k + 1]);
+      mu2[k] = BP2<T>::pack(a.mean[c0 + 2 * k], a.mean[c0 + 2 * k + 1]);
+      rs2[k] = BP2<T>::pack(a.rstd[c0 + 2 * k], a.rstd[c0 + 2 * k + 1]);
+    }
+  }
+  const P zero2 = BP2<T>::bcast(0.f), six2 = BP2<T>::bcast(6.f);
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  T* out = reinterpret_cast<T*>(a.out);
+  const uint32_t t_off = static_cast<uint32_t>((r_in * a.C + c0) * sizeof(T));      // this thread inside one pass
+  const uint32_t pass_bytes = static_cast<uint32_t>(a.rpb * row_bytes);
+
+  int st = 0; uint32_t ph = 0;
+  for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+    mbar_wait(&full[st], ph);
+    if (active) {
+      const uint8_t* s_in0 = s_raw + st * stage_bytes + t_off;
+      const uint8_t* s_in1 = s_in0 + a.slot_bytes;
+      const long long r_base = blk * a.rows_per_stage + r_in;
+      constexpr int UB = 4;
+      for (int u0 = 0; u0 < a.U; u0 += UB) {
+        BV8<T> xv[UB], gv[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          if (u0 + u < a.U) {
+            const uint4 q = *reinterpret_cast<const uint4*>(s_in0 + (u0 + u) * pass_bytes);
+            xv[u] = *reinterpret_cast<const BV8<T>*>(&q);
+            if (kMode != 0 || a.n_in > 1) {
+              const uint4 q1 = *reinterpret_cast<const uint4*>(s_in1 + (u0 + u) * pass_bytes);
+              gv[u] = *reinterpret_cast<const BV8<T>*>(&q1);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const long long r = r_base + static_cast<long long>(u0 + u) * a.rpb;
+          if (u0 + u >= a.U || r >= a.M) continue;
+          if (kMode == 0) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = BP2<T>::unpack(xv[u].h[k]);
+              o[2 * k] = apply_act(fmaf(f.x, sc[2 * k], sh[2 * k]), a.act);
+              o[2 * k + 1] = apply_act(fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]), a.act);
+              if (a.n_in > 1) {
+                const float2 g = BP2<T>::unpack(gv[u].h[k]);
+                o[2 * k] += g.x; o[2 * k + 1] += g.y;
+              }
+            }
+            Vec8<T>::st(out + r * a.C + c0, o);
+          } else {
+            BV8<T> ov;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              P dz = gv[u].h[k];
+              if (a.act != DLB_ACT_NONE) {
+                const P z = __hfma2(xv[u].h[k], sc2[k], sh2[k]);
+                P m = __hgt2(z, zero2);
+                if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
+                dz = __hmul2(dz, m);
+              }
+              const P xh2 = __hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]);
+              if (kMode == 1) {
+                const float2 f1 = BP2<T>::unpack(dz), f2 = BP2<T>::unpack(__hmul2(dz, xh2));
+                s1[2 * k] += f1.x; s1[2 * k + 1] += f1.y; s2[2 * k] += f2.x; s2[2 * k + 1] += f2.y;
+              } else {
+                const float2 dzf = BP2<T>::unpack(dz), xh = BP2<T>::unpack(xh2);
+                ov.h[k] = BP2<T>::pack(sc[2 * k] * (dzf.x - k1[2 * k] - xh.x * k2[2 * k]),
+                                       sc[2 * k + 1] * (dzf.y - k1[2 * k + 1] - xh.y * k2[2 * k + 1]));
+              }
+            }
+            if (kMode == 2) stg_bh8(out + r * a.C + c0, ov);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (++st == a.n_stages) { st = 0; ph ^= 1; }
+  }
+  if (kMode == 1) {
+    // per-row-group partials -> stage memory (all stages are drained) -> one fp64 atomic per channel and CTA
+    asm volatile("bar.sync 1, %0;" ::"n"(kSConsumers) : "memory");
+    float* s_red = reinterpret_cast<float*>(s_raw);       // [rpb][2C] = 32 KB
+    if (active) {
+      float* row = s_red + static_cast<size_t>(r_in) * 2 * a.C;
+      *reinterpret_cast<float4*>(row + c0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      *reinterpret_cast<float4*>(row + c0 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+      *reinterpret_cast<float4*>(row + a.C + c0) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+      *reinterpret_cast<float4*>(row + a.C + c0 + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kSConsumers) : "memory");
+    for (int i = tid; i < 2 * a.C; i += kSConsumers) {
+      float t = 0.f;
+      for (int r = 0; r < a.rpb; ++r) t += s_red[static_cast<size_t>(r) * 2 * a.C + i];
+      atomicAdd(&a.red[i], static_cast<double>(t));
+    }
+  }
+}
+
+// returns 0 if the streaming kernel was launched, 1 if the shape is not eligible (caller falls back), <0 on error
+template <int kMode>
+static int launch_bn_stream(StreamArgs a, int dtype, cudaStream_t st) {
+  if (dtype != DLB_F16 && dtype != DLB_BF16) return 1;
+  if (a.C % 8 != 0 || a.C / 8 > kSConsumers / 2 || a.M < 1024) return 1;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a.in0) | reinterpret_cast<uintptr_t>(a.in1) | reinterpret_cast<uintptr_t>(a.out);
+  if (al & 15) return 1;
+  a.cv = a.C / 8;
+  a.rpb = kSConsumers / a.cv;
+  const long long pass_bytes = static_cast<long long>(a.rpb) * a.C * 2;
+  a.U = static_cast<int>(24576 / pass_bytes);
+  if (a.U < 1) a.U = 1;
+  a.rows_per_stage = a.rpb * a.U;
+  a.slot_bytes = static_cast<uint32_t>((static_cast<long long>(a.rows_per_stage) * a.C * 2 + 127) / 128 * 128);
+  const long long budget = 200 * 1024;
+  a.n_stages = static_cast<int>(budget / (static_cast<long long>(a.slot_bytes) * a.n_in));
+  if (a.n_stages > kSMaxStages) a.n_stages = kSMaxStages;
+  if (a.n_stages < 2) return 1;
+  size_t smem = static_cast<size_t>(a.n_stages) * a.slot_bytes * a.n_in + 2 * kSMaxStages * 8;
+  if (kMode == 1 && smem < 32768 + 256) smem = 32768 + 256;
+  const long long n_blk = (a.M + a.rows_per_stage - 1) / a.rows_per_stage;
+  const int grid = static_cast<int>(n_blk < num_sms() ? n_blk : num_sms());
+  if (dtype == DLB_F16) {
+    DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__half, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bn_stream_kernel<__half, kMode><<<grid, kSThreads, smem, st>>>(a);
+  } else {
+    DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__nv_bfloat16, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bn_stream_kernel<__nv_bfloat16, kMode><<<grid, kSThreads, smem, st>>>(a);
+  }
+  g_launches++;
+  return check_launch("bn_stream_kernel");
+}
+
 static int grid_for(long long n, int threads, int per_sm) {
   long long blocks = (n + threads - 1) / threads;
   long long cap = static_cast<long long>(num_sms()) * per_sm;
@@ -478,6 +707,14 @@ extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   DLB_REQUIRE(p->C / 8 <= 256, "bn_act_apply: C <= 2048");
   ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed,
               reinterpret_cast<const long long*>(p->drop_seed_dev)};
+  cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  if (p->drop_rate <= 0.f && g_bn_stream) {
+    StreamArgs sa{};
+    sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->res; sa.out = p->y; sa.n_in = p->res ? 2 : 1;
+    sa.scale = p->scale; sa.shift = p->shift; sa.act = p->act;
+    const int rc = launch_bn_stream<0>(sa, p->dtype, st0);
+    if (rc <= 0) return rc;
+  }
   const int rpb_ = 256 / (p->C / 8);
   long long blocks_ = (p->M + static_cast<long long>(rpb_) * 4 - 1) / (static_cast<long long>(rpb_) * 4);
   const long long cap_ = static_cast<long long>(num_sms()) * 8;
@@ -505,6 +742,13 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   BwdArgs a{};
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
+  if (p->drop_rate <= 0.f && g_bn_stream) {
+    StreamArgs sa{};
+    sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->da; sa.out = nullptr; sa.n_in = 2;
+    sa.scale = p->scale; sa.shift = p->shift; sa.mean = p->mean; sa.rstd = p->rstd; sa.act = p->act; sa.red = p->red;
+    rc = launch_bn_stream<1>(sa, p->dtype, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   long long blocks = (a.M + a.rpb * 4LL - 1) / (a.rpb * 4LL);
   long long cap = static_cast<long long>(num_sms()) * 6;
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
@@ -526,6 +770,14 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
   DLB_REQUIRE(p->dx, "bn_bwd_apply: dx is null");
+  if (p->drop_rate <= 0.f && g_bn_stream) {
+    StreamArgs sa{};
+    sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->da; sa.out = p->dx; sa.n_in = 2;
+    sa.scale = p->scale; sa.shift = p->shift; sa.mean = p->mean; sa.rstd = p->rstd; sa.act = p->act; sa.red = p->red;
+    sa.frozen = p->frozen_stats; sa.dgamma = p->dgamma; sa.dbeta = p->dbeta;
+    rc = launch_bn_stream<2>(sa, p->dtype, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   long long blocks = (a.M + a.rpb * 4LL - 1) / (a.rpb * 4LL);
   long long cap = static_cast<long long>(num_sms()) * 6;
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
