@@ -73,6 +73,10 @@ typedef struct {
   int shuffle_r, shuffle_h, shuffle_w;  /* Subpixel store: r, low-res H, W ; 0 = plain store */
 } dlb_pw_gemm_params;
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
+/* Tiling plan dlb_pw_gemm would use for a 16-bit GEMM of this shape (host arithmetic only, no device needed):
+ * plan[10] = {epilogue warp sets, chunk_n, n_chunks, chunks_per_group, n_groups, accumulator columns per stage,
+ *             accumulator stages, alt_tiles, smem pipeline stages, dynamic shared memory bytes}.  0 or DLB_ERR_INVALID. */
+int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_r, int* plan);
 
 /* Weight gradient of a 1x1 convolution: dW[K, N] (+)= A[M, K]^T * dY[M, N]  (fp32 out, ld = N).
  * tcgen05 with MN-major operands for 16-bit dtypes; SIMT for f32.  beta = 0 overwrites, 1 accumulates (only 0 / 1).

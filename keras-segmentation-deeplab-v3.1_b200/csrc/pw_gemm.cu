@@ -21,6 +21,7 @@
 //
 // DLB_F32 inputs take an exact-fp32 SIMT path (the 1e-3 parity mode of BASELINE.json; tf32 would not hold it).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
@@ -35,8 +36,9 @@ constexpr int kBlockM = 128;
 constexpr int kSwzBytes = 128;
 constexpr int kABytes = kBlockM * kSwzBytes;   // 16 KB per A stage
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
-constexpr int kEpiThreads = 256;
+constexpr int kMaxAccStages = 4;
+constexpr int kStageTileBytes = 4096;          // per epilogue warp: 32 rows x 128 B (64 x 16-bit columns)
+constexpr int kMaxSmem = 227 * 1024;
 
 struct GemmArgs {
   int M, N, K;
@@ -56,15 +58,56 @@ struct GemmArgs {
   int k_elems_per_block, umma_k;   // 64/16 for 16-bit inputs
   uint32_t idesc;
   uint32_t stage_bytes;
-  int alt_tiles;   // N <= 64: the two epilogue warp sets take alternate M tiles (one accumulator stage each)
+  int alt_tiles;   // narrow outputs: epilogue warp set s owns accumulator stage s and drains whole M tiles alone
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
 
-template <typename OutT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// explicit shared-space accesses on 32-bit addresses (run-time selected tile pointers otherwise decay to generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+  return u;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(u) : "r"(saddr));
+  return u;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+// packed fp32 pairs (sm_100 FADD2 / FFMA2): one instruction per two columns in the statistics walk
+__device__ __forceinline__ void f32x2_acc(unsigned long long& s, unsigned long long& q, float a, float b) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(v));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q) : "l"(v));
+}
+__device__ __forceinline__ float2 f32x2_unpack(unsigned long long v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+template <typename OutT> __device__ __forceinline__ float2 word_to_float2(uint32_t w);
+template <> __device__ __forceinline__ float2 word_to_float2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <> __device__ __forceinline__ float2 word_to_float2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 word_to_float2<float>(uint32_t w) { return make_float2(0.f, 0.f); }
+
+// kSets epilogue warp sets of 4 warps (one warp per TMEM lane quarter).  kSets == 4 is the 16-bit staged-output
+// instance (host guarantees: 16-bit OutT, no phase-shift store); kSets == 2 also carries the fp32 / phase-shift stores.
+template <typename OutT, int kSets>
+__global__ void __launch_bounds__(64 + 128 * kSets, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmArgs g) {
+  constexpr int kThreads = 64 + 128 * kSets;
+  constexpr int kEpiThreads = 128 * kSets;
+  constexpr bool kStagedOnly = kSets == 4;
+  constexpr bool kCanStage = sizeof(OutT) == 2;
   extern __shared__ uint8_t smem_dyn[];
   // round up to the 1024-byte swizzle-atom alignment by OFFSETTING the shared array (a uintptr_t round trip makes
   // every later access a generic LD/ST instead of LDS/STS)
@@ -77,24 +120,24 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kMaxAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccStages);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
   const int npad = g.n_chunks * g.chunk_n;
   float* s_shift = s_scale + npad;
   float* s_sum = s_shift + npad;
   float* s_sqs = s_sum + npad;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_sqs + npad);   // 8 warps x 4 KB; 16-byte aligned (npad is a multiple of 16)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_sqs + npad);   // 4*kSets warps x 4 KB; 16-byte aligned (npad is a multiple of 16)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? kEpiThreads / 64 : kEpiThreads / 32); }
+    for (int i = 0; i < kMaxAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? 4 : 4 * kSets); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < npad; i += kGemmThreads) {
+  for (int i = threadIdx.x; i < npad; i += kThreads) {
     s_scale[i] = (g.col_scale && i < g.N) ? g.col_scale[i] : 1.f;
     s_shift[i] = (g.col_shift && i < g.N) ? g.col_shift[i] : 0.f;
     s_sum[i] = 0.f;
@@ -165,30 +208,42 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    // Two warps per TMEM lane quarter; each takes every other 64-column block of the accumulator group.
-    //  * thread = accumulator row: tcgen05.ld (2 x 16 columns in flight) -> BN-affine / per-image bias -> BatchNorm
-    //    statistics (recursive-halving warp reduction) -> activation
-    //  * 16-bit outputs are staged through a swizzled 32 x 64 shared-memory tile per warp and written back with
-    //    4 rows x 128 B per instruction (a thread-per-row store costs 32 L1 wavefronts per 512 B; ncu showed the LSU
-    //    pipe, not HBM, bounding the wide expand / dgrad GEMMs); the residual is added in that coalesced phase.
+    // ===================== epilogue warps (2 .. 2 + 4*kSets) =====================
+    // A warp set = 4 warps, one per TMEM lane quarter.  Wide outputs: all sets drain the same accumulator group and
+    // take every kSets-th 64-column block.  Narrow outputs (alt_tiles): set s owns accumulator stage s, i.e. every
+    // acc_stages-th M tile, and drains all of its blocks.
+    //  * thread = accumulator row: tcgen05.ld (2 x 16 columns in flight) -> BN-affine / per-image bias
+    //  * 16-bit outputs are staged through a swizzled 32 x 64 shared-memory tile per warp; BatchNorm statistics are
+    //    taken from the staged (rounded) tile with a lane = 2 adjacent columns walk on packed fp32 pairs, and the tile
+    //    is written back with 4 rows x 128 B per instruction (a thread-per-row store costs 32 L1 wavefronts per 512 B);
+    //    residual and activation are applied in that coalesced phase.
     const int quad = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;           // which 64-column blocks
+    const int set = (warp - 2) >> 2;
     const bool do_stats = g.stat_sum != nullptr;
     const bool affine = g.col_scale != nullptr || g.col_shift != nullptr;
+    const bool staged = kStagedOnly || (kCanStage && g.shuffle_r == 0);
+    const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(warp - 2) * kStageTileBytes;   // [32 rows][8 chunks of 16 B]
+    // drain: chunk q of row `lane` -> slot q ^ (lane & 7)
+    const uint32_t stg_row = stg + lane * 128;
+    const uint32_t lane7 = lane & 7;
+    // statistics walk: lane owns word `lane` (columns 2*lane, 2*lane+1) of every row; rows r and r + 8k share a swizzle
+    const uint32_t st_chunk = lane >> 2, st_word = (lane & 3) * 4;
+    // write-back: 8 lanes cover the 128 B of one row, 4 rows per instruction; rows i*4 + rsub alternate two swizzles
+    const int cchunk = lane & 7, rsub = lane >> 3;
+    const uint32_t wb0 = stg + rsub * 128 + ((cchunk ^ rsub) << 4);
+    const uint32_t wb1 = stg + (rsub + 4) * 128 + ((cchunk ^ (rsub + 4)) << 4);
+    const bool wb_plain = g.R == nullptr && g.act == DLB_ACT_NONE;
     const int red_col = reduce16_col_of_lane(lane);
-    constexpr bool kStaged = sizeof(OutT) == 2;
-    uint4* stg = reinterpret_cast<uint4*>(s_stage) + static_cast<size_t>(warp - 2) * 32 * 8;   // [32 rows][8 chunks of 16 B]
-    const bool staged = kStaged && g.shuffle_r == 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
       const int m_base = tile * kBlockM + quad * 32;
       const int m = m_base + lane;
       const bool row_ok = m < g.M;
+      const int rows_left = g.M - m_base;
       const float* rb = nullptr;
       if (g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
       size_t shuf_row_base = 0;
-      if (g.shuffle_r > 0 && row_ok) {
+      if (!kStagedOnly && g.shuffle_r > 0 && row_ok) {
         const int hw = g.shuffle_h * g.shuffle_w;
         const int b = m / hw, rem = m - b * hw;
         const int a = rem / g.shuffle_w, bb = rem - a * g.shuffle_w;
@@ -201,12 +256,13 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
         const int as = it % g.acc_stages;
         const uint32_t aphase = (it / g.acc_stages) & 1;
-        if (g.alt_tiles && as != half) continue;     // narrow outputs: this warp set owns accumulator stage `half`
+        if (g.alt_tiles && as != set) continue;     // narrow outputs: this warp set owns accumulator stage `set`
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const int gcols = chunks * g.chunk_n;
         const int col_base = grp * group_rows;
-        for (int j64 = g.alt_tiles ? 0 : half * 64; j64 < gcols; j64 += 128) {
+        const int j_step = g.alt_tiles ? 64 : 64 * kSets;
+        for (int j64 = g.alt_tiles ? 0 : set * 64; j64 < gcols; j64 += j_step) {
 #pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             const int j = j64 + sub * 32;
@@ -252,29 +308,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
               for (int i = 0; i < 16; ++i) { v[1][i] = 0.f; if (all) v[0][i] = 0.f; }
             }
-            if (do_stats && !staged) {
-              float s1[2][16], s2[2][16];
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float q = v[h][i];
-                  s1[h][i] = q; s2[h][i] = q * q;
-                }
-              const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
-              const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
-              if ((lane & 1) == 0) {
-                const int n0 = col_base + j;
-                atomicAdd(&s_sum[n0 + red_col], t1a);
-                atomicAdd(&s_sqs[n0 + red_col], t2a);
-                if (two) {
-                  atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
-                  atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
-                }
-              }
-            }
             if (staged) {
-              // pack to 16 bit and park in the swizzled staging tile: chunk c of row `lane` -> slot c ^ (lane & 7)
+              // pack to 16 bit and park in the swizzled staging tile
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 float o[8];
@@ -282,94 +317,123 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int i = 0; i < 8; ++i) o[i] = v[c >> 1][(c & 1) * 8 + i];
                 uint4 pk;
                 Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
-                stg[lane * 8 + ((sub * 4 + c) ^ (lane & 7))] = pk;
+                sts128(stg_row + (((sub * 4 + c) ^ lane7) << 4), pk);
               }
-            } else if (row_ok) {
+            }
+            if constexpr (!kStagedOnly) {
+              if (!staged) {
+                if (do_stats) {
+                  float s1[2][16], s2[2][16];
 #pragma unroll
-              for (int h8 = 0; h8 < 4; ++h8) {
-                const int n = col_base + j + h8 * 8;
-                if (n >= g.n_store || (h8 >= 2 && !two)) continue;
-                float o[8];
+                  for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
-                if (g.R) {
-                  float rr[8];
-                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] += rr[i];
+                    for (int i = 0; i < 16; ++i) {
+                      const float q = v[h][i];
+                      s1[h][i] = q; s2[h][i] = q * q;
+                    }
+                  const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
+                  const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
+                  if ((lane & 1) == 0) {
+                    const int n0 = col_base + j;
+                    atomicAdd(&s_sum[n0 + red_col], t1a);
+                    atomicAdd(&s_sqs[n0 + red_col], t2a);
+                    if (two) {
+                      atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
+                      atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
+                    }
+                  }
                 }
-                OutT* dst;
-                if (g.shuffle_r > 0) {
-                  const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
-                  const int jj = n / rowlen, rem = n - jj * rowlen;
-                  dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
-                        static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
-                } else {
-                  dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
-                }
-                if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
-                } else {
-                  Vec8<OutT>::st(dst, o);
+                if (row_ok) {
+#pragma unroll
+                  for (int h8 = 0; h8 < 4; ++h8) {
+                    const int n = col_base + j + h8 * 8;
+                    if (n >= g.n_store || (h8 >= 2 && !two)) continue;
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
+                    if (g.R) {
+                      float rr[8];
+                      Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) o[i] += rr[i];
+                    }
+                    OutT* dst;
+                    if (g.shuffle_r > 0) {
+                      const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
+                      const int jj = n / rowlen, rem = n - jj * rowlen;
+                      dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
+                            static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
+                    } else {
+                      dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
+                    }
+                    if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
+                      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
+                    } else {
+                      Vec8<OutT>::st(dst, o);
+                    }
+                  }
                 }
               }
             }
           }
           if (staged) {
-            __syncwarp();
-            if (do_stats) {
-              // BatchNorm statistics of the (rounded, pre-activation) tile: lane owns 2 adjacent columns, walks the
-              // 32 rows of the staging tile (conflict-free: a warp reads one 128-byte row per step)
-              const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
-              const int chunk = lane >> 2, wsel = lane & 3;
-              float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
-#pragma unroll 8
-              for (int row = 0; row < 32; ++row) {
-                const uint32_t wv = words[row * 32 + ((chunk ^ (row & 7)) << 2) + wsel];
-                float fa, fb;
-                if (sizeof(OutT) == 2 && std::is_same<OutT, __half>::value) {
-                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv));
-                  fa = f.x; fb = f.y;
-                } else {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
-                  fa = f.x; fb = f.y;
-                }
-                sa += fa; sb += fb; qa = fmaf(fa, fa, qa); qb = fmaf(fb, fb, qb);
-              }
-              const int jc = j64 + 2 * lane;
-              if (jc < gcols) {
-                atomicAdd(&s_sum[col_base + jc], sa); atomicAdd(&s_sum[col_base + jc + 1], sb);
-                atomicAdd(&s_sqs[col_base + jc], qa); atomicAdd(&s_sqs[col_base + jc + 1], qb);
-              }
-            }
-            // coalesced write-back: 8 lanes cover the 128 B of one row, 4 rows per instruction
-            const int cchunk = lane & 7;
-            const int n = col_base + j64 + cchunk * 8;
+            if constexpr (kCanStage) {
+              __syncwarp();
+              if (do_stats) {
+                // BatchNorm statistics of the (rounded, pre-activation) tile: conflict-free, a warp reads one
+                // 128-byte row per step
+                unsigned long long acc_s = 0ull, acc_q = 0ull;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + (lane >> 3);
-              const int mm = m_base + row;
-              if (mm < g.M && n < g.n_store && j64 + cchunk * 8 < gcols) {
-                uint4 pk = stg[row * 8 + (cchunk ^ (row & 7))];
-                OutT* dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(mm) * g.ldc + n;
-                if (g.R || g.act != DLB_ACT_NONE) {
-                  float o[8];
-                  Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
+                for (int r8 = 0; r8 < 8; ++r8) {
+                  const uint32_t a0 = stg + r8 * 128 + (((st_chunk ^ r8) << 4) | st_word);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
-                  if (g.R) {
-                    float rr[8];
-                    Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(mm) * g.ldr + n, rr);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = word_to_float2<OutT>(lds32(a0 + k * 1024));
+                    f32x2_acc(acc_s, acc_q, f.x, f.y);
                   }
-                  Vec8<OutT>::st(dst, o);
-                } else {
-                  *reinterpret_cast<uint4*>(dst) = pk;
+                }
+                const int jc = j64 + 2 * lane;
+                if (jc < gcols) {
+                  const float2 s = f32x2_unpack(acc_s), q = f32x2_unpack(acc_q);
+                  atomicAdd(&s_sum[col_base + jc], s.x); atomicAdd(&s_sum[col_base + jc + 1], s.y);
+                  atomicAdd(&s_sqs[col_base + jc], q.x); atomicAdd(&s_sqs[col_base + jc + 1], q.y);
                 }
               }
+              // coalesced write-back
+              const int n = col_base + j64 + cchunk * 8;
+              if (n < g.n_store && j64 + cchunk * 8 < gcols) {
+                OutT* dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m_base + rsub) * g.ldc + n;
+                const size_t step = static_cast<size_t>(4) * g.ldc;
+                if (wb_plain) {
+                  uint4 pk[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pk[i] = lds128(((i & 1) ? wb1 : wb0) + (i >> 1) * 1024);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (i * 4 + rsub < rows_left) *reinterpret_cast<uint4*>(dst + i * step) = pk[i];
+                } else {
+                  const OutT* res = g.R ? reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m_base + rsub) * g.ldr + n : nullptr;
+                  const size_t rstep = static_cast<size_t>(4) * g.ldr;
+#pragma unroll 2
+                  for (int i = 0; i < 8; ++i) {
+                    if (i * 4 + rsub >= rows_left) break;
+                    const uint4 pk = lds128(((i & 1) ? wb1 : wb0) + (i >> 1) * 1024);
+                    float o[8];
+                    Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                    if (res) {
+                      float rr[8];
+                      Vec8<OutT>::ld(res + i * rstep, rr);
+#pragma unroll
+                      for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                    }
+                    Vec8<OutT>::st(dst + i * step, o);
+                  }
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
         }
         tc_fence_before();
@@ -572,6 +636,47 @@ int make_tmap_nhwc_sw128(CUtensorMap* map, int dtype, const void* ptr, int B, in
   return DLB_OK;
 }
 
+// Tiling plan of the tensor-core kernel (pure host arithmetic; exported as dlb_pw_gemm_plan for the CPU tests).
+// Returns the number of epilogue warp sets (4 or 2), or 0 if no pipeline fits.
+static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, GemmArgs* gp, size_t* tail_out) {
+  GemmArgs& g = *gp;
+  // 16-bit row-major outputs take the 4-set (16 epilogue warps) staged instance; fp32 / phase-shift stores the 2-set one
+  const int sets = (out_dtype != DLB_F32 && shuffle_r == 0) ? 4 : 2;
+  const int npad = (N + 15) / 16 * 16;
+  g.n_chunks = (npad + 255) / 256;
+  g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
+  g.k_elems_per_block = 64; g.umma_k = 16;
+  g.num_k_blocks = (K + 63) / 64;
+  g.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  const size_t tail = (2 * kMaxStages + 2 * kMaxAccStages) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 +
+                      static_cast<size_t>(4 * sets) * kStageTileBytes;
+  *tail_out = tail;
+  static const int tune_cpg = [] { const char* e = getenv("DLB_GEMM_CPG"); return e ? atoi(e) : 0; }();   // tuning aid
+  // Two chunks per accumulator group share one A fetch (matters when K is large); for small K prefer one chunk per
+  // group so the group fits twice in TMEM and the epilogue of one group overlaps the MMAs of the next.
+  for (int cpg = (g.n_chunks >= 2 && K > 256 && 2 * g.chunk_n <= 512 && tune_cpg != 1) ? 2 : 1; cpg >= 1; --cpg) {
+    g.chunks_per_group = cpg;
+    g.n_groups = (g.n_chunks + cpg - 1) / cpg;
+    g.acc_cols = cpg * g.chunk_n;
+    g.acc_stages = g.acc_cols <= 256 ? 2 : 1;
+    g.alt_tiles = 0;
+    if (g.n_groups == 1) {
+      // per-tile critical path in 64-column block units: all sets on one group vs one set per accumulator stage
+      int alt_stages = 512 / g.acc_cols;
+      if (alt_stages > sets) alt_stages = sets;
+      const int blocks = (g.acc_cols + 63) / 64;
+      const int cost_split = (blocks + sets - 1) / sets * 64;
+      if (alt_stages >= 2 && g.acc_cols < cost_split * alt_stages) { g.alt_tiles = 1; g.acc_stages = alt_stages; }
+    }
+    g.stage_bytes = kABytes + g.acc_cols * kSwzBytes;
+    if (static_cast<size_t>(kMaxSmem) < 1024 + tail + 2 * static_cast<size_t>(g.stage_bytes)) continue;
+    g.num_stages = static_cast<int>((kMaxSmem - 1024 - tail) / g.stage_bytes);
+    if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+    return sets;
+  }
+  return 0;
+}
+
 static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   GemmArgs g{};
   g.M = p->M; g.N = p->N; g.K = p->K;
@@ -583,25 +688,9 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
 
-  const int npad = (p->N + 15) / 16 * 16;
-  g.n_chunks = (npad + 255) / 256;
-  g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
-  // Two chunks per accumulator group share one A fetch (matters when K is large); for small K prefer one chunk per
-  // group so the group fits twice in TMEM and the epilogue of one group overlaps the MMAs of the next.
-  g.chunks_per_group = (g.n_chunks >= 2 && p->K > 256) ? 2 : 1;
-  if (g.chunks_per_group * g.chunk_n > 512) g.chunks_per_group = 1;
-  g.n_groups = (g.n_chunks + g.chunks_per_group - 1) / g.chunks_per_group;
-  g.acc_cols = g.chunks_per_group * g.chunk_n;
-  g.acc_stages = g.acc_cols <= 256 ? 2 : 1;
-  g.alt_tiles = (g.n_groups == 1 && g.acc_cols <= 64 && g.acc_stages == 2) ? 1 : 0;
-  g.k_elems_per_block = 64; g.umma_k = 16;
-  g.num_k_blocks = (p->K + 63) / 64;
-  g.num_m_tiles = (p->M + kBlockM - 1) / kBlockM;
-  g.stage_bytes = kABytes + g.acc_cols * kSwzBytes;
-  const int smem_budget = 168 * 1024;      // + 32 KB epilogue staging + barriers / per-column vectors
-  g.num_stages = smem_budget / g.stage_bytes;
-  if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
-  if (g.num_stages < 2) g.num_stages = 2;
+  size_t tail = 0;
+  const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, &g, &tail);
+  DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
   g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 0, 0);
 
   CUtensorMap ta, tb;
@@ -610,19 +699,18 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, 64);
   if (rc) return rc;
 
-  const size_t tail = (2 * kMaxStages + 4) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 + 8 * 4096;
   const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
   const int grid = g.num_m_tiles < num_sms() ? g.num_m_tiles : num_sms();
 
-#define LAUNCH(OT)                                                                                             \
+#define LAUNCH(OT, SETS)                                                                                       \
   do {                                                                                                         \
-    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                   (int)smem_bytes));                                                           \
-    pw_gemm_tc_kernel<OT><<<grid, kGemmThreads, smem_bytes, st>>>(ta, tb, g);                                  \
+    pw_gemm_tc_kernel<OT, SETS><<<grid, 64 + 128 * SETS, smem_bytes, st>>>(ta, tb, g);                         \
   } while (0)
-  if (p->out_dtype == DLB_F16) LAUNCH(__half);
-  else if (p->out_dtype == DLB_BF16) LAUNCH(__nv_bfloat16);
-  else LAUNCH(float);
+  if (p->out_dtype == DLB_F16) { if (sets == 4) LAUNCH(__half, 4); else LAUNCH(__half, 2); }
+  else if (p->out_dtype == DLB_BF16) { if (sets == 4) LAUNCH(__nv_bfloat16, 4); else LAUNCH(__nv_bfloat16, 2); }
+  else LAUNCH(float, 2);
 #undef LAUNCH
   g_launches++;
   return check_launch("pw_gemm_tc_kernel");
@@ -648,6 +736,18 @@ static int launch_simt(const dlb_pw_gemm_params* p, cudaStream_t st) {
 }
 
 }  // namespace dlb
+
+extern "C" int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_r, int* plan) {
+  using namespace dlb;
+  GemmArgs g{};
+  size_t tail = 0;
+  const int sets = plan_tc(N, K, M, out_dtype, shuffle_r, &g, &tail);
+  if (sets == 0) return DLB_ERR_INVALID;
+  plan[0] = sets; plan[1] = g.chunk_n; plan[2] = g.n_chunks; plan[3] = g.chunks_per_group; plan[4] = g.n_groups;
+  plan[5] = g.acc_cols; plan[6] = g.acc_stages; plan[7] = g.alt_tiles; plan[8] = g.num_stages;
+  plan[9] = static_cast<int>(1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail);
+  return DLB_OK;
+}
 
 extern "C" int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream) {
   using namespace dlb;

@@ -77,3 +77,29 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py") and fn != "selftest.py":
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_pw_gemm_plan_fits_every_layer_shape(lib):
+    """The tensor-core GEMM's tiling plan (host arithmetic) must fit TMEM (512 columns) and shared memory (227 KB)
+    with a >= 2-stage pipeline for every (K, N) of the MobileNetV2 / Xception graphs, forward and dgrad."""
+    L = lib.lib()
+    L.dlb_pw_gemm_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)]
+    chans = [(16, 96), (96, 24), (24, 144), (144, 24), (144, 32), (32, 192), (192, 32), (192, 64), (64, 384), (384, 64),
+             (384, 96), (96, 576), (576, 96), (576, 160), (160, 960), (960, 160), (960, 320), (32, 16), (320, 256),
+             (512, 256), (256, 21), (256, 1344), (2048, 256), (1280, 256), (304, 256), (256, 48), (728, 728),
+             (1536, 2048), (1024, 1536), (256, 256), (128, 256), (256, 728), (728, 1024)]
+    M = 16 * 64 * 64
+    F16, F32 = lib.F16, lib.F32
+    for k, n in chans:
+        for (kk, nn) in ((k, n), (n, k)):           # forward and backward-data
+            for od, shuf in ((F16, 0), (F32, 0), (F16, 8 if nn == 1344 else 0)):
+                plan = (C.c_int * 10)()
+                assert L.dlb_pw_gemm_plan(M, nn, kk, od, shuf, plan) == 0, (kk, nn, od, shuf)
+                sets, chunk_n, n_chunks, cpg, n_groups, acc_cols, acc_stages, alt, stages, smem = list(plan)
+                assert sets == (4 if (od != F32 and shuf == 0) else 2)
+                assert chunk_n % 16 == 0 and 16 <= chunk_n <= 256 and chunk_n * n_chunks >= nn
+                assert acc_cols * acc_stages <= 512, (kk, nn, list(plan))
+                assert 2 <= stages <= 8 and smem <= 227 * 1024, (kk, nn, list(plan))
+                assert acc_stages <= sets if alt else acc_stages <= 2
+                if alt:
+                    assert n_groups == 1
