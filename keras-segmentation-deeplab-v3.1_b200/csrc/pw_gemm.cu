@@ -89,6 +89,19 @@ __device__ __forceinline__ float2 f32x2_unpack(unsigned long long v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
   return f;
 }
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" ::"r"(bar_saddr),
+      "r"(parity)
+      : "memory");
+}
 template <typename OutT> __device__ __forceinline__ float2 word_to_float2(uint32_t w);
 template <> __device__ __forceinline__ float2 word_to_float2<__half>(uint32_t w) {
   return __half22float2(*reinterpret_cast<const __half2*>(&w));
@@ -100,7 +113,9 @@ template <> __device__ __forceinline__ float2 word_to_float2<float>(uint32_t w) 
 
 // kSets epilogue warp sets of 4 warps (one warp per TMEM lane quarter).  kSets == 4 is the 16-bit staged-output
 // instance (host guarantees: 16-bit OutT, no phase-shift store); kSets == 2 also carries the fp32 / phase-shift stores.
-template <typename OutT, int kSets>
+// kLean: no BN-affine and no per-image bias (every training-step GEMM but concat_projection) -- the drain is then
+// tcgen05.ld -> pack -> st.shared with no option tests.
+template <typename OutT, int kSets, bool kLean>
 __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmArgs g) {
@@ -176,12 +191,10 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       // ===================== MMA issuer =====================
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
+      int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
-        for (int grp = 0; grp < g.n_groups; ++grp, ++it) {
+        for (int grp = 0; grp < g.n_groups; ++grp) {
           const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
-          const int as = it % g.acc_stages;
-          const uint32_t aphase = (it / g.acc_stages) & 1;
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
           for (int kb = 0; kb < g.num_k_blocks; ++kb) {
@@ -204,6 +217,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(&tfull_bar[as]);          // accumulator group complete -> epilogue
+          if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
         }
       }
     }
@@ -220,7 +234,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int quad = warp & 3;                  // TMEM lane quarter this warp may access
     const int set = (warp - 2) >> 2;
     const bool do_stats = g.stat_sum != nullptr;
-    const bool affine = g.col_scale != nullptr || g.col_shift != nullptr;
+    const bool affine = !kLean && (g.col_scale != nullptr || g.col_shift != nullptr);
     const bool staged = kStagedOnly || (kCanStage && g.shuffle_r == 0);
     const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(warp - 2) * kStageTileBytes;   // [32 rows][8 chunks of 16 B]
     // drain: chunk q of row `lane` -> slot q ^ (lane & 7)
@@ -234,14 +248,17 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t wb1 = stg + (rsub + 4) * 128 + ((cchunk ^ (rsub + 4)) << 4);
     const bool wb_plain = g.R == nullptr && g.act == DLB_ACT_NONE;
     const int red_col = reduce16_col_of_lane(lane);
-    int it = 0;
+    const uint32_t tfull_a = smem_u32(tfull_bar);
+    const int j_first = g.alt_tiles ? 0 : set * 64;
+    const int j_step = g.alt_tiles ? 64 : 64 * kSets;
+    int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
       const int m_base = tile * kBlockM + quad * 32;
       const int m = m_base + lane;
       const bool row_ok = m < g.M;
       const int rows_left = g.M - m_base;
       const float* rb = nullptr;
-      if (g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
+      if (!kLean && g.row_bias && row_ok) rb = g.row_bias + static_cast<size_t>(m / g.rows_per_img) * g.ld_row_bias;
       size_t shuf_row_base = 0;
       if (!kStagedOnly && g.shuffle_r > 0 && row_ok) {
         const int hw = g.shuffle_h * g.shuffle_w;
@@ -252,24 +269,24 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                          static_cast<size_t>(bb) * g.shuffle_r) *
                         g.shuffle_cs;
       }
-      for (int grp = 0; grp < g.n_groups; ++grp, ++it) {
+      for (int grp = 0; grp < g.n_groups; ++grp) {
         const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
-        const int as = it % g.acc_stages;
-        const uint32_t aphase = (it / g.acc_stages) & 1;
-        if (g.alt_tiles && as != set) continue;     // narrow outputs: this warp set owns accumulator stage `set`
-        mbar_wait(&tfull_bar[as], aphase);
+        const int as_cur = as;
+        const uint32_t aphase_cur = aphase;
+        if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
+        if (g.alt_tiles && as_cur != set) continue;     // narrow outputs: this warp set owns accumulator stage `set`
+        mbar_wait_s(tfull_a + as_cur * 8, aphase_cur);
         tc_fence_after();
         const int gcols = chunks * g.chunk_n;
         const int col_base = grp * group_rows;
-        const int j_step = g.alt_tiles ? 64 : 64 * kSets;
-        for (int j64 = g.alt_tiles ? 0 : set * 64; j64 < gcols; j64 += j_step) {
+        for (int j64 = j_first; j64 < gcols; j64 += j_step) {
 #pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             const int j = j64 + sub * 32;
             if (j >= gcols) break;
             const bool two = j + 16 < gcols;
             uint32_t r[2][16];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * g.acc_cols + j;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as_cur * g.acc_cols + j;
             tmem_ld16(taddr, r[0]);
             if (two) tmem_ld16(taddr + 16, r[1]);
             tmem_ld_wait();
@@ -279,7 +296,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[h][i] = __uint_as_float(r[h][i]);
             // kernel-uniform options are tested once per 32 columns, not per element
-            if (affine) {
+            if (!kLean && affine) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col_base + j + h * 16);
@@ -294,7 +311,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
               }
             }
-            if (rb) {
+            if (!kLean && rb) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int n0 = col_base + j + h * 16;
@@ -382,16 +399,20 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (do_stats) {
                 // BatchNorm statistics of the (rounded, pre-activation) tile: conflict-free, a warp reads one
                 // 128-byte row per step
-                unsigned long long acc_s = 0ull, acc_q = 0ull;
+                unsigned long long acc_s = 0ull, acc_q = 0ull, acc_s2 = 0ull, acc_q2 = 0ull;   // two chains per statistic
 #pragma unroll
                 for (int r8 = 0; r8 < 8; ++r8) {
                   const uint32_t a0 = stg + r8 * 128 + (((st_chunk ^ r8) << 4) | st_word);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
+                  for (int k = 0; k < 4; k += 2) {
                     const float2 f = word_to_float2<OutT>(lds32(a0 + k * 1024));
+                    const float2 h = word_to_float2<OutT>(lds32(a0 + (k + 1) * 1024));
                     f32x2_acc(acc_s, acc_q, f.x, f.y);
+                    f32x2_acc(acc_s2, acc_q2, h.x, h.y);
                   }
                 }
+                acc_s = f32x2_add(acc_s, acc_s2);
+                acc_q = f32x2_add(acc_q, acc_q2);
                 const int jc = j64 + 2 * lane;
                 if (jc < gcols) {
                   const float2 s = f32x2_unpack(acc_s), q = f32x2_unpack(acc_q);
@@ -405,30 +426,44 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 OutT* dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m_base + rsub) * g.ldc + n;
                 const size_t step = static_cast<size_t>(4) * g.ldc;
                 if (wb_plain) {
-                  uint4 pk[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) pk[i] = lds128(((i & 1) ? wb1 : wb0) + (i >> 1) * 1024);
+                  for (int i0 = 0; i0 < 8; i0 += 4) {
+                    uint4 pk[4];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    if (i * 4 + rsub < rows_left) *reinterpret_cast<uint4*>(dst + i * step) = pk[i];
+                    for (int i = 0; i < 4; ++i) pk[i] = lds128((((i0 + i) & 1) ? wb1 : wb0) + ((i0 + i) >> 1) * 1024);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      if ((i0 + i) * 4 + rsub < rows_left) *reinterpret_cast<uint4*>(dst + (i0 + i) * step) = pk[i];
+                  }
                 } else {
+                  // activation, then the residual (loaded 4 rows ahead: the thread-per-vector loads are latency bound)
                   const OutT* res = g.R ? reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m_base + rsub) * g.ldr + n : nullptr;
                   const size_t rstep = static_cast<size_t>(4) * g.ldr;
-#pragma unroll 2
-                  for (int i = 0; i < 8; ++i) {
-                    if (i * 4 + rsub >= rows_left) break;
-                    const uint4 pk = lds128(((i & 1) ? wb1 : wb0) + (i >> 1) * 1024);
-                    float o[8];
-                    Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                  for (int i0 = 0; i0 < 8; i0 += 4) {
+                    uint4 rr[4];
                     if (res) {
-                      float rr[8];
-                      Vec8<OutT>::ld(res + i * rstep, rr);
 #pragma unroll
-                      for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                      for (int i = 0; i < 4; ++i)
+                        rr[i] = ((i0 + i) * 4 + rsub < rows_left) ? *reinterpret_cast<const uint4*>(res + (i0 + i) * rstep)
+                                                                  : make_uint4(0u, 0u, 0u, 0u);
                     }
-                    Vec8<OutT>::st(dst + i * step, o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const int ii = i0 + i;
+                      const uint4 pk = lds128(((ii & 1) ? wb1 : wb0) + (ii >> 1) * 1024);
+                      float o[8];
+                      Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
+#pragma unroll
+                      for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                      if (res) {
+                        float rf[8];
+                        Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&rr[i]), rf);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] += rf[q];
+                      }
+                      if (ii * 4 + rsub < rows_left) Vec8<OutT>::st(dst + ii * step, o);
+                    }
                   }
                 }
               }
@@ -438,7 +473,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) mbar_arrive(&tempty_bar[as_cur]);
       }
     }
     if (do_stats) {
@@ -702,15 +737,18 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
   const int grid = g.num_m_tiles < num_sms() ? g.num_m_tiles : num_sms();
 
-#define LAUNCH(OT, SETS)                                                                                       \
-  do {                                                                                                         \
-    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                  (int)smem_bytes));                                                           \
-    pw_gemm_tc_kernel<OT, SETS><<<grid, 64 + 128 * SETS, smem_bytes, st>>>(ta, tb, g);                         \
+  const bool lean = !p->col_scale && !p->col_shift && !p->row_bias;
+#define LAUNCH(OT, SETS, LEAN)                                                                                   \
+  do {                                                                                                           \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem_bytes));                                                             \
+    pw_gemm_tc_kernel<OT, SETS, LEAN><<<grid, 64 + 128 * SETS, smem_bytes, st>>>(ta, tb, g);                     \
   } while (0)
-  if (p->out_dtype == DLB_F16) { if (sets == 4) LAUNCH(__half, 4); else LAUNCH(__half, 2); }
-  else if (p->out_dtype == DLB_BF16) { if (sets == 4) LAUNCH(__nv_bfloat16, 4); else LAUNCH(__nv_bfloat16, 2); }
-  else LAUNCH(float, 2);
+#define LAUNCH2(OT, SETS) do { if (lean) LAUNCH(OT, SETS, true); else LAUNCH(OT, SETS, false); } while (0)
+  if (p->out_dtype == DLB_F16) { if (sets == 4) LAUNCH2(__half, 4); else LAUNCH2(__half, 2); }
+  else if (p->out_dtype == DLB_BF16) { if (sets == 4) LAUNCH2(__nv_bfloat16, 4); else LAUNCH2(__nv_bfloat16, 2); }
+  else LAUNCH2(float, 2);
+#undef LAUNCH2
 #undef LAUNCH
   g_launches++;
   return check_launch("pw_gemm_tc_kernel");
