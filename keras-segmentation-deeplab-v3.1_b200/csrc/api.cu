@@ -1,6 +1,7 @@
 // C-ABI plumbing (version, thread-local error, launch counter) + optimizer / cast / fill kernels.
 //   Adam : Keras 2.2.4 optimizers.Adam as configured at segmentation.ipynb cell "compile" (ipynb:107):
 //          Adam(lr=7e-4, epsilon=1e-8, decay=1e-6)
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +29,11 @@ int check_launch(const char* what) {
   return DLB_OK;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DLB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -41,6 +47,7 @@ int num_sms() {
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
                             float eps, float decay, float gmult) {
+  pdl_prologue();
   const long long it = *step;                 // iterations before this update
   const float t = static_cast<float>(it) + 1.f;
   float lr_t = lr;
@@ -55,10 +62,12 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
   }
 }
-__global__ void step_inc_kernel(long long* step) { *step += 1; }
+__global__ void step_inc_kernel(long long* step) {
+  pdl_prologue(); *step += 1; }
 
 template <typename T>
 __global__ void cast_weight_kernel(int K, int N, const float* __restrict__ w, T* __restrict__ w_kn, T* __restrict__ w_nk) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   const int k = i / N, n = i - k * N;
@@ -69,6 +78,7 @@ __global__ void cast_weight_kernel(int K, int N, const float* __restrict__ w, T*
 
 // one launch for all layers: entry found by binary search over the prefix of flat element counts
 __global__ void __launch_bounds__(256) cast_weights_batched_kernel(int n_entries, const long long* __restrict__ tab, long long total) {
+  pdl_prologue();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     int lo = 0, hi = n_entries - 1;
@@ -98,6 +108,7 @@ __global__ void __launch_bounds__(256) cast_weights_batched_kernel(int n_entries
 
 template <typename S, typename D>
 __global__ void cast_kernel(long long n, const S* __restrict__ s, D* __restrict__ d) {
+  pdl_prologue();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     Act<D>::st(&d[i], Act<S>::ld(&s[i]));
@@ -125,9 +136,9 @@ extern "C" int dlb_adam_step(int64_t n, float* param, const float* grad, float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
-  adam_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(
+  launch_k(adam_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, 
       n, param, grad, m, v, reinterpret_cast<const long long*>(step_dev), lr, beta1, beta2, eps, decay, grad_mult);
-  step_inc_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(step_dev));
+  launch_k(step_inc_kernel, 1, 1, 0, st, reinterpret_cast<long long*>(step_dev));
   g_launches += 2;
   return check_launch("adam_kernel");
 }
@@ -136,9 +147,9 @@ extern "C" int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_
   DLB_REQUIRE(w && (w_kn || w_nk) && K > 0 && N > 0, "cast_weight: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (K * N + 255) / 256;
-  if (dtype == DLB_F16) cast_weight_kernel<__half><<<grid, 256, 0, st>>>(K, N, w, (__half*)w_kn, (__half*)w_nk);
-  else if (dtype == DLB_BF16) cast_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(K, N, w, (__nv_bfloat16*)w_kn, (__nv_bfloat16*)w_nk);
-  else cast_weight_kernel<float><<<grid, 256, 0, st>>>(K, N, w, (float*)w_kn, (float*)w_nk);
+  if (dtype == DLB_F16) launch_k(cast_weight_kernel<__half>, grid, 256, 0, st, K, N, w, (__half*)w_kn, (__half*)w_nk);
+  else if (dtype == DLB_BF16) launch_k(cast_weight_kernel<__nv_bfloat16>, grid, 256, 0, st, K, N, w, (__nv_bfloat16*)w_kn, (__nv_bfloat16*)w_nk);
+  else launch_k(cast_weight_kernel<float>, grid, 256, 0, st, K, N, w, (float*)w_kn, (float*)w_nk);
   g_launches++;
   return check_launch("cast_weight_kernel");
 }
@@ -148,7 +159,7 @@ extern "C" int dlb_cast_weights_batched(int n_entries, const int64_t* table, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
-  cast_weights_batched_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(
+  launch_k(cast_weights_batched_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, 
       n_entries, reinterpret_cast<const long long*>(table), total);
   g_launches++;
   return check_launch("cast_weights_batched_kernel");
@@ -160,7 +171,7 @@ extern "C" int dlb_cast(int64_t n, int src_dtype, const void* src, int dst_dtype
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-#define GO(S, D) cast_kernel<S, D><<<grid, 256, 0, st>>>(n, (const S*)src, (D*)dst)
+#define GO(S, D) launch_k(cast_kernel<S, D>, grid, 256, 0, st, n, (const S*)src, (D*)dst)
   if (src_dtype == DLB_F32 && dst_dtype == DLB_F16) GO(float, __half);
   else if (src_dtype == DLB_F32 && dst_dtype == DLB_BF16) GO(float, __nv_bfloat16);
   else if (src_dtype == DLB_F16 && dst_dtype == DLB_F32) GO(__half, float);

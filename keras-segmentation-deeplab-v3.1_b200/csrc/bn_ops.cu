@@ -17,6 +17,7 @@ __global__ void bn_finalize_kernel(int C, double count, double* sum, double* sqs
                                    const float* beta, float eps, float momentum, float* moving_mean,
                                    float* moving_var, float* scale, float* shift, float* mean_out, float* rstd_out,
                                    int reset) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sum[c] / count;
@@ -39,6 +40,7 @@ __global__ void bn_finalize_kernel(int C, double count, double* sum, double* sqs
 
 __global__ void bn_fold_kernel(int C, const float* gamma, const float* beta, const float* mm, const float* mv,
                                float eps, float* scale, float* shift) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] / sqrtf(mv[c] + eps);
@@ -64,6 +66,7 @@ struct ApplyArgs {
 // contiguous block of memory), 4 rows in flight per thread
 template <typename T>
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const ApplyArgs a) {
+  pdl_prologue();
   const T* x = reinterpret_cast<const T*>(a.x);
   const T* res = reinterpret_cast<const T*>(a.res);
   T* y = reinterpret_cast<T*>(a.y);
@@ -116,6 +119,7 @@ struct BwdArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs a) {
+  pdl_prologue();
   extern __shared__ float s_red[];   // [2*C]
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * a.C; i += blockDim.x) s_red[i] = 0.f;
@@ -184,6 +188,7 @@ template <typename T> __device__ __forceinline__ void stg_bh8(void* p, const BV8
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a) {
+  pdl_prologue();
   extern __shared__ float s_red[];   // [rpb][2*C] per-row-group partial sums (no shared atomics: they were a 32-way
                                      // CAS contention, a third of the kernel on the narrow project BNs)
   const int tid = threadIdx.x;
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_h_kernel(const BwdArgs a
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
+  pdl_prologue();
   const int tid = threadIdx.x;
   if (blockIdx.x == 0) {
     for (int c = tid; c < a.C; c += blockDim.x) {
@@ -308,6 +314,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdArgs a) {
 // dz - mean(dz) - xhat * mean(dz * xhat) in fp32 (the mean terms are far below one fp16 ulp of dz)
 template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_h_kernel(const BwdArgs a) {
+  pdl_prologue();
   const int tid = threadIdx.x;
   if (blockIdx.x == 0) {
     for (int c = tid; c < a.C; c += blockDim.x) {
@@ -380,6 +387,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(int HW, int C, int cv, int rpb, int splits, const T* x,
                                                           const float* in_scale, const float* in_shift, int in_act,
                                                           float* out) {
+  pdl_prologue();
   extern __shared__ float s_acc[];   // [C]
   const int tid = threadIdx.x;
   const int b = blockIdx.x / splits, sp = blockIdx.x - b * splits;
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(int HW, int C, int cv,
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(long long nvec, int HW, int C, const float* dout, T* dx,
                                                           int accumulate) {
+  pdl_prologue();
   const float inv = 1.f / static_cast<float>(HW);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -430,6 +439,7 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(long long nvec, int HW
 // tiny fp32 GEMM, one thread per output element (M, N <= a few hundred)
 __global__ void small_gemm_kernel(int M, int N, int K, const float* A, int lda, int tA, const float* B, int ldb,
                                   int tB, float* C, int ldc, float alpha, float beta) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (n >= N || m >= M) return;
@@ -478,6 +488,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
 
 template <typename T, int kMode>
 __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   using P = typename BP2<T>::t;
   const int tid = threadIdx.x;
@@ -660,10 +671,10 @@ static int launch_bn_stream(StreamArgs a, int dtype, cudaStream_t st) {
   const int grid = static_cast<int>(n_blk < num_sms() ? n_blk : num_sms());
   if (dtype == DLB_F16) {
     DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__half, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_stream_kernel<__half, kMode><<<grid, kSThreads, smem, st>>>(a);
+    launch_k(bn_stream_kernel<__half, kMode>, grid, kSThreads, smem, st, a);
   } else {
     DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__nv_bfloat16, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bn_stream_kernel<__nv_bfloat16, kMode><<<grid, kSThreads, smem, st>>>(a);
+    launch_k(bn_stream_kernel<__nv_bfloat16, kMode>, grid, kSThreads, smem, st, a);
   }
   g_launches++;
   return check_launch("bn_stream_kernel");
@@ -686,7 +697,7 @@ extern "C" int dlb_bn_finalize(int C, double count, double* sum, double* sqs, co
                                float* shift, float* mean, float* rstd, int reset, void* stream) {
   DLB_REQUIRE(C > 0 && sum && sqs && gamma && beta && scale && shift, "bn_finalize: null pointer");
   DLB_REQUIRE(count > 0, "bn_finalize: count must be positive");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
       C, count, sum, sqs, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, mean, rstd, reset);
   g_launches++;
   return check_launch("bn_finalize_kernel");
@@ -695,7 +706,7 @@ extern "C" int dlb_bn_finalize(int C, double count, double* sum, double* sqs, co
 extern "C" int dlb_bn_fold(int C, const float* gamma, const float* beta, const float* moving_mean,
                            const float* moving_var, float eps, float* scale, float* shift, void* stream) {
   DLB_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && shift, "bn_fold: null pointer");
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(C, gamma, beta, moving_mean,
+  launch_k(bn_fold_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), C, gamma, beta, moving_mean,
                                                                                  moving_var, eps, scale, shift);
   g_launches++;
   return check_launch("bn_fold_kernel");
@@ -720,9 +731,9 @@ extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   const long long cap_ = static_cast<long long>(num_sms()) * 8;
   const int grid = static_cast<int>(blocks_ < cap_ ? (blocks_ > 0 ? blocks_ : 1) : cap_);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16) bn_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else if (p->dtype == DLB_BF16) bn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
-  else bn_apply_kernel<float><<<grid, 256, 0, st>>>(a);
+  if (p->dtype == DLB_F16) launch_k(bn_apply_kernel<__half>, grid, 256, 0, st, a);
+  else if (p->dtype == DLB_BF16) launch_k(bn_apply_kernel<__nv_bfloat16>, grid, 256, 0, st, a);
+  else launch_k(bn_apply_kernel<float>, grid, 256, 0, st, a);
   g_launches++;
   return check_launch("bn_apply_kernel");
 }
@@ -755,12 +766,12 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   const size_t smem = 2 * p->C * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dtype == DLB_F16 && p->drop_rate <= 0.f)
-    bn_bwd_reduce_h_kernel<__half><<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);       // [rpb][2C] <= 16 KB
+    launch_k(bn_bwd_reduce_h_kernel<__half>, grid, 256, static_cast<size_t>(a.rpb) * smem, st, a);       // [rpb][2C] <= 16 KB
   else if (p->dtype == DLB_BF16 && p->drop_rate <= 0.f)
-    bn_bwd_reduce_h_kernel<__nv_bfloat16><<<grid, 256, static_cast<size_t>(a.rpb) * smem, st>>>(a);
-  else if (p->dtype == DLB_F16) bn_bwd_reduce_kernel<__half><<<grid, 256, smem, st>>>(a);
-  else if (p->dtype == DLB_BF16) bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a);
-  else bn_bwd_reduce_kernel<float><<<grid, 256, smem, st>>>(a);
+    launch_k(bn_bwd_reduce_h_kernel<__nv_bfloat16>, grid, 256, static_cast<size_t>(a.rpb) * smem, st, a);
+  else if (p->dtype == DLB_F16) launch_k(bn_bwd_reduce_kernel<__half>, grid, 256, smem, st, a);
+  else if (p->dtype == DLB_BF16) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, grid, 256, smem, st, a);
+  else launch_k(bn_bwd_reduce_kernel<float>, grid, 256, smem, st, a);
   g_launches++;
   return check_launch("bn_bwd_reduce_kernel");
 }
@@ -782,11 +793,11 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   long long cap = static_cast<long long>(num_sms()) * 6;
   const int grid = static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else if (p->dtype == DLB_BF16 && p->drop_rate <= 0.f) bn_bwd_apply_h_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
-  else if (p->dtype == DLB_F16) bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(a);
-  else if (p->dtype == DLB_BF16) bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
-  else bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(a);
+  if (p->dtype == DLB_F16 && p->drop_rate <= 0.f) launch_k(bn_bwd_apply_h_kernel<__half>, grid, 256, 0, st, a);
+  else if (p->dtype == DLB_BF16 && p->drop_rate <= 0.f) launch_k(bn_bwd_apply_h_kernel<__nv_bfloat16>, grid, 256, 0, st, a);
+  else if (p->dtype == DLB_F16) launch_k(bn_bwd_apply_kernel<__half>, grid, 256, 0, st, a);
+  else if (p->dtype == DLB_BF16) launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, grid, 256, 0, st, a);
+  else launch_k(bn_bwd_apply_kernel<float>, grid, 256, 0, st, a);
   g_launches++;
   return check_launch("bn_bwd_apply_kernel");
 }
@@ -803,9 +814,9 @@ extern "C" int dlb_global_avgpool_fwd(int B, int HW, int C, int dtype, const voi
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   const size_t smem = C * sizeof(float);
-  if (dtype == DLB_F16) avgpool_fwd_kernel<__half><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const __half*)x, in_scale, in_shift, in_act, out);
-  else if (dtype == DLB_BF16) avgpool_fwd_kernel<__nv_bfloat16><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const __nv_bfloat16*)x, in_scale, in_shift, in_act, out);
-  else avgpool_fwd_kernel<float><<<B * splits, 256, smem, st>>>(HW, C, cv, rpb, splits, (const float*)x, in_scale, in_shift, in_act, out);
+  if (dtype == DLB_F16) launch_k(avgpool_fwd_kernel<__half>, B * splits, 256, smem, st, HW, C, cv, rpb, splits, (const __half*)x, in_scale, in_shift, in_act, out);
+  else if (dtype == DLB_BF16) launch_k(avgpool_fwd_kernel<__nv_bfloat16>, B * splits, 256, smem, st, HW, C, cv, rpb, splits, (const __nv_bfloat16*)x, in_scale, in_shift, in_act, out);
+  else launch_k(avgpool_fwd_kernel<float>, B * splits, 256, smem, st, HW, C, cv, rpb, splits, (const float*)x, in_scale, in_shift, in_act, out);
   g_launches++;
   return check_launch("avgpool_fwd_kernel");
 }
@@ -816,9 +827,9 @@ extern "C" int dlb_global_avgpool_bwd(int B, int HW, int C, int dtype, const flo
   const long long nvec = static_cast<long long>(B) * HW * C / 8;
   const int grid = grid_for(nvec, 256, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DLB_F16) avgpool_bwd_kernel<__half><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (__half*)dx, accumulate);
-  else if (dtype == DLB_BF16) avgpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (__nv_bfloat16*)dx, accumulate);
-  else avgpool_bwd_kernel<float><<<grid, 256, 0, st>>>(nvec, HW, C, dout, (float*)dx, accumulate);
+  if (dtype == DLB_F16) launch_k(avgpool_bwd_kernel<__half>, grid, 256, 0, st, nvec, HW, C, dout, (__half*)dx, accumulate);
+  else if (dtype == DLB_BF16) launch_k(avgpool_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, nvec, HW, C, dout, (__nv_bfloat16*)dx, accumulate);
+  else launch_k(avgpool_bwd_kernel<float>, grid, 256, 0, st, nvec, HW, C, dout, (float*)dx, accumulate);
   g_launches++;
   return check_launch("avgpool_bwd_kernel");
 }
@@ -827,7 +838,7 @@ extern "C" int dlb_small_gemm(int M, int N, int K, const float* A, int lda, int 
                               int transB, float* C, int ldc, float alpha, float beta, void* stream) {
   DLB_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "small_gemm: bad arguments");
   dim3 grid((N + 127) / 128, M);
-  small_gemm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(M, N, K, A, lda, transA, B, ldb, transB, C,
+  launch_k(small_gemm_kernel, grid, 128, 0, static_cast<cudaStream_t>(stream), M, N, K, A, lda, transA, B, ldb, transB, C,
                                                                         ldc, alpha, beta);
   g_launches++;
   return check_launch("small_gemm_kernel");

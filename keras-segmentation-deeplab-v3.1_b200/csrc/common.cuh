@@ -313,4 +313,33 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   return a1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_prologue(), so the CTAs of kernel i+1 are
+// scheduled (and run their launch / index-math prologue) while kernel i drains; griddepcontrol.wait returns only
+// after the preceding grid has completed and flushed, so no kernel touches global memory early.  A step is ~430
+// dependent launches; this hides most of the kernel-boundary latency inside the captured CUDA graph.
+// DLB_PDL=0 in the environment disables the attribute (plain stream order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+#ifdef DLB_PDL_EARLY_TRIGGER
+  pdl_trigger();
+#endif
+  pdl_wait();
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through check_launch()
+}
+
 }  // namespace dlb

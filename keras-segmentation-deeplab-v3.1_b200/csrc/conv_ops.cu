@@ -34,6 +34,7 @@ struct DwArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const DwArgs a) {
+  pdl_prologue();
   extern __shared__ float s_stats[];   // [2*C] when stats are requested
   const int tid = threadIdx.x;
   const bool active = tid < a.ppb * a.cv;
@@ -125,6 +126,7 @@ struct DwBwdArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const DwBwdArgs a) {
+  pdl_prologue();
   const int tid = threadIdx.x;
   if (tid >= a.ppb * a.cv) return;
   const int p_in_blk = tid / a.cv;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const DwBwdArgs a) {
 // depthwise backward-weight: dw[ky,kx,c] += sum a[b, ho*s - pad + ky*d, wo*s - pad + kx*d, c] * dy[b,ho,wo,c]
 template <typename T>
 __global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const DwBwdArgs a) {
+  pdl_prologue();
   extern __shared__ float s_dw[];   // [9*C]
   const int tid = threadIdx.x;
   for (int i = tid; i < 9 * a.C; i += blockDim.x) s_dw[i] = 0.f;
@@ -297,6 +300,7 @@ __device__ __forceinline__ void dw_stage_input(const DwTileArgs& a, T* s_in, int
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_kernel(const DwTileArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t s_raw[];
   T* s_in = reinterpret_cast<T*>(s_raw);
   float* s_stats = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T));   // [2][64]
@@ -405,6 +409,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tiled_kernel(const DwTileArgs a
 // backward-weight, tiled: dw[tap, c] += sum_pixels a[pix + tap] * dy[pix]; 72 accumulators per thread
 template <typename T>
 __global__ void __launch_bounds__(256, 1) dw_wgrad_tiled_kernel(const DwTileArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t s_raw[];
   T* s_in = reinterpret_cast<T*>(s_raw);
   float* s_dw = reinterpret_cast<float*>(s_raw + static_cast<size_t>(a.ih) * a.iw * kCV * 8 * sizeof(T));   // [9][64]
@@ -622,6 +627,7 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
@@ -756,6 +762,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 
 template <typename T>
 __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
@@ -893,6 +900,7 @@ struct DwS2Args {
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwS2Args a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   constexpr int IH = kTH + 1, IW = kTW + 1;
   constexpr uint32_t tile_bytes = IH * IW * kCV * 16;
@@ -1009,6 +1017,7 @@ struct StemArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const StemArgs a) {
+  pdl_prologue();
   __shared__ float s_w[27 * 32];
   __shared__ float s_stat[64];
   const int tid = threadIdx.x;
@@ -1086,6 +1095,7 @@ template <typename T>
 __global__ void __launch_bounds__(224) stem_wgrad_kernel(int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
                                                          const float* __restrict__ x, const T* __restrict__ dy,
                                                          float* __restrict__ dw, long long npix) {
+  pdl_prologue();
   constexpr int PIX = 64;
   __shared__ __align__(16) float s_x[PIX][28];
   __shared__ __align__(16) float s_dy[PIX][32];
@@ -1158,6 +1168,7 @@ __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(int B, int H, int W, i
                                                           const float* __restrict__ w, T* __restrict__ y,
                                                           const float* __restrict__ out_scale,
                                                           const float* __restrict__ out_shift, int out_act) {
+  pdl_prologue();
   extern __shared__ float s_w[];   // [9*Cin][Cout]
   const int tid = threadIdx.x;
   for (int i = tid; i < 9 * Cin * Cout; i += 256) s_w[i] = w[i];
@@ -1215,6 +1226,7 @@ __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(int B, int H, int W, i
 template <typename T>
 __global__ void __launch_bounds__(256) subsample_kernel(int B, int H, int W, int C, int step, int Ho, int Wo,
                                                         const T* __restrict__ x, T* __restrict__ y) {
+  pdl_prologue();
   const int cv = C / 8;
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
@@ -1233,6 +1245,7 @@ __global__ void __launch_bounds__(256) subsample_kernel(int B, int H, int W, int
 template <typename T>
 __global__ void __launch_bounds__(256) resize_feat_kernel(int B, int h, int w, int C, int H, int W, int ldo,
                                                           const T* __restrict__ x, T* __restrict__ y) {
+  pdl_prologue();
   const int cv = C / 8;
   const long long total = static_cast<long long>(B) * H * W * cv;
   const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
@@ -1279,6 +1292,7 @@ struct AsppArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256, 1) aspp_dw3_kernel(const AsppArgs a) {
+  pdl_prologue();
   constexpr int VP = 32 / (8 * sizeof(T));          // 8-channel vectors per pixel in the slice (2 for 16-bit, 1 for fp32)
   constexpr int CC = VP * 8;
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -1375,7 +1389,7 @@ static int launch_dw_gather_fwd(const dlb_dw_conv_params* p, cudaStream_t st) {
   a.cv = p->C / 8; a.ppb = 256 / a.cv; a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
   const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
   const size_t smem = p->stat_sum ? 2 * p->C * sizeof(float) : 0;
-  dw_fwd_kernel<T><<<grid, 256, smem, st>>>(a);
+  launch_k(dw_fwd_kernel<T>, grid, 256, smem, st, a);
   g_launches++;
   return check_launch("dw_fwd_kernel");
 }
@@ -1401,14 +1415,14 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
     int ngrp = (num_sms() * per_sm_h) / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;
-    dw_fwd_tma_h_kernel<T><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+    launch_k(dw_fwd_tma_h_kernel<T>, ngrp * a.chunks, 256, smem_t, st, tm, a);
     g_launches++;
     return check_launch("dw_fwd_tma_h_kernel");
   } else {
     const int per_sm = smem > 100 * 1024 ? 1 : 2;
     const int cap = num_sms() * per_sm;
     const int grid = a.num_tiles < cap ? a.num_tiles : cap;
-    dw_fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+    launch_k(dw_fwd_tiled_kernel<T>, grid, 256, smem, st, a);
     g_launches++;
     return check_launch("dw_fwd_tiled_kernel");
   }
@@ -1436,11 +1450,11 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
     int ngrp = num_sms() / a.chunks;
     if (ngrp < 1) ngrp = 1;
     if (ngrp > n_sp) ngrp = n_sp;
-    dw_wgrad_tma_h_kernel<T><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+    launch_k(dw_wgrad_tma_h_kernel<T>, ngrp * a.chunks, 256, smem_t, st, tm, a);
     g_launches++;
     return check_launch("dw_wgrad_tma_h_kernel");
   } else {
-    dw_wgrad_tiled_kernel<T><<<grid, 256, smem, st>>>(a);
+    launch_k(dw_wgrad_tiled_kernel<T>, grid, 256, smem, st, a);
     g_launches++;
     return check_launch("dw_wgrad_tiled_kernel");
   }
@@ -1503,8 +1517,8 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
       int ngrp = (num_sms() * 2) / a.chunks;
       if (ngrp < 1) ngrp = 1;
       if (ngrp > n_sp) ngrp = n_sp;
-      if (p->dtype == DLB_F16) dw_bwd_data_s2_tma_h_kernel<__half><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
-      else dw_bwd_data_s2_tma_h_kernel<__nv_bfloat16><<<ngrp * a.chunks, 256, smem_t, st>>>(tm, a);
+      if (p->dtype == DLB_F16) launch_k(dw_bwd_data_s2_tma_h_kernel<__half>, ngrp * a.chunks, 256, smem_t, st, tm, a);
+      else launch_k(dw_bwd_data_s2_tma_h_kernel<__nv_bfloat16>, ngrp * a.chunks, 256, smem_t, st, tm, a);
       g_launches++;
       rc = check_launch("dw_bwd_data_s2_tma_h_kernel");
       if (rc) return rc;
@@ -1517,9 +1531,9 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
       a.cv = p->C / 8; a.ppb = 256 / a.cv;
       a.npix = static_cast<long long>(p->B) * p->H * p->W;
       const int grid = pick_grid((a.npix + a.ppb - 1) / a.ppb, 16);
-      if (p->dtype == DLB_F16) dw_bwd_data_kernel<__half><<<grid, 256, 0, st>>>(a);
-      else if (p->dtype == DLB_BF16) dw_bwd_data_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
-      else dw_bwd_data_kernel<float><<<grid, 256, 0, st>>>(a);
+      if (p->dtype == DLB_F16) launch_k(dw_bwd_data_kernel<__half>, grid, 256, 0, st, a);
+      else if (p->dtype == DLB_BF16) launch_k(dw_bwd_data_kernel<__nv_bfloat16>, grid, 256, 0, st, a);
+      else launch_k(dw_bwd_data_kernel<float>, grid, 256, 0, st, a);
       g_launches++;
       int rc = check_launch("dw_bwd_data_kernel");
       if (rc) return rc;
@@ -1542,7 +1556,7 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
   do {                                                                                                         \
     if (smem > 48 * 1024)                                                                                      \
       DLB_CUDA(cudaFuncSetAttribute(dw_bwd_weight_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dw_bwd_weight_kernel<TT><<<grid, 256, smem, st>>>(g);                                                      \
+    launch_k(dw_bwd_weight_kernel<TT>, grid, 256, smem, st, g);                                                      \
   } while (0)
       if (p->dtype == DLB_F16) LG(__half);
       else if (p->dtype == DLB_BF16) LG(__nv_bfloat16);
@@ -1577,9 +1591,9 @@ extern "C" int dlb_stem_conv_fwd(const dlb_stem_conv_params* p, void* stream) {
   a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
   const int grid = pick_grid((a.npix + 127) / 128, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F16) stem_fwd_kernel<__half><<<grid, 128, 0, st>>>(a);
-  else if (p->dtype == DLB_BF16) stem_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
-  else stem_fwd_kernel<float><<<grid, 128, 0, st>>>(a);
+  if (p->dtype == DLB_F16) launch_k(stem_fwd_kernel<__half>, grid, 128, 0, st, a);
+  else if (p->dtype == DLB_BF16) launch_k(stem_fwd_kernel<__nv_bfloat16>, grid, 128, 0, st, a);
+  else launch_k(stem_fwd_kernel<float>, grid, 128, 0, st, a);
   g_launches++;
   return check_launch("stem_fwd_kernel");
 }
@@ -1596,11 +1610,11 @@ extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, con
   const int grid = pick_grid((npix + 63) / 64, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == DLB_F16)
-    stem_wgrad_kernel<__half><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
+    launch_k(stem_wgrad_kernel<__half>, grid, 224, 0, st, B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
   else if (dtype == DLB_BF16)
-    stem_wgrad_kernel<__nv_bfloat16><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const __nv_bfloat16*)dy, dw, npix);
+    launch_k(stem_wgrad_kernel<__nv_bfloat16>, grid, 224, 0, st, B, H, W, Ho, Wo, pad_t, pad_l, x, (const __nv_bfloat16*)dy, dw, npix);
   else
-    stem_wgrad_kernel<float><<<grid, 224, 0, st>>>(B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
+    launch_k(stem_wgrad_kernel<float>, grid, 224, 0, st, B, H, W, Ho, Wo, pad_t, pad_l, x, (const float*)dy, dw, npix);
   g_launches++;
   return check_launch("stem_wgrad_kernel");
 }
@@ -1618,7 +1632,7 @@ extern "C" int dlb_conv3x3_fwd(int B, int H, int W, int Cin, int Cout, int dtype
   do {                                                                                                           \
     if (smem > 48 * 1024)                                                                                        \
       DLB_CUDA(cudaFuncSetAttribute(conv3x3_fwd_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3x3_fwd_kernel<TT><<<grid, 256, smem, st>>>(B, H, W, Cin, Cout, (const TT*)x, w, (TT*)y, out_scale, out_shift, out_act); \
+    launch_k(conv3x3_fwd_kernel<TT>, grid, 256, smem, st, B, H, W, Cin, Cout, (const TT*)x, w, (TT*)y, out_scale, out_shift, out_act); \
   } while (0)
   if (dtype == DLB_F16) L3(__half);
   else if (dtype == DLB_BF16) L3(__nv_bfloat16);
@@ -1634,9 +1648,9 @@ extern "C" int dlb_subsample(int B, int H, int W, int C, int step, int dtype, co
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
   const int grid = pick_grid((total + 255) / 256, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DLB_F32) subsample_kernel<float><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const float*)x, (float*)y);
-  else if (dtype == DLB_F16) subsample_kernel<__half><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const __half*)x, (__half*)y);
-  else subsample_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(B, H, W, C, step, Ho, Wo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  if (dtype == DLB_F32) launch_k(subsample_kernel<float>, grid, 256, 0, st, B, H, W, C, step, Ho, Wo, (const float*)x, (float*)y);
+  else if (dtype == DLB_F16) launch_k(subsample_kernel<__half>, grid, 256, 0, st, B, H, W, C, step, Ho, Wo, (const __half*)x, (__half*)y);
+  else launch_k(subsample_kernel<__nv_bfloat16>, grid, 256, 0, st, B, H, W, C, step, Ho, Wo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
   g_launches++;
   return check_launch("subsample_kernel");
 }
@@ -1647,9 +1661,9 @@ extern "C" int dlb_resize_bilinear(int B, int h, int w, int C, int H, int W, int
   const long long total = static_cast<long long>(B) * H * W * (C / 8);
   const int grid = pick_grid((total + 255) / 256, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DLB_F32) resize_feat_kernel<float><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const float*)x, (float*)y);
-  else if (dtype == DLB_F16) resize_feat_kernel<__half><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const __half*)x, (__half*)y);
-  else resize_feat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(B, h, w, C, H, W, ldo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  if (dtype == DLB_F32) launch_k(resize_feat_kernel<float>, grid, 256, 0, st, B, h, w, C, H, W, ldo, (const float*)x, (float*)y);
+  else if (dtype == DLB_F16) launch_k(resize_feat_kernel<__half>, grid, 256, 0, st, B, h, w, C, H, W, ldo, (const __half*)x, (__half*)y);
+  else launch_k(resize_feat_kernel<__nv_bfloat16>, grid, 256, 0, st, B, h, w, C, H, W, ldo, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
   g_launches++;
   return check_launch("resize_feat_kernel");
 }
@@ -1671,7 +1685,7 @@ extern "C" int dlb_aspp_dw3_fwd(int B, int H, int W, int C, int dtype, const voi
 #define LA(TT)                                                                                              \
   do {                                                                                                      \
     DLB_CUDA(cudaFuncSetAttribute(aspp_dw3_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    aspp_dw3_kernel<TT><<<grid, 256, smem, st>>>(a);                                                        \
+    launch_k(aspp_dw3_kernel<TT>, grid, 256, smem, st, a);                                                        \
   } while (0)
   if (dtype == DLB_F16) LA(__half);
   else if (dtype == DLB_BF16) LA(__nv_bfloat16);

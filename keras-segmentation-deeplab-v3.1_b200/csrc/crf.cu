@@ -92,6 +92,7 @@ struct Lattice {
 template <int D>
 __global__ void __launch_bounds__(256) crf_embed_kernel(int H, int W, const uint8_t* __restrict__ im, float sx, float sy,
                                                         float sr, Lattice L) {
+  pdl_prologue();
   const int N = H * W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) crf_embed_kernel(int H, int W, const uint
 }
 
 __global__ void __launch_bounds__(256) crf_compact_kernel(Lattice L) {
+  pdl_prologue();
   const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= L.cap) return;
   const unsigned long long k = L.table[s];
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(256) crf_compact_kernel(Lattice L) {
 }
 
 __global__ void __launch_bounds__(256) crf_relabel_kernel(int n_inc, Lattice L) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_inc) return;
   const int idx = L.slot_idx[L.offset[e]];
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256) crf_relabel_kernel(int n_inc, Lattice L) 
 // exclusive scan of deg[0..n) in place, n read from the device (n = *count, padded grid); 3 phases
 constexpr int kScanBlock = 1024;
 __global__ void __launch_bounds__(kScanBlock) scan_phase1(int* data, const int* n_dev, int* block_sums) {
+  pdl_prologue();
   __shared__ int s[kScanBlock];
   const int n = *n_dev + 1;
   const int i = blockIdx.x * kScanBlock + threadIdx.x;
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_phase1(int* data, const int* 
   if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = s[threadIdx.x];
 }
 __global__ void __launch_bounds__(kScanBlock) scan_phase2(int* block_sums, const int* n_dev) {
+  pdl_prologue();
   __shared__ int s[kScanBlock];
   __shared__ int carry;
   const int nb = (*n_dev + 1 + kScanBlock - 1) / kScanBlock;
@@ -241,12 +246,14 @@ __global__ void __launch_bounds__(kScanBlock) scan_phase2(int* block_sums, const
   }
 }
 __global__ void __launch_bounds__(kScanBlock) scan_phase3(int* data, const int* n_dev, const int* block_sums) {
+  pdl_prologue();
   const int n = *n_dev + 1;
   const int i = blockIdx.x * kScanBlock + threadIdx.x;
   if (i < n) data[i] += block_sums[blockIdx.x];
 }
 
 __global__ void __launch_bounds__(256) crf_fill_kernel(int n_inc, int dp1, Lattice L) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_inc) return;
   const int idx = L.offset[e];
@@ -257,6 +264,7 @@ __global__ void __launch_bounds__(256) crf_fill_kernel(int n_inc, int dp1, Latti
 
 template <int D>
 __global__ void __launch_bounds__(256) crf_neighbors_kernel(int nv_max, Lattice L) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *L.count) return;
   int key[D];
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(256) crf_neighbors_kernel(int nv_max, Lattice 
 __global__ void __launch_bounds__(256) crf_splat_kernel(int vs4, const float4* __restrict__ src,
                                                         const float* __restrict__ pix_scale, float4* __restrict__ values,
                                                         Lattice L) {
+  pdl_prologue();
   const long long total = static_cast<long long>(*L.count) * vs4;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -299,6 +308,7 @@ __global__ void __launch_bounds__(256) crf_splat_kernel(int vs4, const float4* _
 
 __global__ void __launch_bounds__(256) crf_blur_kernel(int vs4, int axis, int nv_max, const float4* __restrict__ in,
                                                        float4* __restrict__ out, Lattice L) {
+  pdl_prologue();
   const long long total = static_cast<long long>(*L.count) * vs4;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -315,6 +325,7 @@ __global__ void __launch_bounds__(256) crf_blur_kernel(int vs4, int axis, int nv
 // slice of a 4-wide value (norm computation): out[p] = 1/sqrt(alpha * sum_j w_j values[off_j].x + 1e-20)
 __global__ void __launch_bounds__(256) crf_slice_norm_kernel(int N, int dp1, float alpha, const float4* __restrict__ values,
                                                              Lattice L) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   float acc = 0.f;
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(128) crf_slice_kernel(int N, int M, int dp1, f
                                                         const float* __restrict__ values, const float* __restrict__ base,
                                                         float* __restrict__ dst, int softmax_out, uint8_t* __restrict__ map_out,
                                                         Lattice L) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   float acc[VS];
@@ -377,6 +389,7 @@ __global__ void __launch_bounds__(128) crf_slice_kernel(int N, int M, int dp1, f
 // label-major [M, N] <-> pixel-major [N, VS] transposes through shared memory
 __global__ void __launch_bounds__(256) crf_unary_in_kernel(int N, int M, int VS, const float* __restrict__ unary,
                                                            float* __restrict__ negU, float* __restrict__ Q) {
+  pdl_prologue();
   // negU[p][k] = -unary[k][p] ; Q = softmax_k(negU)
   extern __shared__ float s[];    // [256][VS+1]
   const int p0 = blockIdx.x * 256;
@@ -402,6 +415,7 @@ __global__ void __launch_bounds__(256) crf_unary_in_kernel(int N, int M, int VS,
   }
 }
 __global__ void __launch_bounds__(256) crf_q_out_kernel(int N, int M, int VS, const float* __restrict__ Q, float* __restrict__ out) {
+  pdl_prologue();
   extern __shared__ float s[];    // [256][VS+1]
   const int p0 = blockIdx.x * 256;
   const int n_here = min(256, N - p0);
@@ -414,6 +428,7 @@ __global__ void __launch_bounds__(256) crf_q_out_kernel(int N, int M, int VS, co
     for (int k = 0; k < M; ++k) out[static_cast<size_t>(k) * N + p0 + threadIdx.x] = s[threadIdx.x * (VS + 1) + k];
 }
 __global__ void fill_ones4_kernel(int N, float4* v) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < N) v[p] = make_float4(1.f, 0.f, 0.f, 0.f);
 }
@@ -511,28 +526,28 @@ static int build_lattice(const dlb_crf_config* c, const LatticeOffsets& o, Latti
   DLB_CUDA(cudaMemsetAsync(L.overflow, 0, 256, st));
   DLB_CUDA(cudaMemsetAsync(L.deg, 0, sizeof(int) * (static_cast<size_t>(n_inc) + 2), st));
   DLB_CUDA(cudaMemsetAsync(L.cursor, 0, sizeof(int) * static_cast<size_t>(n_inc), st));
-  crf_embed_kernel<D><<<grid1d(N, 256), 256, 0, st>>>(c->H, c->W, image, sx, sx, sr, L);
-  crf_compact_kernel<<<grid1d(L.cap, 256), 256, 0, st>>>(L);
-  crf_relabel_kernel<<<grid1d(n_inc, 256), 256, 0, st>>>(n_inc, L);
+  launch_k(crf_embed_kernel<D>, grid1d(N, 256), 256, 0, st, c->H, c->W, image, sx, sx, sr, L);
+  launch_k(crf_compact_kernel, grid1d(L.cap, 256), 256, 0, st, L);
+  launch_k(crf_relabel_kernel, grid1d(n_inc, 256), 256, 0, st, n_inc, L);
   const int nblk = (n_inc + 1 + kScanBlock - 1) / kScanBlock;
-  scan_phase1<<<nblk, kScanBlock, 0, st>>>(L.deg, L.count, L.block_sums);
-  scan_phase2<<<1, kScanBlock, 0, st>>>(L.block_sums, L.count);
-  scan_phase3<<<nblk, kScanBlock, 0, st>>>(L.deg, L.count, L.block_sums);
-  crf_fill_kernel<<<grid1d(n_inc, 256), 256, 0, st>>>(n_inc, D + 1, L);
-  crf_neighbors_kernel<D><<<grid1d(o.nv_max, 256), 256, 0, st>>>(o.nv_max, L);
+  launch_k(scan_phase1, nblk, kScanBlock, 0, st, L.deg, L.count, L.block_sums);
+  launch_k(scan_phase2, 1, kScanBlock, 0, st, L.block_sums, L.count);
+  launch_k(scan_phase3, nblk, kScanBlock, 0, st, L.deg, L.count, L.block_sums);
+  launch_k(crf_fill_kernel, grid1d(n_inc, 256), 256, 0, st, n_inc, D + 1, L);
+  launch_k(crf_neighbors_kernel<D>, grid1d(o.nv_max, 256), 256, 0, st, o.nv_max, L);
   g_launches += 8;
   // norm = 1/sqrt(K 1 + 1e-20): filter a ones vector (value width 4, channel 0)
   float4* ones = reinterpret_cast<float4*>(scratch_n4);   // [N] float4 scratch (the mean-field tmp buffer)
-  fill_ones4_kernel<<<grid1d(N, 256), 256, 0, st>>>(N, ones);
+  launch_k(fill_ones4_kernel, grid1d(N, 256), 256, 0, st, N, ones);
   float4* v0 = reinterpret_cast<float4*>(val0);
   float4* v1 = reinterpret_cast<float4*>(val1);
-  crf_splat_kernel<<<grid_cap(static_cast<long long>(o.nv_max), 256), 256, 0, st>>>(1, ones, nullptr, v0, L);
+  launch_k(crf_splat_kernel, grid_cap(static_cast<long long>(o.nv_max), 256), 256, 0, st, 1, ones, nullptr, v0, L);
   for (int j = 0; j <= D; ++j) {
-    crf_blur_kernel<<<grid_cap(static_cast<long long>(o.nv_max), 256), 256, 0, st>>>(1, j, o.nv_max, v0, v1, L);
+    launch_k(crf_blur_kernel, grid_cap(static_cast<long long>(o.nv_max), 256), 256, 0, st, 1, j, o.nv_max, v0, v1, L);
     float4* t = v0; v0 = v1; v1 = t;
   }
   const float alpha = 1.0f / (1.0f + powf(2.0f, -static_cast<float>(D)));
-  crf_slice_norm_kernel<<<grid1d(N, 256), 256, 0, st>>>(N, D + 1, alpha, v0, L);
+  launch_k(crf_slice_norm_kernel, grid1d(N, 256), 256, 0, st, N, D + 1, alpha, v0, L);
   g_launches += 3 + D + 1;
   return check_launch("crf build");
 }
@@ -559,15 +574,15 @@ static int run_meanfield(const dlb_crf_config* c, const CrfPlan& P, uint8_t* bas
       float4* v0 = reinterpret_cast<float4*>(val0);
       float4* v1 = reinterpret_cast<float4*>(val1);
       const long long work = static_cast<long long>(o.nv_max) * vs4;
-      crf_splat_kernel<<<grid_cap(work, 256), 256, 0, st>>>(vs4, reinterpret_cast<const float4*>(Q), L.norm, v0, L);
+      launch_k(crf_splat_kernel, grid_cap(work, 256), 256, 0, st, vs4, reinterpret_cast<const float4*>(Q), L.norm, v0, L);
       for (int j = 0; j <= D; ++j) {
-        crf_blur_kernel<<<grid_cap(work, 256), 256, 0, st>>>(vs4, j, o.nv_max, v0, v1, L);
+        launch_k(crf_blur_kernel, grid_cap(work, 256), 256, 0, st, vs4, j, o.nv_max, v0, v1, L);
         float4* t = v0; v0 = v1; v1 = t;
       }
       const bool last = (!is_g) || !use_b;
       const float alpha = 1.0f / (1.0f + powf(2.0f, -static_cast<float>(D)));
       const bool want_map = last && map_out && it == c->iters - 1;
-      crf_slice_kernel<VS><<<grid1d(N, 128), 128, 0, st>>>(N, M, D + 1, alpha, is_g ? c->compat_gauss : c->compat_bilat,
+      launch_k(crf_slice_kernel<VS>, grid1d(N, 128), 128, 0, st, N, M, D + 1, alpha, is_g ? c->compat_gauss : c->compat_bilat,
                                                            reinterpret_cast<const float*>(v0), basep, last ? Q : tmp,
                                                            last ? 1 : 0, want_map ? map_out : nullptr, L);
       basep = tmp;
@@ -612,7 +627,7 @@ extern "C" int dlb_crf_inference(const dlb_crf_config* cfg, const float* unary, 
   float* negU = reinterpret_cast<float*>(base + P.negU);
   float* Q = reinterpret_cast<float*>(base + P.Q);
   const size_t smem = sizeof(float) * 256 * (P.VS + 1);
-  crf_unary_in_kernel<<<(N + 255) / 256, 256, smem, st>>>(N, cfg->M, P.VS, unary, negU, Q);
+  launch_k(crf_unary_in_kernel, (N + 255) / 256, 256, smem, st, N, cfg->M, P.VS, unary, negU, Q);
   g_launches++;
   switch (P.VS) {
 #define VSCASE(V) case V: rc = run_meanfield<V>(cfg, P, base, Lg, Lb, map_out, st); break;
@@ -621,7 +636,7 @@ extern "C" int dlb_crf_inference(const dlb_crf_config* cfg, const float* unary, 
     default: set_last_error("crf_inference: bad value stride"); return DLB_ERR_INVALID;
   }
   if (rc) return rc;
-  crf_q_out_kernel<<<(N + 255) / 256, 256, smem, st>>>(N, cfg->M, P.VS, Q, Q_out);
+  launch_k(crf_q_out_kernel, (N + 255) / 256, 256, smem, st, N, cfg->M, P.VS, Q, Q_out);
   g_launches++;
   return check_launch("crf_q_out_kernel");
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(128) resize_softmax_fwd_kernel(int B, int h, i
                                                                  const float* __restrict__ logits,
                                                                  float* __restrict__ probs,
                                                                  uint8_t* __restrict__ argmax_out) {
+  pdl_prologue();
   __shared__ float s_out[128 * C];
   const long long npix = static_cast<long long>(B) * H * W;
   const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
@@ -91,6 +92,7 @@ struct CeArgs {
 
 template <int C, int S>
 __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs a) {
+  pdl_prologue();
   constexpr int TILE = 64 / S >= 8 ? 8 : 64 / S;      // low-res cells per tile side (8 for S=8, 8 for S=4 -> 32px)
   constexpr int TP = TILE + 1;
   constexpr int PX = TILE * S;                        // output pixels per tile side (64 or 32)
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
 // S == 1 (Subpixel head: logits already at full resolution)
 template <int C>
 __global__ void __launch_bounds__(256) softmax_ce_full_kernel(const CeArgs a) {
+  pdl_prologue();
   __shared__ float s_loss[8];
   const long long npix = static_cast<long long>(a.B) * a.H * a.W;
   const float gs = *a.grad_scale;
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(256) softmax_ce_full_kernel(const CeArgs a) {
 }
 
 __global__ void count_nonzero_kernel(long long n, const float* sw, double* count) {
+  pdl_prologue();
   __shared__ unsigned int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -269,6 +273,7 @@ __global__ void count_nonzero_kernel(long long n, const float* sw, double* count
   if (threadIdx.x == 0) atomicAdd(count, static_cast<double>(s_cnt));
 }
 __global__ void grad_scale_kernel(long long n, int has_sw, double* count, float* grad_scale) {
+  pdl_prologue();
   if (!has_sw) *count = static_cast<double>(n);
   const double c = *count;
   *grad_scale = c > 0.0 ? static_cast<float>(1.0 / c) : 0.f;
@@ -279,6 +284,7 @@ __global__ void grad_scale_kernel(long long n, int has_sw, double* count, float*
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void phase_shift_kernel(long long total, int h, int w, int Cs, int r, const T* in, T* out, int inverse) {
+  pdl_prologue();
   for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < total;
        o += static_cast<long long>(gridDim.x) * blockDim.x) {
     // o indexes the high-res tensor [n, h*r, w*r, Cs]
@@ -296,6 +302,7 @@ __global__ void phase_shift_kernel(long long total, int h, int w, int Cs, int r,
 
 __global__ void __launch_bounds__(256) confusion_kernel(long long npix, int C, const float* labels,
                                                         const uint8_t* argmax, unsigned long long* conf) {
+  pdl_prologue();
   extern __shared__ unsigned int s_conf[];   // [(C+1)*C]
   const int b = blockIdx.y;
   const int nb = (C + 1) * C;
@@ -326,7 +333,7 @@ extern "C" int dlb_resize_softmax_fwd(int B, int h, int w, int C, int ldl, int H
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (C) {
-#define CASE(CC) case CC: resize_softmax_fwd_kernel<CC><<<grid, 128, 0, st>>>(B, h, w, ldl, H, W, logits, probs, argmax); break;
+#define CASE(CC) case CC: launch_k(resize_softmax_fwd_kernel<CC>, grid, 128, 0, st, B, h, w, ldl, H, W, logits, probs, argmax); break;
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
     CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
 #undef CASE
@@ -344,13 +351,13 @@ static int launch_ce(const CeArgs& a, cudaStream_t st) {
     const long long npix = static_cast<long long>(a.B) * a.H * a.W;
     long long blocks = (npix + 255) / 256;
     const long long cap = static_cast<long long>(num_sms()) * 8;
-    softmax_ce_full_kernel<C><<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(a);
+    launch_k(softmax_ce_full_kernel<C>, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, a);
   } else if (a.S == 8) {
     const int tiles = ((a.w + 7) / 8) * ((a.h + 7) / 8);
-    resize_softmax_ce_kernel<C, 8><<<a.B * tiles, 256, 0, st>>>(a);
+    launch_k(resize_softmax_ce_kernel<C, 8>, a.B * tiles, 256, 0, st, a);
   } else if (a.S == 4) {
     const int tiles = ((a.w + 7) / 8) * ((a.h + 7) / 8);
-    resize_softmax_ce_kernel<C, 4><<<a.B * tiles, 256, 0, st>>>(a);
+    launch_k(resize_softmax_ce_kernel<C, 4>, a.B * tiles, 256, 0, st, a);
   } else {
     set_last_error("resize_softmax_ce: scale %d unsupported (1, 4, 8)", a.S);
     return DLB_ERR_UNSUPPORTED;
@@ -389,10 +396,10 @@ extern "C" int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_s
   if (sample_w) {
     long long blocks = (n + 255) / 256;
     const long long cap = static_cast<long long>(num_sms()) * 8;
-    count_nonzero_kernel<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(n, sample_w, wcount);
+    launch_k(count_nonzero_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, n, sample_w, wcount);
     g_launches++;
   }
-  grad_scale_kernel<<<1, 1, 0, st>>>(n, sample_w != nullptr, wcount, grad_scale_dev);
+  launch_k(grad_scale_kernel, 1, 1, 0, st, n, sample_w != nullptr, wcount, grad_scale_dev);
   g_launches++;
   return check_launch("grad_scale_kernel");
 }
@@ -405,8 +412,8 @@ extern "C" int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, co
   const long long cap = static_cast<long long>(num_sms()) * 16;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DLB_F32) phase_shift_kernel<float><<<grid, 256, 0, st>>>(total, h, w, Cs, r, (const float*)in, (float*)out, inverse);
-  else phase_shift_kernel<uint16_t><<<grid, 256, 0, st>>>(total, h, w, Cs, r, (const uint16_t*)in, (uint16_t*)out, inverse);
+  if (dtype == DLB_F32) launch_k(phase_shift_kernel<float>, grid, 256, 0, st, total, h, w, Cs, r, (const float*)in, (float*)out, inverse);
+  else launch_k(phase_shift_kernel<uint16_t>, grid, 256, 0, st, total, h, w, Cs, r, (const uint16_t*)in, (uint16_t*)out, inverse);
   g_launches++;
   return check_launch("phase_shift_kernel");
 }
@@ -417,7 +424,7 @@ extern "C" int dlb_confusion(int B, int64_t npix, int C, const float* labels, co
   long long blocks = (npix + 255) / 256;
   if (blocks > 64) blocks = 64;
   dim3 grid(static_cast<unsigned>(blocks), B);
-  confusion_kernel<<<grid, 256, (C + 1) * C * sizeof(unsigned int), static_cast<cudaStream_t>(stream)>>>(
+  launch_k(confusion_kernel, grid, 256, (C + 1) * C * sizeof(unsigned int), static_cast<cudaStream_t>(stream), 
       npix, C, labels, argmax, conf);
   g_launches++;
   return check_launch("confusion_kernel");

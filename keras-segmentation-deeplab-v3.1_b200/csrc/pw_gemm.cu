@@ -152,6 +152,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  pdl_wait();     // everything above is independent of the preceding kernel's output
   for (int i = threadIdx.x; i < npad; i += kThreads) {
     s_scale[i] = (g.col_scale && i < g.N) ? g.col_scale[i] : 1.f;
     s_shift[i] = (g.col_shift && i < g.N) ? g.col_shift[i] : 0.f;
@@ -503,6 +504,7 @@ struct SimtArgs {
 };
 
 __global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const SimtArgs g) {
+  pdl_prologue();
   constexpr int TM = 64, TN = 64, TK = 16;
   __shared__ float sA[TK][TM + 4];
   __shared__ float sB[TK][TN + 4];
@@ -742,7 +744,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   do {                                                                                                           \
     DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem_bytes));                                                             \
-    pw_gemm_tc_kernel<OT, SETS, LEAN><<<grid, 64 + 128 * SETS, smem_bytes, st>>>(ta, tb, g);                     \
+    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, g);                     \
   } while (0)
 #define LAUNCH2(OT, SETS) do { if (lean) LAUNCH(OT, SETS, true); else LAUNCH(OT, SETS, false); } while (0)
   if (p->out_dtype == DLB_F16) { if (sets == 4) LAUNCH2(__half, 4); else LAUNCH2(__half, 2); }
@@ -768,7 +770,7 @@ static int launch_simt(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
   const int ncols = p->n_store > p->N ? p->n_store : p->N;
   dim3 grid((p->M + 63) / 64, (ncols + 63) / 64);
-  pw_gemm_simt_kernel<<<grid, 256, 0, st>>>(g);
+  launch_k(pw_gemm_simt_kernel, grid, 256, 0, st, g);
   g_launches++;
   return check_launch("pw_gemm_simt_kernel");
 }

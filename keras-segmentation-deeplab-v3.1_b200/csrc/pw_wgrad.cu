@@ -61,6 +61,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // barrier init / TMEM allocation above overlap the preceding kernel's tail
 
   // work item of this CTA
   int wi = blockIdx.x;
@@ -153,6 +154,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 __global__ void __launch_bounds__(256) pw_wgrad_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                             const float* __restrict__ dY, int ldy, float* __restrict__ dW,
                                                             int ldw, int rows_per_split) {
+  pdl_prologue();
   constexpr int T = 64, TR = 16;
   __shared__ float sA[TR][T + 4];
   __shared__ float sB[TR][T + 4];
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_simt_kernel(int M, int N, int K,
 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const T* __restrict__ dY, int ldy, float* __restrict__ out) {
+  pdl_prologue();
   // one block per 32 columns-slab; threads stride rows
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
@@ -232,9 +235,9 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   if (p->dbias) {
     DLB_CUDA(cudaMemsetAsync(p->dbias, 0, sizeof(float) * p->N, st));
     dim3 grid((p->N + 31) / 32, 128);
-    if (p->dtype == DLB_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>(p->M, p->N, (const __half*)p->dY, p->ldy, p->dbias);
-    else if (p->dtype == DLB_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p->M, p->N, (const __nv_bfloat16*)p->dY, p->ldy, p->dbias);
-    else colsum_kernel<float><<<grid, 256, 0, st>>>(p->M, p->N, (const float*)p->dY, p->ldy, p->dbias);
+    if (p->dtype == DLB_F16) launch_k(colsum_kernel<__half>, grid, 256, 0, st, p->M, p->N, (const __half*)p->dY, p->ldy, p->dbias);
+    else if (p->dtype == DLB_BF16) launch_k(colsum_kernel<__nv_bfloat16>, grid, 256, 0, st, p->M, p->N, (const __nv_bfloat16*)p->dY, p->ldy, p->dbias);
+    else launch_k(colsum_kernel<float>, grid, 256, 0, st, p->M, p->N, (const float*)p->dY, p->ldy, p->dbias);
     g_launches++;
   }
   if (p->dtype == DLB_F32) {
@@ -245,7 +248,7 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
     int rps = ((p->M + splits - 1) / splits + 15) / 16 * 16;
     splits = (p->M + rps - 1) / rps;
     dim3 grid(kt, nt, splits);
-    pw_wgrad_simt_kernel<<<grid, 256, 0, st>>>(p->M, p->N, p->K, (const float*)p->A, p->lda, (const float*)p->dY,
+    launch_k(pw_wgrad_simt_kernel, grid, 256, 0, st, p->M, p->N, p->K, (const float*)p->A, p->lda, (const float*)p->dY,
                                                p->ldy, p->dW, p->ldw, rps);
     g_launches++;
     return check_launch("pw_wgrad_simt_kernel");
@@ -285,7 +288,7 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   if (rc) return rc;
   const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + (2 * kWgMaxStages + 1) * 8 + 16;
   DLB_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  pw_wgrad_tc_kernel<<<tiles * splits, kWgThreads, smem_bytes, st>>>(ta, ty, g);
+  launch_k(pw_wgrad_tc_kernel, tiles * splits, kWgThreads, smem_bytes, st, ta, ty, g);
   g_launches++;
   return check_launch("pw_wgrad_tc_kernel");
 }

@@ -117,6 +117,7 @@ __device__ __forceinline__ ItemGeom decode_item(const FusedArgs& a, int item) {
 template <typename T>
 __global__ void __launch_bounds__(kFThreads, 1)
 sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ WMaps wmaps, const FusedArgs a) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t s0 = smem_u32(smem);
@@ -400,6 +401,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 // packed per-(branch, 64-channel chunk) depthwise parameters, all 16-bit: [9 taps][64 ch] | scale[64] | shift[64]
 template <typename T>
 __global__ void aspp_pack_kernel(int C, int nk, const float* w, const float* scale, const float* shift, uint8_t* pack) {
+  pdl_prologue();
   const int kc = blockIdx.x, ch = threadIdx.x;     // 64 threads
   const int c = kc * 64 + ch;
   uint8_t* dst = pack + static_cast<size_t>(kc) * kFPackBytes;
@@ -428,8 +430,8 @@ extern "C" int dlb_sepconv_pack_dw(int C, int dtype, int n_branches, const float
     uint8_t* dst = static_cast<uint8_t*>(pack) + static_cast<size_t>(i) * nk * kFPackBytes;
     const float* sc = scale ? scale[i] : nullptr;
     const float* sh = shift ? shift[i] : nullptr;
-    if (dtype == DLB_F16) aspp_pack_kernel<__half><<<nk, 64, 0, st>>>(C, nk, w_dw[i], sc, sh, dst);
-    else aspp_pack_kernel<__nv_bfloat16><<<nk, 64, 0, st>>>(C, nk, w_dw[i], sc, sh, dst);
+    if (dtype == DLB_F16) launch_k(aspp_pack_kernel<__half>, nk, 64, 0, st, C, nk, w_dw[i], sc, sh, dst);
+    else launch_k(aspp_pack_kernel<__nv_bfloat16>, nk, 64, 0, st, C, nk, w_dw[i], sc, sh, dst);
     g_launches++;
   }
   return check_launch("aspp_pack_kernel");
@@ -492,10 +494,10 @@ extern "C" int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* st
   DLB_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), st));
   if (p->dtype == DLB_F16) {
     DLB_CUDA(cudaFuncSetAttribute(sepconv_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-    sepconv_fused_kernel<__half><<<grid, kFThreads, kFSmem, st>>>(tx, wm, a);
+    launch_k(sepconv_fused_kernel<__half>, grid, kFThreads, kFSmem, st, tx, wm, a);
   } else {
     DLB_CUDA(cudaFuncSetAttribute(sepconv_fused_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-    sepconv_fused_kernel<__nv_bfloat16><<<grid, kFThreads, kFSmem, st>>>(tx, wm, a);
+    launch_k(sepconv_fused_kernel<__nv_bfloat16>, grid, kFThreads, kFSmem, st, tx, wm, a);
   }
   g_launches++;
   return check_launch("sepconv_fused_kernel");
