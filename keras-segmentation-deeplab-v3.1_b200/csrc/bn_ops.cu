@@ -488,7 +488,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
 
 template <typename T, int kMode>
 __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArgs a) {
-  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   using P = typename BP2<T>::t;
   const int tid = threadIdx.x;
@@ -500,6 +499,7 @@ __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArg
     for (int i = 0; i < a.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSConsumers / 32); }
     mbar_fence_init();
   }
+  pdl_wait();     // barrier init above overlaps the preceding kernel's tail
   if (kMode == 2 && blockIdx.x == 0) {
     for (int c = tid; c < a.C; c += kSThreads) {
       if (a.dbeta) a.dbeta[c] = static_cast<float>(a.red[c]);

@@ -627,7 +627,6 @@ __device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
-  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
@@ -684,6 +683,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
     tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
+  pdl_wait();     // index math and barrier init above overlap the preceding kernel's tail; no global access before this
   if (grp >= ngrp) return;
   if (tid == 0 && grp < n_sp) issue(grp, 0);
   for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
@@ -762,7 +762,6 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
 
 template <typename T>
 __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwTileArgs a) {
-  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
@@ -823,6 +822,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
     tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
+  pdl_wait();     // index math and barrier init above overlap the preceding kernel's tail; no global access before this
   if (grp >= ngrp) return;
   if (tid == 0 && grp < n_sp) issue(grp, 0);
   for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
@@ -900,7 +900,6 @@ struct DwS2Args {
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __grid_constant__ CUtensorMap tmap, const DwS2Args a) {
-  pdl_prologue();
   extern __shared__ __align__(128) uint8_t s_raw[];
   constexpr int IH = kTH + 1, IW = kTW + 1;
   constexpr uint32_t tile_bytes = IH * IW * kCV * 16;
@@ -937,6 +936,7 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_data_s2_tma_h_kernel(const __gr
     mbar_expect_tx(&full[slot], tile_bytes);
     tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, n0 - 1, m0 - 1, b);
   };
+  pdl_wait();     // index math and barrier init above overlap the preceding kernel's tail; no global access before this
   if (grp >= ngrp) return;
   if (tid == 0 && grp < n_sp) issue(grp, 0);
   T* dx = reinterpret_cast<T*>(a.dx);
