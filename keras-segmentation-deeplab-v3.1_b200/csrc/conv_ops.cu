@@ -1577,6 +1577,21 @@ extern "C" int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream) {
   return DLB_OK;
 }
 
+namespace dlb {
+// stem_mma.cu: warp-MMA stem kernels for 16-bit activations
+struct StemMmaArgs {
+  int B, H, W, Ho, Wo, pad_t, pad_l;
+  const float* x; void* y; const float* w;
+  const float* out_scale; const float* out_shift; int out_act;
+  double* stat_sum; double* stat_sqs;
+  const void* dy; float* dw;
+  long long npix;
+  int n_tiles;
+};
+int stem_fwd_mma(int dtype, const StemMmaArgs& a, cudaStream_t st);
+int stem_wgrad_mma(int dtype, const StemMmaArgs& a, cudaStream_t st);
+}  // namespace dlb
+
 extern "C" int dlb_stem_conv_fwd(const dlb_stem_conv_params* p, void* stream) {
   DLB_REQUIRE(p && p->x && p->y && p->w, "stem_conv_fwd: null pointer");
   DLB_REQUIRE(p->Cout == 32, "stem_conv_fwd: Cout must be 32 (got %d)", p->Cout);
@@ -1591,6 +1606,13 @@ extern "C" int dlb_stem_conv_fwd(const dlb_stem_conv_params* p, void* stream) {
   a.npix = static_cast<long long>(p->B) * p->Ho * p->Wo;
   const int grid = pick_grid((a.npix + 127) / 128, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dtype != DLB_F32 && a.npix < (1ll << 31)) {
+    StemMmaArgs m{};
+    m.B = a.B; m.H = a.H; m.W = a.W; m.Ho = a.Ho; m.Wo = a.Wo; m.pad_t = a.pad_t; m.pad_l = a.pad_l;
+    m.x = a.x; m.y = a.y; m.w = a.w; m.out_scale = a.out_scale; m.out_shift = a.out_shift; m.out_act = a.out_act;
+    m.stat_sum = a.stat_sum; m.stat_sqs = a.stat_sqs; m.npix = a.npix;
+    return stem_fwd_mma(p->dtype, m, st);
+  }
   if (p->dtype == DLB_F16) launch_k(stem_fwd_kernel<__half>, grid, 128, 0, st, a);
   else if (p->dtype == DLB_BF16) launch_k(stem_fwd_kernel<__nv_bfloat16>, grid, 128, 0, st, a);
   else launch_k(stem_fwd_kernel<float>, grid, 128, 0, st, a);
@@ -1609,6 +1631,12 @@ extern "C" int dlb_stem_conv_wgrad(int B, int H, int W, int Cout, int dtype, con
   DLB_REQUIRE(Ho * Wo >= 64, "stem_conv_wgrad: output map %dx%d smaller than one 64-pixel slab", Ho, Wo);
   const int grid = pick_grid((npix + 63) / 64, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype != DLB_F32 && npix < (1ll << 31)) {
+    StemMmaArgs m{};
+    m.B = B; m.H = H; m.W = W; m.Ho = Ho; m.Wo = Wo; m.pad_t = pad_t; m.pad_l = pad_l;
+    m.x = x; m.dy = dy; m.dw = dw; m.npix = npix;
+    return stem_wgrad_mma(dtype, m, st);
+  }
   if (dtype == DLB_F16)
     launch_k(stem_wgrad_kernel<__half>, grid, 224, 0, st, B, H, W, Ho, Wo, pad_t, pad_l, x, (const __half*)dy, dw, npix);
   else if (dtype == DLB_BF16)
