@@ -263,6 +263,34 @@ __host__ __device__ inline uint32_t make_idesc(int fmt, int m, int n, int a_majo
   return d;
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FFMA2): one instruction per two columns in the statistics walk
+__device__ __forceinline__ void f32x2_acc(unsigned long long& s, unsigned long long& q, float a, float b) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(v));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q) : "l"(v));
+}
+__device__ __forceinline__ float2 f32x2_unpack(unsigned long long v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_pack(float a, float b) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  return v;
+}
+// s += v ; q += v * v   on a packed pair
+__device__ __forceinline__ void f32x2_acc_v(unsigned long long& s, unsigned long long& q, unsigned long long v) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(v));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q) : "l"(v));
+}
+
 // Sum 16 per-thread values (one per column) over the 32 lanes of a warp with 15+1 shuffles instead of 80:
 // recursive halving -- after the call, lane l holds the full 32-lane sum of column (l >> 1) & 15 ... see below.
 // Returns the total for column `col_of_lane(lane)`; both lanes 2c and 2c+1 return the same value.

@@ -250,6 +250,7 @@ struct DwTileArgs {
   // TMA kernels only: dilation-phase decomposition (sub = d: a tile is one phase of the d x d sub-sampled grids, read
   // with TMA element strides, so the dilated conv is an undilated one in shared memory), smem dilation, NaN padding
   int sub, sdil, nan_fill;
+  int n_buf;       // TMA ring depth of the *_tma_h kernels (2..4 tiles in flight per CTA)
 };
 
 template <typename T>
@@ -563,16 +564,23 @@ template <typename T> __device__ __forceinline__ void sts_h8(uint32_t saddr, con
 }
 
 template <typename T>
-__device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_t s_in, int oy0, int ox0, int c0, bool cv_ok) {
+__device__ __forceinline__ void dw_transform_tile_h(const DwTileArgs& a, uint32_t s_in, int oy0, int ox0, int c0, bool cv_ok,
+                                                    const uint4* s_aff = nullptr) {
   // in place: a = act(x * scale + shift) inside the image, exact zeros in the padding
   const int tid = threadIdx.x, v = tid & 7;
   const int cc = c0 + v * 8;
   if (!cv_ok) return;
   typename P2<T>::t sc2[4], sh2[4];
+  if (s_aff) {       // packed (scale, shift) pairs of the CTA's 64 channels, staged once per CTA
+    const uint4 us = s_aff[v], uh = s_aff[8 + v];
+    *reinterpret_cast<uint4*>(sc2) = us;
+    *reinterpret_cast<uint4*>(sh2) = uh;
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    sc2[i] = P2<T>::pack(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
-    sh2[i] = P2<T>::pack(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {
+      sc2[i] = P2<T>::pack(a.in_scale[cc + 2 * i], a.in_scale[cc + 2 * i + 1]);
+      sh2[i] = P2<T>::pack(a.in_shift[cc + 2 * i], a.in_shift[cc + 2 * i + 1]);
+    }
   }
   const typename P2<T>::t zero2 = P2<T>::bcast(0.f), six2 = P2<T>::bcast(6.f);
   const int npos = a.ih * a.iw;
@@ -631,19 +639,23 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
   const uint32_t s_base = smem_u32(s_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
-  float* s_stats = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [2][64]
+  const int nb = a.n_buf;                                                     // ring of nb tiles (up to 4)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + nb * buf_stride);
+  float* s_stats = reinterpret_cast<float*>(s_raw + nb * buf_stride + 32);   // [2][64]
+  uint4* s_aff = reinterpret_cast<uint4*>(s_raw + nb * buf_stride + 32 + 512);          // packed prologue scale / shift [2][8]
+  int* s_info = reinterpret_cast<int*>(s_raw + nb * buf_stride + 32 + 512 + 256);       // per ring slot: b, oy0, ox0
   const int tid = threadIdx.x, v = tid & 7;
   const bool stats = a.stat_sum != nullptr;
   const bool pro = a.in_scale != nullptr;
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    for (int i = 0; i < nb; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   typename P2<T>::t w2[9][4];
   float ssum[8], ssqs[8];
+  unsigned long long ssum2[4] = {0ull, 0ull, 0ull, 0ull}, ssqs2[4] = {0ull, 0ull, 0ull, 0ull};   // packed running statistics
   int off[9];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
@@ -653,6 +665,11 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   T* y = reinterpret_cast<T*>(a.y);
 
   auto flush_stats = [&](int chunk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 s = f32x2_unpack(ssum2[i]), q = f32x2_unpack(ssqs2[i]);
+      ssum[2 * i] = s.x; ssum[2 * i + 1] = s.y; ssqs[2 * i] = q.x; ssqs[2 * i + 1] = q.y;
+    }
     __syncthreads();
     if (tid < 128) s_stats[tid] = 0.f;
     __syncthreads();
@@ -677,26 +694,32 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
   const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
   const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
   auto issue = [&](int sp, int slot) {
+    // the tile coordinates are decoded ONCE, by the issuing thread (5 integer divisions: 14 % of the kernel's
+    // instructions when all 256 threads did it), and travel with the slot; the mbarrier orders them for the readers
     int b, oy0, ox0;
     dw_decode_tile(a, sp, b, oy0, ox0);
+    s_info[slot * 4 + 0] = b; s_info[slot * 4 + 1] = oy0; s_info[slot * 4 + 2] = ox0;
     mbar_expect_tx(&full[slot], tile_bytes);
     tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
   pdl_wait();     // index math and barrier init above overlap the preceding kernel's tail; no global access before this
   if (grp >= ngrp) return;
-  if (tid == 0 && grp < n_sp) issue(grp, 0);
-  for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
-    const int slot = it & 1;
-    int b, oy0, ox0;
-    dw_decode_tile(a, sp, b, oy0, ox0);
+  // nb - 1 tiles are requested ahead: one 23 KB tile in flight per CTA left the kernel latency bound (Little: 2 CTAs x
+  // 23 KB x 148 SMs / ~2 us = 3.4 TB/s of input at best)
+  if (tid == 0) {
+    for (int i = 0; i < nb - 1; ++i)
+      if (grp + i * ngrp < n_sp) issue(grp + i * ngrp, i);
+  }
+  int slot = 0; uint32_t par = 0;
+  for (int sp = grp; sp < n_sp; sp += ngrp) {
     const int c0 = chunk * 64, cc = c0 + v * 8;
     const bool cv_ok = cc < a.C;
     if (chunk != cur_chunk) {
       if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
       cur_chunk = chunk;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssqs[i] = 0.f; }
+      for (int i = 0; i < 4; ++i) { ssum2[i] = 0ull; ssqs2[i] = 0ull; }
       if (cv_ok) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
@@ -705,16 +728,80 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
           for (int i = 0; i < 4; ++i) w2[t][i] = P2<T>::pack(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
         }
       }
-    }
-    // prefetch the next tile into the other buffer (free since the __syncthreads that ended the previous iteration)
-    if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
-    mbar_wait(&full[slot], (it >> 1) & 1);
-    const uint32_t s_in = s_base + slot * buf_stride;
-    if (pro) {
-      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok);
+      if (pro && tid < 64) {
+        typename P2<T>::t* af = reinterpret_cast<typename P2<T>::t*>(s_aff);
+        const int ch = c0 + 2 * (tid & 31);
+        const float* src = tid < 32 ? a.in_scale : a.in_shift;
+        af[tid] = ch + 1 < a.C ? P2<T>::pack(src[ch], src[ch + 1]) : P2<T>::bcast(0.f);
+      }
       __syncthreads();
     }
-    if (cv_ok) {
+    // prefetch the next tile into the other buffer (free since the __syncthreads that ended the previous iteration)
+    if (tid == 0 && sp + (nb - 1) * ngrp < n_sp) issue(sp + (nb - 1) * ngrp, slot == 0 ? nb - 1 : slot - 1);
+    mbar_wait(&full[slot], par);
+    const int b = s_info[slot * 4 + 0], oy0 = s_info[slot * 4 + 1], ox0 = s_info[slot * 4 + 2];
+    const uint32_t s_in = s_base + slot * buf_stride;
+    if (pro) {
+      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok, s_aff);
+      __syncthreads();
+    }
+    if (cv_ok && a.stride == 1 && a.sdil == 1) {
+      // Column walk: a thread owns 4 consecutive output rows of one column and rolls over the 6 input rows they need,
+      // so every input vector is read from shared memory 3 times (once per horizontal neighbour) instead of 9 -- the
+      // tile loads, not the math, were at 62 % of the shared-memory bandwidth (ncu l1tex throughput).
+      const int slot = tid >> 3;
+      const int ox = slot & (kTW - 1), oyb = (slot / kTW) * 4;
+      const int gx = ox0 + ox * a.sub;
+      if (gx < a.Wo && oy0 + oyb * a.sub < a.Ho) {
+        unsigned long long acc2[4][4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc2[o][i] = 0ull;
+        const uint32_t base = s_in + static_cast<uint32_t>((oyb * a.iw + ox) * kCV + v) * 16u;
+        const uint32_t row_b = static_cast<uint32_t>(a.iw) * kCV * 16u;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const V8<T> x0 = lds_h8<T>(base + r * row_b), x1 = lds_h8<T>(base + r * row_b + kCV * 16u),
+                      x2 = lds_h8<T>(base + r * row_b + 2u * kCV * 16u);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int ky = r - o;
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const typename P2<T>::t racc =
+                  __hfma2(x2.h[i], w2[ky * 3 + 2][i], __hfma2(x1.h[i], w2[ky * 3 + 1][i], __hmul2(x0.h[i], w2[ky * 3][i])));
+              const float2 f = P2<T>::unpack(racc);
+              acc2[o][i] = f32x2_add(acc2[o][i], f32x2_pack(f.x, f.y));
+            }
+          }
+        }
+        T* yp = y + ((static_cast<size_t>(b) * a.Ho + oy0 + oyb * a.sub) * a.Wo + gx) * a.C + cc;
+        const size_t ystep = static_cast<size_t>(a.sub) * a.Wo * a.C;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int gy = oy0 + (oyb + o) * a.sub;
+          if (gy >= a.Ho) break;
+          if (a.out_scale) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = f32x2_unpack(acc2[o][i]);
+              acc2[o][i] = f32x2_pack(apply_act(fmaf(f.x, a.out_scale[cc + 2 * i], a.out_shift[cc + 2 * i]), a.out_act),
+                                      apply_act(fmaf(f.y, a.out_scale[cc + 2 * i + 1], a.out_shift[cc + 2 * i + 1]), a.out_act));
+            }
+          }
+          if (stats) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f32x2_acc_v(ssum2[i], ssqs2[i], acc2[o][i]);
+          }
+          V8<T> ov;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = f32x2_unpack(acc2[o][i]); ov.h[i] = P2<T>::pack(f.x, f.y); }
+          stg_h8(yp + o * ystep, ov);
+        }
+      }
+    } else if (cv_ok) {
 #pragma unroll 2
       for (int j = 0; j < (kTH * kTW) / 32; ++j) {
         const int q = (tid >> 3) + 32 * j;
@@ -722,7 +809,7 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
         const int gy = oy0 + oy * a.sub, gx = ox0 + ox * a.sub;
         if (gy >= a.Ho || gx >= a.Wo) continue;
         const uint32_t base = s_in + static_cast<uint32_t>((oy * a.stride * a.iw + ox * a.stride) * kCV + v) * 16u;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long acc2[4] = {0ull, 0ull, 0ull, 0ull};     // fp32 pairs: rows are folded with FADD2
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           typename P2<T>::t racc[4];
@@ -738,24 +825,29 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
             for (int i = 0; i < 4; ++i) racc[i] = __hfma2(xv.h[i], w2[ky * 3 + kx][i], racc[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { const float2 f = P2<T>::unpack(racc[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+          for (int i = 0; i < 4; ++i) { const float2 f = P2<T>::unpack(racc[i]); acc2[i] = f32x2_add(acc2[i], f32x2_pack(f.x, f.y)); }
         }
         if (a.out_scale) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = apply_act(fmaf(acc[i], a.out_scale[cc + i], a.out_shift[cc + i]), a.out_act);
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = f32x2_unpack(acc2[i]);
+            acc2[i] = f32x2_pack(apply_act(fmaf(f.x, a.out_scale[cc + 2 * i], a.out_shift[cc + 2 * i]), a.out_act),
+                                 apply_act(fmaf(f.y, a.out_scale[cc + 2 * i + 1], a.out_shift[cc + 2 * i + 1]), a.out_act));
+          }
         }
         if (stats) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { ssum[i] += acc[i]; ssqs[i] = fmaf(acc[i], acc[i], ssqs[i]); }
+          for (int i = 0; i < 4; ++i) f32x2_acc_v(ssum2[i], ssqs2[i], acc2[i]);
         }
         V8<T> o;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o.h[i] = P2<T>::pack(acc[2 * i], acc[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) { const float2 f = f32x2_unpack(acc2[i]); o.h[i] = P2<T>::pack(f.x, f.y); }
         stg_h8(y + ((static_cast<size_t>(b) * a.Ho + gy) * a.Wo + gx) * a.C + cc, o);
       }
     }
     if (pro) fence_proxy_async();     // generic-proxy writes of the transform vs the TMA that will refill this buffer
     __syncthreads();
+    if (++slot == nb) { slot = 0; par ^= 1; }
   }
   if (stats && cur_chunk >= 0) flush_stats(cur_chunk);
 }
@@ -1405,7 +1497,10 @@ static int launch_dw_tiled(DwTileArgs& a, cudaStream_t st) {
     constexpr int kDt = std::is_same<T, __half>::value ? DLB_F16 : DLB_BF16;
     fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
-    const size_t smem_t = 2 * tile_b + 16 + 128 * sizeof(float);
+    // ring depth: as many tiles as fit in half an SM's shared memory (2 CTAs / SM), 2..4
+    a.n_buf = static_cast<int>((110 * 1024 - 32 - 128 * sizeof(float) - 256 - 64) / tile_b);
+    a.n_buf = a.n_buf > 4 ? 4 : (a.n_buf < 2 ? 2 : a.n_buf);
+    const size_t smem_t = a.n_buf * tile_b + 32 + 128 * sizeof(float) + 256 + 64;   // ring + barriers + stats + affine + slot info
     CUtensorMap tm;
     int rc = make_tmap_nhwc(&tm, kDt, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;

@@ -77,23 +77,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& u) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
-// packed fp32 pairs (sm_100 FADD2 / FFMA2): one instruction per two columns in the statistics walk
-__device__ __forceinline__ void f32x2_acc(unsigned long long& s, unsigned long long& q, float a, float b) {
-  unsigned long long v;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(v));
-  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q) : "l"(v));
-}
-__device__ __forceinline__ float2 f32x2_unpack(unsigned long long v) {
-  float2 f;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
-  return f;
-}
-__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
