@@ -858,13 +858,16 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   const uint32_t tile_bytes = static_cast<uint32_t>(a.ih) * a.iw * kCV * sizeof(V8<T>);
   const uint32_t buf_stride = (tile_bytes + 127u) & ~127u;
   const uint32_t s_base = smem_u32(s_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + 2 * buf_stride);
-  float* s_dw = reinterpret_cast<float*>(s_raw + 2 * buf_stride + 16);   // [9][64]
+  const int nb = a.n_buf;                                                  // ring of nb tiles (up to 8: one CTA per SM)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_raw + nb * buf_stride);
+  float* s_dw = reinterpret_cast<float*>(s_raw + nb * buf_stride + 64);   // [9][64]
+  uint4* s_aff = reinterpret_cast<uint4*>(s_raw + nb * buf_stride + 64 + 9 * 64 * 4);        // packed prologue scale / shift [2][8]
+  int* s_info = reinterpret_cast<int*>(s_raw + nb * buf_stride + 64 + 9 * 64 * 4 + 256);     // per ring slot: b, oy0, ox0
   const int tid = threadIdx.x, v = tid & 7, lane = tid & 31;
   const bool pro = a.in_scale != nullptr;
   if (tid == 0) {
     tma_prefetch_desc(&tmap);
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    for (int i = 0; i < nb; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -908,19 +911,22 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
   const int chunk = blockIdx.x % a.chunks, grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
   const int n_sp = a.B * a.tiles_y * a.tiles_x * a.sub * a.sub;
   auto issue = [&](int sp, int slot) {
-    int b, oy0, ox0;
+    int b, oy0, ox0;           // decoded once, by the issuing thread; travels with the ring slot
     dw_decode_tile(a, sp, b, oy0, ox0);
+    s_info[slot * 4 + 0] = b; s_info[slot * 4 + 1] = oy0; s_info[slot * 4 + 2] = ox0;
     mbar_expect_tx(&full[slot], tile_bytes);
     tma_load_4d(s_raw + slot * buf_stride, &tmap, &full[slot], chunk * 64, ox0 * a.stride - a.pad_l, oy0 * a.stride - a.pad_t, b);
   };
 
   pdl_wait();     // index math and barrier init above overlap the preceding kernel's tail; no global access before this
   if (grp >= ngrp) return;
-  if (tid == 0 && grp < n_sp) issue(grp, 0);
-  for (int sp = grp, it = 0; sp < n_sp; sp += ngrp, ++it) {
-    const int slot = it & 1;
-    int b, oy0, ox0;
-    dw_decode_tile(a, sp, b, oy0, ox0);
+  if (tid == 0) {
+    for (int i = 0; i < nb - 1; ++i)
+      if (grp + i * ngrp < n_sp) issue(grp + i * ngrp, i);
+  }
+  __syncthreads();           // slot info of the first tile is read before its mbarrier wait (dy prefetch below)
+  int slot = 0; uint32_t par = 0;
+  for (int sp = grp; sp < n_sp; sp += ngrp) {
     const int c0 = chunk * 64, cc = c0 + v * 8;
     const bool cv_ok = cc < a.C;
     if (chunk != cur_chunk) {
@@ -930,8 +936,17 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
       for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+      if (pro && tid < 64) {
+        typename P2<T>::t* af = reinterpret_cast<typename P2<T>::t*>(s_aff);
+        const int ch = c0 + 2 * (tid & 31);
+        const float* src = tid < 32 ? a.in_scale : a.in_shift;
+        af[tid] = ch + 1 < a.C ? P2<T>::pack(src[ch], src[ch + 1]) : P2<T>::bcast(0.f);
+      }
+      __syncthreads();
     }
-    if (tid == 0 && sp + ngrp < n_sp) issue(sp + ngrp, slot ^ 1);
+    // slot info of THIS tile was written at least one __syncthreads ago (prologue or an earlier iteration's issue)
+    const int b = s_info[slot * 4 + 0], oy0 = s_info[slot * 4 + 1], ox0 = s_info[slot * 4 + 2];
+    if (tid == 0 && sp + (nb - 1) * ngrp < n_sp) issue(sp + (nb - 1) * ngrp, slot == 0 ? nb - 1 : slot - 1);
     // the thread's four dy vectors are requested before waiting for the input tile
     constexpr int NP = (kTH * kTW) / 32;
     V8<T> g[NP];
@@ -947,10 +962,10 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) g[j].h[i] = P2<T>::bcast(0.f);
       }
     }
-    mbar_wait(&full[slot], (it >> 1) & 1);
+    mbar_wait(&full[slot], par);
     const uint32_t s_in = s_base + slot * buf_stride;
     if (pro) {
-      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok);
+      dw_transform_tile_h<T>(a, s_in, oy0, ox0, c0, cv_ok, s_aff);
       __syncthreads();
     }
     if (cv_ok) {
@@ -971,6 +986,7 @@ __global__ void __launch_bounds__(256, 1) dw_wgrad_tma_h_kernel(const __grid_con
     }
     if (pro) fence_proxy_async();
     __syncthreads();
+    if (++slot == nb) { slot = 0; par ^= 1; }
   }
   if (cur_chunk >= 0) flush(cur_chunk);
 }
@@ -1536,7 +1552,10 @@ static int launch_dw_wgrad_tiled(DwTileArgs& a, cudaStream_t st) {
     constexpr int kDt = std::is_same<T, __half>::value ? DLB_F16 : DLB_BF16;
     fill_tma_geometry(a);
     const size_t tile_b = (static_cast<size_t>(a.ih) * a.iw * kCV * 16 + 127) & ~size_t(127);
-    const size_t smem_t = 2 * tile_b + 16 + 9 * 64 * sizeof(float);
+    const size_t fixed = 64 + 9 * 64 * sizeof(float) + 256 + 128;     // barriers, dw staging, affine, slot info
+    a.n_buf = static_cast<int>((200 * 1024 - fixed) / tile_b);       // one CTA per SM: up to 8 tiles in flight
+    a.n_buf = a.n_buf > 8 ? 8 : (a.n_buf < 2 ? 2 : a.n_buf);
+    const size_t smem_t = a.n_buf * tile_b + fixed;
     CUtensorMap tm;
     int rc = make_tmap_nhwc(&tm, kDt, a.x, a.B, a.H, a.W, a.C, 64, a.iw * a.sub, a.ih * a.sub, a.sub, a.nan_fill);
     if (rc) return rc;
