@@ -28,7 +28,9 @@ struct WgArgs {
   int M, N, K;
   int rows_per_stage;          // R: reduction rows per pipeline stage (32 or 64)
   int n_boxes;                 // 64-wide dY boxes per stage (N group / 64)
-  int n_chunks, chunk_n;       // UMMA N chunks per group
+  int n_chunks, chunk_n;       // UMMA N chunks per group: chunks 0..n_chunks-2 are chunk_n wide, the last one chunk_last
+  int chunk_last, group_cols;
+  uint32_t idesc_last;
   int k_tiles, n_groups, splits;
   int rows_per_split;          // multiple of R
   int num_stages;
@@ -103,7 +105,8 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const uint64_t adesc = make_sw128_desc(sa + ks * 2048, R * 128, 1024);
           for (int c = 0; c < g.n_chunks; ++c) {
             const uint64_t bdesc = make_sw128_desc(sy + c * (g.chunk_n / 64) * R * 128 + ks * 2048, R * 128, 1024);
-            umma_f16(tmem_base + c * g.chunk_n, adesc, bdesc, g.idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(tmem_base + c * g.chunk_n, adesc, bdesc, c + 1 == g.n_chunks ? g.idesc_last : g.idesc,
+                     (it > 0 || ks > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -115,7 +118,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int quad = warp & 3;
     const int k = k0 + quad * 32 + lane;
     float* dst_row = g.dW + static_cast<size_t>(k) * g.N;
-    const int ncols = g.n_chunks * g.chunk_n;
+    const int ncols = g.group_cols;
     if (iters > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -263,10 +266,14 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   g.n_groups = (npad64 + 511) / 512;
   const int group_cols = ((npad64 / 64 + g.n_groups - 1) / g.n_groups) * 64;   // <= 512, multiple of 64
   g.n_boxes = group_cols / 64;
+  // UMMA N chunks: multiples of 64 (a chunk starts on a 64-column box), <= 256; uneven splits take a narrower last
+  // chunk (320 = 192 + 128) instead of falling back to five 64-wide MMAs
+  g.group_cols = group_cols;
   g.n_chunks = (group_cols + 255) / 256;
-  g.chunk_n = group_cols / g.n_chunks;
-  if (g.chunk_n % 64 != 0) { g.n_chunks = g.n_boxes; g.chunk_n = 64; }      // fall back to 64-wide chunks
-  g.rows_per_stage = group_cols <= 256 ? 64 : 32;
+  g.chunk_n = ((g.n_boxes + g.n_chunks - 1) / g.n_chunks) * 64;
+  g.chunk_last = group_cols - (g.n_chunks - 1) * g.chunk_n;
+  // 64 reduction rows per stage whenever >= 3 stages of that size fit
+  g.rows_per_stage = (2 + g.n_boxes) * 64 * 128 * 3 <= 200 * 1024 ? 64 : 32;
   g.k_tiles = (p->K + 127) / 128;
   const int tiles = g.k_tiles * g.n_groups;
   int splits = (num_sms() + tiles - 1) / tiles;
@@ -281,6 +288,7 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   g.num_stages = (200 * 1024) / g.stage_bytes;
   if (g.num_stages > kWgMaxStages) g.num_stages = kWgMaxStages;
   g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 1, 1);
+  g.idesc_last = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_last, 1, 1);
   CUtensorMap ta, ty;
   int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, R, 64);
   if (rc) return rc;
