@@ -301,6 +301,16 @@ int dlb_confusion(int B, int64_t npix, int C, const float* labels, const uint8_t
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * SegmentationGenerator label contract (utils.py:360-399), the step right before the hot path: void remap
+ * (labels outside 0..n_classes-1 -> n_classes) into y[B, npix] and per-image 'balanced' class weights
+ * sw[B, npix] = n_valid / (n_present * count[label]) (0 for void), float64 arithmetic stored as float32 --
+ * bit-exact with sklearn.utils.class_weight.compute_class_weight('balanced').  label_type: 0 = uint8, 1 = int32,
+ * 2 = float32.  counts: caller-owned workspace [B, n_classes + 1] uint64 (zeroed here).  y or sw may be NULL.
+ * ------------------------------------------------------------------------------------------------- */
+int dlb_label_weights(int B, int64_t npix, int n_classes, int label_type, const void* labels,
+                      unsigned long long* counts, float* y, float* sw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Dense CRF (utils.py:74-91 -> pydensecrf DenseCRF2D.inference): permutohedral lattice mean field.
  *   unary   : [M, N] fp32 energies (N = H*W pixels, label-major as pydensecrf)
  *   image   : [H, W, 3] uint8

@@ -112,7 +112,7 @@ EXPORTS = [
     "dlb_resize_softmax_fwd", "dlb_resize_softmax_ce", "dlb_ce_grad_scale", "dlb_phase_shift", "dlb_adam_step",
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
-    "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan",
+    "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan", "dlb_label_weights",
 ]
 
 _lib = None
@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
         L.dlb_cast_weights_batched.argtypes = [i32, vp, i64, vp]
         L.dlb_fill_zero.argtypes = [vp, i64, vp]
         L.dlb_confusion.argtypes = [i32, i64, i32, vp, vp, vp, vp]
+        L.dlb_label_weights.argtypes = [i32, i64, i32, i32, vp, vp, vp, vp, vp]
         L.dlb_stem_conv_wgrad.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.dlb_pw_wgrad_workspace_bytes.argtypes = [i32, i32, i32]
         L.dlb_conv3x3_fwd.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]

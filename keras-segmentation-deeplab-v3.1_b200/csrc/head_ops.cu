@@ -319,9 +319,100 @@ __global__ void __launch_bounds__(256) confusion_kernel(long long npix, int C, c
     if (s_conf[i]) atomicAdd(&conf[static_cast<size_t>(b) * nb + i], static_cast<unsigned long long>(s_conf[i]));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SegmentationGenerator label contract (reference utils.py:360-399): void remap + per-image balanced class weights.
+//   y  = label, every value outside 0..n_classes-1 -> n_classes (void)            (utils.py:360-365)
+//   sw = n_valid / (n_present * count[y]) for valid pixels, 0 for void             (utils.py:388-399, sklearn
+//        compute_class_weight('balanced'): n_samples / (n_classes_present * bincount), float64 then stored as float32)
+// Two passes over the labels: per-image histogram (shared-memory bins), then weights; bit-exact with the numpy path.
+// ---------------------------------------------------------------------------------------------
+template <typename LT>
+__device__ __forceinline__ int label_remap(LT v, int n_classes) {
+  const long long l = static_cast<long long>(v);
+  return (l < 0 || l >= n_classes || static_cast<LT>(l) != v) ? n_classes : static_cast<int>(l);
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(256) label_hist_kernel(long long npix, int n_classes, const LT* __restrict__ labels,
+                                                         unsigned long long* __restrict__ counts) {
+  pdl_prologue();
+  extern __shared__ unsigned int s_hist[];   // [n_classes + 1]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i <= n_classes; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const LT* lb = labels + static_cast<size_t>(b) * npix;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    atomicAdd(&s_hist[label_remap(lb[i], n_classes)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i <= n_classes; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&counts[static_cast<size_t>(b) * (n_classes + 1) + i], static_cast<unsigned long long>(s_hist[i]));
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(256) label_weight_kernel(long long npix, int n_classes, const LT* __restrict__ labels,
+                                                           const unsigned long long* __restrict__ counts,
+                                                           float* __restrict__ y, float* __restrict__ sw) {
+  pdl_prologue();
+  extern __shared__ float s_w[];             // [n_classes + 1]
+  __shared__ double s_nvalid;
+  __shared__ int s_present;
+  const int b = blockIdx.y;
+  const unsigned long long* cnt = counts + static_cast<size_t>(b) * (n_classes + 1);
+  if (threadIdx.x == 0) {
+    unsigned long long nv = 0; int k = 0;
+    for (int c = 0; c < n_classes; ++c) { nv += cnt[c]; k += cnt[c] > 0; }
+    s_nvalid = static_cast<double>(nv); s_present = k;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= n_classes; c += blockDim.x) {
+    float w = 0.f;
+    if (c < n_classes && cnt[c] > 0)
+      w = static_cast<float>(s_nvalid / (static_cast<double>(s_present) * static_cast<double>(cnt[c])));
+    s_w[c] = w;
+  }
+  __syncthreads();
+  const LT* lb = labels + static_cast<size_t>(b) * npix;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = label_remap(lb[i], n_classes);
+    if (y) y[static_cast<size_t>(b) * npix + i] = static_cast<float>(l);
+    if (sw) sw[static_cast<size_t>(b) * npix + i] = s_w[l];
+  }
+}
+
 }  // namespace dlb
 
 using namespace dlb;
+
+extern "C" int dlb_label_weights(int B, int64_t npix, int n_classes, int label_type, const void* labels,
+                                 unsigned long long* counts, float* y, float* sw, void* stream) {
+  DLB_REQUIRE(labels && counts && (y || sw), "label_weights: null pointer");
+  DLB_REQUIRE(B > 0 && npix > 0 && n_classes > 0 && n_classes <= 4096, "label_weights: bad shape B=%d npix=%lld classes=%d", B,
+              (long long)npix, n_classes);
+  DLB_REQUIRE(label_type >= 0 && label_type <= 2, "label_weights: label_type must be 0 (u8), 1 (i32) or 2 (f32)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DLB_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * B * (n_classes + 1), st));
+  long long blocks = (npix + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (static_cast<long long>(num_sms()) * 8 + B - 1) / B;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(static_cast<unsigned>(blocks), B);
+  const size_t smem = (n_classes + 1) * sizeof(unsigned int);
+#define LW(LT)                                                                                              \
+  do {                                                                                                      \
+    launch_k(label_hist_kernel<LT>, grid, 256, smem, st, (long long)npix, n_classes, (const LT*)labels, counts);   \
+    launch_k(label_weight_kernel<LT>, grid, 256, smem, st, (long long)npix, n_classes, (const LT*)labels,          \
+             (const unsigned long long*)counts, y, sw);                                                     \
+  } while (0)
+  if (label_type == 0) LW(uint8_t);
+  else if (label_type == 1) LW(int);
+  else LW(float);
+#undef LW
+  g_launches += 2;
+  return check_launch("label_weight_kernel");
+}
 
 extern "C" int dlb_resize_softmax_fwd(int B, int h, int w, int C, int ldl, int H, int W, const float* logits,
                                       float* probs, uint8_t* argmax, void* stream) {

@@ -281,6 +281,21 @@ def confusion(labels: torch.Tensor, argmax: torch.Tensor, C_: int, conf: torch.T
             "confusion")
 
 
+def label_weights(labels: torch.Tensor, n_classes: int, y: Optional[torch.Tensor] = None,
+                  sw: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None):
+    """Generator label contract on the device (reference utils.py:360-399): void remap into y [B, P] f32 and the
+    per-image balanced class weights sw [B, P] f32; see dlb_label_weights.  labels: [B, P] uint8 / int32 / float32."""
+    L.require_cuda(labels)
+    lt = {torch.uint8: 0, torch.int32: 1, torch.float32: 2}[labels.dtype]
+    B = labels.shape[0]
+    P = labels.numel() // B
+    if counts is None:
+        counts = torch.empty(B, n_classes + 1, device=labels.device, dtype=torch.int64)
+    L.check(L.lib().dlb_label_weights(B, P, n_classes, lt, labels.data_ptr(), counts.data_ptr(), L.ptr(y), L.ptr(sw),
+                                      L.stream_ptr()), "label_weights")
+    return y, sw, counts
+
+
 def conv3x3_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, out_scale=None, out_shift=None, out_act=ACT_NONE):
     B, H, W_, Cin = x.shape
     L.check(L.lib().dlb_conv3x3_fwd(B, H, W_, Cin, y.shape[-1], L.dt(x), x.data_ptr(), w.data_ptr(), y.data_ptr(),

@@ -220,3 +220,49 @@ class SegModel:
     @classmethod
     def set_batch_size(cls, new_batch_size):
         cls.batch_size = new_batch_size
+
+# ---------------------------------------------------------------------------------------------------------
+# the data formats either side of the hot path
+# ---------------------------------------------------------------------------------------------------------
+def generator_labels_and_weights(labels, n_classes):
+    """What `SegmentationGenerator.__getitem__` hands to `fit_generator` besides the image (reference utils.py:360-399),
+    computed on the device: labels [B, H, W] or [B, P] (uint8 / int32 / float32, raw dataset values) ->
+      Y  [B, P, 1] float32 with every value outside 0..n_classes-1 mapped to the void label n_classes (:360-365)
+      SW [B, P]    float32 per-image balanced class weights, 0 on void pixels (:388-399; sklearn 'balanced')
+    Returns CUDA tensors (`{'pred_mask': SW}` is the sample-weight dict the notebook passes)."""
+    t = torch.as_tensor(labels)
+    if t.dtype not in (torch.uint8, torch.int32, torch.float32):
+        t = t.to(torch.int32)
+    t = t.cuda().contiguous()
+    B = t.shape[0]
+    t = t.view(B, -1)
+    y = torch.empty(B, t.shape[1], device="cuda", dtype=torch.float32)
+    sw = torch.empty_like(y)
+    ops.label_weights(t, int(n_classes), y, sw)
+    return y.unsqueeze(-1), sw
+
+
+def calculate_iou(model, nb_classes=21, data=None, batch_size=16):
+    """Dataset-level confusion matrix of the notebook (segmentation.ipynb cell 10, `calculate_iou`): predict, argmax,
+    count (label, prediction) pairs over all non-void pixels.  The reference walks 262 144 x N pixels in a Python loop;
+    here the counts come from the device (dlb_confusion).  `data` = (X [N,H,W,3], label [N,P]) replaces the notebook's
+    global validation generator.  Returns conf_m [nb_classes, nb_classes] float64 with the reference's indexing
+    `conf_m[l-1, p-1] += 1` (a cyclic shift of both axes; IoU / mean IoU are invariant to it)."""
+    if data is None:
+        raise ValueError("calculate_iou needs data=(X, label): the notebook's global SegClass generator is not part of this package")
+    X, label = data
+    X = torch.as_tensor(X)
+    label = torch.as_tensor(label).reshape(X.shape[0], -1)
+    conf = torch.zeros(nb_classes + 1, nb_classes, device="cuda", dtype=torch.int64)
+    for i in range(0, X.shape[0], batch_size):
+        xb = X[i:i + batch_size]
+        probs = model.predict_on_batch(xb)
+        probs = _as_cuda(probs).reshape(xb.shape[0], -1, nb_classes)
+        Bb, T, Cn = probs.shape
+        am = torch.empty(Bb, T, device="cuda", dtype=torch.uint8)
+        ops.resize_softmax_fwd(torch.log(probs.clamp_min(1e-30)).view(Bb, T, 1, Cn).contiguous(), Cn, T, 1, None, am)
+        cb = torch.zeros(Bb, Cn + 1, Cn, device="cuda", dtype=torch.int64)
+        ops.confusion(label[i:i + batch_size].float().cuda().contiguous().view(Bb, T, 1), am, Cn, cb)
+        conf += cb.sum(0)
+    c = conf[:nb_classes].cpu().numpy().astype(np.float64)     # void row dropped (reference: `if l == nb_classes: continue`)
+    return np.roll(np.roll(c, -1, axis=0), -1, axis=1)          # conf_m[l-1, p-1]

@@ -250,3 +250,34 @@ def keras_adam(p, g, m, v, iterations, lr=7e-4, beta1=0.9, beta2=0.999, eps=1e-8
     v = beta2 * v + (1 - beta2) * g * g
     p = p - lr_t * m / (torch.sqrt(v) + eps)
     return p, m, v
+
+# ---------------------------------------------------------------------------------------------------------
+# data formats either side of the hot path (test infrastructure, like everything in oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def generator_labels_and_weights(label, n_classes):
+    """Restatement of SegmentationGenerator.__getitem__'s label handling for ONE image (reference utils.py:360-399):
+    void remap (:360-365), then adaptive per-pixel weights from sklearn's compute_class_weight('balanced', classes,
+    y) = n_samples / (n_classes_present * bincount(y)) over the non-void pixels (:388-397), void weight 0 (:399).
+    label: int array of any shape; returns (y [P] int32, sw [P] float32)."""
+    y = np.asarray(label).astype(np.int64).flatten()
+    y = np.where((y < 0) | (y > n_classes - 1), n_classes, y)         # setxor1d remap + `y[y>(n_classes-1)] = n_classes`
+    filt = y[y != n_classes]
+    sw = np.zeros(y.shape, dtype=np.float32)
+    u = np.unique(filt)
+    if len(u):
+        counts = np.bincount(filt, minlength=n_classes)[u]
+        w = len(filt) / (len(u) * counts.astype(np.float64))          # float64, as sklearn
+        for cls, wc in zip(u, w):
+            np.putmask(sw, y == cls, wc)                              # stored into the float32 SW buffer
+    return y.astype(np.int32), sw
+
+
+def calculate_iou_conf(pred_argmax, label, nb_classes):
+    """The counting loop of segmentation.ipynb cell 10 (`calculate_iou`), vectorised: conf_m[l-1, p-1] += 1 for every
+    pixel whose label is not void."""
+    p = np.ravel(pred_argmax).astype(int)
+    l = np.ravel(label).astype(int)
+    conf = np.zeros((nb_classes, nb_classes), dtype=float)
+    keep = (l != nb_classes) & (l < nb_classes) & (p < nb_classes)
+    np.add.at(conf, ((l[keep] - 1) % nb_classes, (p[keep] - 1) % nb_classes), 1)
+    return conf

@@ -375,3 +375,33 @@ def test_graph_replay_equals_eager_and_mious_match():
         m1 = R.notebook_miou(gt, p[b].argmax(-1))
         m2 = R.notebook_miou(gt, pref[b].argmax(-1).numpy())
         assert abs(m1 - m2) <= 1e-3
+
+
+def test_generator_contract_and_calculate_iou():
+    """The data formats either side of the hot path: device-side SegmentationGenerator labels / balanced
+    sample weights feed train_on_batch, and calculate_iou's confusion matrix equals the notebook's counting loop
+    applied to the model's own argmax."""
+    from deeplab_b200.model import Adam
+    from deeplab_b200.utils import SegModel, calculate_iou, generator_labels_and_weights
+    from oracle import network as N
+    from oracle import ref_ops as R
+    B, H, Wd = 4, 64, 64
+    x, y, _ = _synthetic_batch(B, H, Wd, seed=31)
+    raw = y[:, :, 0].astype(np.int32).copy()
+    raw[raw == 21] = 255                                   # VOC-style void value in the raw label files
+    Y, SW = generator_labels_and_weights(raw.reshape(B, H, Wd), 21)
+    assert Y.shape == (B, H * Wd, 1) and SW.shape == (B, H * Wd)
+    for b in range(B):
+        yr, swr = R.generator_labels_and_weights(raw[b], 21)
+        assert np.array_equal(Y[b, :, 0].cpu().numpy(), yr.astype(np.float32))
+        assert np.array_equal(SW[b].cpu().numpy(), swr)
+    sm = SegModel(image_size=(H, Wd), compute_dtype='float32')
+    model = sm.create_seg_model("original", n=21)
+    _push_weights(model, N.random_mobilenetv2_weights(seed=6, head="conv_upsample"))
+    model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+    out = model.train_on_batch(x, Y, sample_weight={"pred_mask": SW})
+    assert np.isfinite(np.asarray(out, dtype=np.float64)).all()
+    conf = calculate_iou(model, nb_classes=21, data=(x, Y[:, :, 0].cpu().numpy()), batch_size=2)
+    pred = model.predict(x).argmax(-1)
+    assert np.array_equal(conf, R.calculate_iou_conf(pred, Y[:, :, 0].cpu().numpy(), 21))
+    assert conf.sum() == (Y[:, :, 0].cpu().numpy() != 21).sum()

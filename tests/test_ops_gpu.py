@@ -6,6 +6,7 @@ failure points at a descriptor / index bug directly.
 import math
 
 import pytest
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -421,3 +422,24 @@ def test_cast_weight_and_confusion():
         idx = labels[b, :, 0].long().cpu() * C + am[b].long().cpu()
         ref[b] = torch.bincount(idx, minlength=(C + 1) * C).view(C + 1, C)
     assert torch.equal(conf.cpu(), ref)
+
+
+@pytest.mark.parametrize("ldtype", [torch.uint8, torch.int32, torch.float32])
+def test_label_weights_bit_exact_vs_oracle(ldtype):
+    """dlb_label_weights (generator contract, reference utils.py:360-399) vs the numpy restatement: exact."""
+    from oracle import ref_ops as R
+    ops = _ops()
+    rng = np.random.RandomState(5)
+    n_classes = 21
+    labs = np.stack([rng.choice([0, 1, 5, 20, 21, 255], size=(64, 48), p=[.5, .1, .1, .1, .1, .1]),
+                     rng.choice([0, 255], size=(64, 48)),
+                     np.full((64, 48), 255),
+                     rng.randint(0, 22, size=(64, 48))]).astype(np.int64)
+    t = torch.from_numpy(labs).to(ldtype).cuda().view(4, -1)
+    y = torch.empty(4, 64 * 48, device="cuda")
+    sw = torch.empty(4, 64 * 48, device="cuda")
+    ops.label_weights(t, n_classes, y, sw)
+    for b in range(4):
+        yr, swr = R.generator_labels_and_weights(labs[b], n_classes)
+        assert np.array_equal(y[b].cpu().numpy(), yr.astype(np.float32))
+        assert np.array_equal(sw[b].cpu().numpy(), swr)

@@ -156,3 +156,40 @@ def test_icnr_matches_reference_sequence():
     # every group of scale^2 consecutive-by-C' channels repeats the sub-kernel: w[..., (i*s+j)*C' + k] == sub[..., k]
     for q in range(16):
         assert torch.equal(w[0, 0, :, q * 3:(q + 1) * 3], sub[0, 0])
+
+
+def test_label_weights_restatement_matches_sklearn():
+    """The oracle's class-weight arithmetic is pinned against the third-party function the reference calls
+    (utils.py:393: sklearn.utils.class_weight.compute_class_weight('balanced', ...)), which is installed here."""
+    from sklearn.utils import class_weight
+    from oracle import ref_ops as R
+    rng = np.random.RandomState(3)
+    for n_classes, present in ((21, [0, 3, 7, 21, 255]), (2, [0, 1]), (21, [255]), (5, [2])):
+        lab = rng.choice(present, size=(37, 29))
+        y, sw = R.generator_labels_and_weights(lab, n_classes)
+        yy = lab.flatten().astype(np.int64)
+        yy[yy > n_classes - 1] = n_classes
+        assert np.array_equal(y, yy)
+        filt = yy[yy != n_classes]
+        exp = np.zeros(yy.shape, dtype=np.float32)
+        u = np.unique(filt)
+        if len(u):
+            cw = class_weight.compute_class_weight(class_weight="balanced", classes=u, y=filt)
+            for c, w in zip(u, cw):
+                np.putmask(exp, yy == c, w)
+        assert np.array_equal(sw, exp)
+
+
+def test_calculate_iou_conf_matches_literal_loop():
+    from oracle import ref_ops as R
+    rng = np.random.RandomState(4)
+    C = 5
+    pred = rng.randint(0, C, size=400)
+    lab = rng.randint(0, C + 1, size=400)
+    conf = np.zeros((C, C))
+    for p, l in zip(pred, lab):          # the notebook's loop, verbatim semantics
+        if l == C:
+            continue
+        if l < C and p < C:
+            conf[l - 1, p - 1] += 1
+    assert np.array_equal(R.calculate_iou_conf(pred, lab, C), conf)
