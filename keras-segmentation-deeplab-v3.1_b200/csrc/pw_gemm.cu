@@ -148,14 +148,19 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int group_rows = g.chunks_per_group * g.chunk_n;
+  // Work unit = (M tile, column group), strided over the CTAs: the 64x64-resolution layers have 512 M tiles = 3.46 per SM
+  // (a quarter-empty fourth round); with the column groups of the wide outputs flattened in, 1024-2048 units leave a
+  // 1-2 % tail.  A is fetched per (tile, group) either way.
+  const int n_units = g.num_m_tiles * g.n_groups;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
         const int m0 = tile * kBlockM;
-        for (int grp = 0; grp < g.n_groups; ++grp) {
+        for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
           const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
           for (int kb = 0; kb < g.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -176,8 +181,9 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // ===================== MMA issuer =====================
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
-        for (int grp = 0; grp < g.n_groups; ++grp) {
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
+        for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
           const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
@@ -236,7 +242,8 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int j_first = g.alt_tiles ? 0 : set * 64;
     const int j_step = g.alt_tiles ? 64 : 64 * kSets;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < g.num_m_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
       const int m_base = tile * kBlockM + quad * 32;
       const int m = m_base + lane;
       const bool row_ok = m < g.M;
@@ -253,7 +260,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                          static_cast<size_t>(bb) * g.shuffle_r) *
                         g.shuffle_cs;
       }
-      for (int grp = 0; grp < g.n_groups; ++grp) {
+      for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
         const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
         const int as_cur = as;
         const uint32_t aphase_cur = aphase;
@@ -720,7 +727,8 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   if (rc) return rc;
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
-  const int grid = g.num_m_tiles < num_sms() ? g.num_m_tiles : num_sms();
+  const int n_units = g.num_m_tiles * g.n_groups;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
 
   const bool lean = !p->col_scale && !p->col_shift && !p->row_bias;
 #define LAUNCH(OT, SETS, LEAN)                                                                                   \

@@ -276,7 +276,10 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   g.rows_per_stage = (2 + g.n_boxes) * 64 * 128 * 3 <= 200 * 1024 ? 64 : 32;
   g.k_tiles = (p->K + 127) / 128;
   const int tiles = g.k_tiles * g.n_groups;
-  int splits = (num_sms() + tiles - 1) / tiles;
+  // one CTA per SM and ONE wave: tiles * splits must not exceed the SM count (ceil() gave 152 CTAs for 8 K tiles --
+  // four stragglers in a second wave doubled the kernel time: 30 % tensor-pipe activity at 1.9 TB/s in the ncu capture)
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
   const int R = g.rows_per_stage;
   int rps = ((p->M + splits - 1) / splits + R - 1) / R * R;
   splits = (p->M + rps - 1) / rps;
