@@ -103,3 +103,52 @@ def test_pw_gemm_plan_fits_every_layer_shape(lib):
                 assert acc_stages <= sets if alt else acc_stages <= 2
                 if alt:
                     assert n_groups == 1
+
+
+def test_every_kernel_honours_the_dependent_launch_contract():
+    """Every kernel is launched through launch_k() with programmatic stream serialization, so every `__global__`
+    body must execute griddepcontrol.wait (pdl_prologue / pdl_wait) before its first global access -- a kernel without
+    it would race with its predecessor.  Static check over csrc/: no raw <<<>>> launches remain, and each kernel body
+    contains the wait ahead of any dereference of a kernel parameter pointer we can recognise (`a.`/`g.`/`p->` loads
+    are allowed before it only for scalars; the check is 'wait present and within the first statements')."""
+    import glob
+    csrc = os.path.join(ROOT, "keras-segmentation-deeplab-v3.1_b200", "csrc")
+    n_kernels = 0
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        src = open(path).read()
+        code = re.sub(r"//[^\n]*", "", src)
+        assert "<<<" not in code, f"{path}: raw kernel launch bypasses launch_k()"
+        pos = 0
+        while True:
+            i = code.find("__global__", pos)
+            if i < 0:
+                break
+            # parameter list: first '(' whose preceding identifier is not __launch_bounds__
+            k = i
+            while True:
+                k = code.find("(", k)
+                ident = re.search(r"([A-Za-z_]\w*)\s*$", code[:k]).group(1)
+                depth, e = 0, k
+                while True:
+                    depth += code[e] == "("
+                    depth -= code[e] == ")"
+                    if depth == 0:
+                        break
+                    e += 1
+                if ident == "__launch_bounds__":
+                    k = e + 1
+                    continue
+                break
+            b = code.find("{", e)
+            depth, j = 0, b
+            while True:
+                depth += code[j] == "{"
+                depth -= code[j] == "}"
+                if depth == 0:
+                    break
+                j += 1
+            body = code[b:j]
+            assert "pdl_prologue();" in body or "pdl_wait();" in body, f"{path}: kernel {ident} never waits on its predecessor"
+            n_kernels += 1
+            pos = j
+    assert n_kernels >= 55, n_kernels

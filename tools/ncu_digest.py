@@ -1,9 +1,13 @@
 """Digest of one `ncu --set full --import-source on` report: headline metrics + instructions / stall samples per source
-line.  Usage: python tools/ncu_digest.py gpurun_out/x.ncu-rep [top_n]   (ncu must be on PATH; no GPU needed)."""
+line.  Usage: python tools/ncu_digest.py gpurun_out/x.ncu-rep [top_n] [--sass]   (ncu must be on PATH; no GPU needed).
+--sass appends the executed-instruction histogram by SASS opcode and the most-sampled SASS instructions (what found the
+per-thread tile decode and the CAS-loop shared atomics in round 1)."""
 import csv, io, subprocess, sys
 
-rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+rep = args[0]
+top = int(args[1]) if len(args) > 1 else 25
+want_sass = "--sass" in sys.argv
 
 
 def run(*a):
@@ -55,3 +59,31 @@ tn = sum(v[0] for v in agg.values()) or 1; ts = sum(v[1] for v in agg.values()) 
 print(f"## per source line: {tn:.0f} warp instructions, {ts:.0f} samples")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0] - kv[1][1] * tn / ts)[:top]:
     print(f"{k[0]:>14s}:{k[1]:<5d} inst {100 * v[0] / tn:5.1f}%  samples {100 * v[1] / ts:5.1f}%  {k[2]}")
+
+if want_sass:
+    import collections
+    rows = list(csv.reader(io.StringIO(run("--page", "source", "--csv", "--print-source", "sass"))))
+    hdr = next((r for r in rows if r and r[0] == "Address"), None)
+    if hdr:
+        ix = {h: i for i, h in enumerate(hdr)}
+        byop, samp, recs, tot = collections.Counter(), collections.Counter(), [], 0
+        for r in rows:
+            if len(r) <= ix["Instructions Executed"] or r[0] == "Address":
+                continue
+            try:
+                n = int(r[ix["Instructions Executed"]]); sm = int(r[ix["# Samples"]])
+            except ValueError:
+                continue
+            toks = r[1].strip().split()
+            if not toks:
+                continue
+            op = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+            byop[op] += n; samp[op] += sm; tot += n
+            recs.append((n, sm, r[1].strip()))
+        ts = sum(samp.values()) or 1
+        print(f"## SASS opcodes: {tot} warp instructions, {ts} samples")
+        for op, n in byop.most_common(top):
+            print(f"{op:12s} inst {100 * n / max(tot, 1):5.1f}%  samples {100 * samp[op] / ts:5.1f}%")
+        print("## most-sampled SASS instructions")
+        for n, sm, t in sorted(recs, key=lambda x: -x[1])[:top]:
+            print(f"samples {100 * sm / ts:5.1f}%  executed {n:9d}  {t[:100]}")
