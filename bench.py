@@ -108,6 +108,10 @@ def cpu_threads():
     return max(1, min(os.cpu_count() or 1, 32))
 
 
+WORKLOAD = ("MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, bs 16/GPU, 512x512x3, 21 classes "
+            "(BASELINE configs[1]); random-init weights")
+
+
 def cpu_train_sample(B, steps, warmup, seed=0):
     """The oracle's training step (torch-CPU restatement + autograd + Keras Adam) on B images per step."""
     from oracle import network as N
@@ -143,9 +147,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, 512x512x3, 21 classes "
-                               "(configs[1]); CPU arm steps on a bounded sample of 2 images",
-                   "parallelism": "host threads"},
+        # the measured arm's config (same workload / global batch); the CPU steps on a bounded sample of it
+        "config": {"workload": WORKLOAD, "global_batch": max(1, args.gpus) * PER_GPU_BATCH,
+                   "parallelism": f"dp{max(1, args.gpus)}",
+                   "l2": "n/a (host arm)", "sample": f"{B} images/step on the host cores"},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{B} images/step x {steps} steps, torch-CPU fp32 restatement of the reference graph "
                                    "(Keras/TF cannot be installed here), all host threads"},
@@ -400,8 +405,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[args.dtype], "data": "synthetic",
-        "config": {"workload": "MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, bs 16/GPU, 512x512x3, 21 classes "
-                               "(BASELINE configs[1]); random-init weights",
+        "config": {"workload": WORKLOAD,
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "no flush needed: per-step activation working set (~7 GB) >> 126 MB L2",
                    "loss_after": final_loss},
