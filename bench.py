@@ -70,7 +70,42 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index, self.samples, self._stop, self.th = index, [], threading.Event(), None
 
+    @staticmethod
+    def _nvml_sample(nv, h):
+        """One sample through NVML in the column order of Q (strings, like nvidia-smi's csv)."""
+        act = lambda bit: "Active" if bit else "Not Active"   # noqa: E731
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = 0.0
+        return [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                f"{pw:.1f}", act(r & 0x8), act(r & 0x40), act(r & 0x20), act(r & 0x4)]
+
     def _run(self):
+        # NVML answers in well under a millisecond, so a 0.2 s timed region gets tens of samples; nvidia-smi (one
+        # process per sample, ~0.1-0.2 s each) stays as the fallback when pynvml or the NVML library is unavailable
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            phys = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis and all(t.strip().isdigit() for t in vis.split(",")) and self.index < len(vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml_sample(nv, h)                              # probe once before committing to this path
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(self._nvml_sample(nv, h))
+                except Exception:
+                    pass
+                self._stop.wait(0.01)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
