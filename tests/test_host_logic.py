@@ -131,3 +131,74 @@ def test_engine_requires_cuda_and_bad_input_shape():
     w2, b2 = e.get_layer_weights(e.head_conv)
     assert np.array_equal(w, w2) and np.array_equal(b, b2)
     assert not np.array_equal(e.head_conv.params[1].data.numpy(), b)       # stored permuted
+
+
+def test_keras_callbacks_follow_keras_224_rules(tmp_path):
+    """The notebook's callbacks (segmentation.ipynb cell 7: ModelCheckpoint(save_best_only, save_weights_only),
+    ReduceLROnPlateau, EarlyStopping, TensorBoard) against the Keras 2.2.4 rules, driven with a stub model."""
+    import json
+    from deeplab_b200.model import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau, TensorBoard
+
+    class Opt:
+        lr = 1e-3
+
+    class Stub:
+        def __init__(self):
+            self.optimizer, self.saved, self.stop_training = Opt(), [], False
+
+        def save_weights(self, path):
+            self.saved.append(path)
+
+        def set_lr(self, lr):
+            self.optimizer.lr = lr
+
+    # ModelCheckpoint: 'Jaccard' in the monitor name -> mode max (auto); saves only on improvement; formats the path
+    m = Stub()
+    ck = ModelCheckpoint(str(tmp_path / "w.{epoch:02d}-{val_Jaccard:.2f}.h5"), monitor="val_Jaccard", save_best_only=True,
+                         save_weights_only=True)
+    ck.set_model(m)
+    for ep, v in enumerate([0.30, 0.25, 0.41, 0.41, float("nan"), 0.50]):
+        ck.on_epoch_end(ep, {"val_Jaccard": v, "val_loss": 1.0})
+    assert [os.path.basename(p) for p in m.saved] == ["w.01-0.30.h5", "w.03-0.41.h5", "w.06-0.50.h5"]
+    # ... and mode min for a loss
+    m = Stub()
+    ck = ModelCheckpoint(str(tmp_path / "l.h5"), monitor="val_loss", save_best_only=True)
+    ck.set_model(m)
+    for ep, v in enumerate([1.0, 1.2, 0.9]):
+        ck.on_epoch_end(ep, {"val_loss": v})
+    assert len(m.saved) == 2
+    # without save_best_only every epoch is written
+    m = Stub()
+    ck = ModelCheckpoint(str(tmp_path / "e{epoch}.h5"))
+    ck.set_model(m)
+    for ep in range(3):
+        ck.on_epoch_end(ep, {})
+    assert len(m.saved) == 3
+
+    # ReduceLROnPlateau(monitor='val_loss', factor=0.2, patience=2, min_lr=1e-5): improvement = cur < best - min_delta
+    m = Stub()
+    rl = ReduceLROnPlateau(monitor="val_loss", factor=0.2, patience=2, min_lr=1e-5, min_delta=1e-4)
+    rl.set_model(m)
+    lrs = []
+    for ep, v in enumerate([1.0, 0.99995, 1.1, 0.8, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9]):
+        rl.on_epoch_end(ep, {"val_loss": v})
+        lrs.append(m.optimizer.lr)
+    # epochs 1, 2 do not improve by min_delta -> reduce after epoch 2; 0.8 improves; then every 2 stale epochs
+    assert np.allclose(lrs[:4], [1e-3, 1e-3, 2e-4, 2e-4])
+    assert np.isclose(lrs[5], 4e-5) and np.isclose(lrs[7], 1e-5) and np.isclose(lrs[-1], 1e-5)   # clamped at min_lr
+
+    # EarlyStopping(patience=3): stops after 3 epochs without improvement
+    m = Stub()
+    es = EarlyStopping(monitor="val_loss", patience=3)
+    es.set_model(m)
+    stopped_at = None
+    for ep, v in enumerate([1.0, 0.9, 0.95, 0.93, 0.91, 0.5]):
+        es.on_epoch_end(ep, {"val_loss": v})
+        if m.stop_training and stopped_at is None:
+            stopped_at = ep
+    assert stopped_at == 4
+
+    tb = TensorBoard(log_dir=str(tmp_path / "logs"))
+    tb.on_epoch_end(0, {"loss": 1.5, "val_Jaccard": 0.25})
+    rec = json.loads(open(tmp_path / "logs" / "scalars.jsonl").read().strip())
+    assert rec == {"epoch": 0, "loss": 1.5, "val_Jaccard": 0.25}
