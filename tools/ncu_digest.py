@@ -14,7 +14,12 @@ def run(*a):
     return subprocess.run(["ncu", "-i", rep, *a], capture_output=True, text=True).stdout
 
 
+import os
+if not os.path.exists(rep):
+    sys.exit(f"{rep}: no such report (gpurun_out/ is scratch -- re-run profiles/run_profile.sh)")
 rows = list(csv.reader(io.StringIO(run("--page", "raw", "--csv"))))
+if len(rows) < 3:
+    sys.exit(f"{rep}: ncu printed no kernel rows")
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
