@@ -13,6 +13,9 @@
  *     statistics and gradients of parameters are always fp32 (BN sums are fp64 accumulators).
  *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), performs no hidden
  *     synchronisation and no device allocation, and is CUDA-graph capturable.
+ *   - kernels are launched with programmatic stream serialization and execute griddepcontrol.wait before their
+ *     first global access: consecutive calls on one stream overlap launch latency, never data.  Kernels the CALLER
+ *     enqueues in between see ordinary stream order.  DLB_PDL=0 in the environment disables the attribute.
  *   - return value: 0 (DLB_OK) or a negative dlb_status; dlb_last_error() gives the thread-local message.
  */
 #ifndef DEEPLAB_B200_H_
@@ -134,6 +137,8 @@ int dlb_dw_conv_bwd(const dlb_dw_conv_bwd_params* p, void* stream);
 /* ---------------------------------------------------------------------------------------------------
  * Stem: Lambda(x/127.5 - 1) + Conv2D(32, 3, strides 2, 'same', no bias)  (deeplabv3p.py:270, :317-321;
  * Xception entry_flow_conv1_1 :283-284).  Input fp32 NHWC [B,H,W,3] in 0..255, TF-SAME padding (0,1).
+ * 16-bit dtypes run on warp-level tensor-core MMAs with the exact operand x - 127.5 (integer inputs assumed, as the
+ * reference's uint8 images are) and hi+lo split weights; DLB_F32 is the exact SIMT parity path.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   int B, H, W, Cout, Ho, Wo;
