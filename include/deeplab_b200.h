@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 1
+#define DLB_ABI_VERSION 2
 
 typedef enum { DLB_OK = 0, DLB_ERR_INVALID = -1, DLB_ERR_UNSUPPORTED = -2, DLB_ERR_CUDA = -3 } dlb_status;
 typedef enum { DLB_F16 = 0, DLB_BF16 = 1, DLB_F32 = 2 } dlb_dtype;
@@ -273,8 +273,10 @@ typedef struct {
   float* dlogits; double* loss_sum; double* wcount; uint8_t* argmax;
 } dlb_softmax_ce_params;
 int dlb_resize_softmax_ce(const dlb_softmax_ce_params* p, void* stream);
-/* counts sample weights != 0 -> *grad_scale = 1 / (n_pix_total * mean(sw != 0)) = 1/#(sw != 0)  */
-int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_scale_dev, double* wcount, void* stream);
+/* counts sample weights != 0 -> *grad_scale = loss_scale / (n_pix_total * mean(sw != 0)) = loss_scale / #(sw != 0);
+ * loss_scale = the static factor x loss_scale_state[0] (the dynamic fp16 scale, see dlb_adam_step; may be NULL) */
+int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_scale_dev, double* wcount, float loss_scale,
+                      const float* loss_scale_state, void* stream);
 
 /* Standalone Subpixel phase shift (subpixel.py:77-88): out[n, a*r+j, b*r+i, k] = in[n, a, b, k*r*r + i*r + j] */
 int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, const void* in, void* out, int inverse,
@@ -285,9 +287,17 @@ int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, const void* i
  *   lr_t = lr / (1 + decay*iter) * sqrt(1 - b2^t) / (1 - b1^t) ; p -= lr_t * m / (sqrt(v) + eps)
  * `step_dev` is a device int64 iteration counter (incremented by the kernel) so the step is graph-replayable.
  * grads are multiplied by grad_mult first (1/world_size after the NCCL sum).
+ * train_mask (optional, n floats): elements with mask 0 belong to layers with trainable=False -- Keras leaves them
+ *   out of the update entirely, so neither p nor m / v are touched (utils.py / ipynb:147-155 freeze regime).
+ * loss_scale_state (optional, device float[4] = {scale, good_steps, found_inf, growth_interval}): dynamic fp16 loss
+ *   scaling.  Gradients are divided by scale; if found_inf != 0 (set by dlb_grad_finite_check) the whole update and
+ *   the iteration counter are skipped and scale is halved, otherwise scale doubles every growth_interval good steps.
  * ------------------------------------------------------------------------------------------------- */
 int dlb_adam_step(int64_t n, float* param, const float* grad, float* m, float* v, int64_t* step_dev, float lr,
-                  float beta1, float beta2, float eps, float decay, float grad_mult, void* stream);
+                  float beta1, float beta2, float eps, float decay, float grad_mult, const float* train_mask,
+                  float* loss_scale_state, void* stream);
+/* sets loss_scale_state[2] = 1 if any of the n gradients (n % 4 == 0, 16-byte aligned) is inf / NaN */
+int dlb_grad_finite_check(int64_t n, const float* grad, float* loss_scale_state, void* stream);
 /* fp32 [K, N] master weight -> 16-bit W[K,N] and Wt[N,K] copies used by the GEMMs (either may be NULL) */
 int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_kn, void* w_nk, void* stream);
 /* The same for every 1x1 layer of the model in ONE launch (after each optimizer step).  `table` is a DEVICE array of

@@ -113,6 +113,7 @@ EXPORTS = [
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
     "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan", "dlb_label_weights",
+    "dlb_grad_finite_check",
 ]
 
 _lib = None
@@ -138,9 +139,10 @@ def lib() -> C.CDLL:
         L.dlb_global_avgpool_bwd.argtypes = [i32, i32, i32, i32, vp, vp, i32, vp]
         L.dlb_small_gemm.argtypes = [i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, f32, f32, vp]
         L.dlb_resize_softmax_fwd.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
-        L.dlb_ce_grad_scale.argtypes = [i64, vp, vp, vp, vp]
+        L.dlb_ce_grad_scale.argtypes = [i64, vp, vp, vp, f32, vp, vp]
         L.dlb_phase_shift.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
-        L.dlb_adam_step.argtypes = [i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp]
+        L.dlb_adam_step.argtypes = [i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp, vp, vp]
+        L.dlb_grad_finite_check.argtypes = [i64, vp, vp, vp]
         L.dlb_cast_weight.argtypes = [i32, i32, vp, i32, vp, vp, vp]
         L.dlb_cast.argtypes = [i64, i32, vp, i32, vp, vp]
         L.dlb_cast_weights_batched.argtypes = [i32, vp, i64, vp]

@@ -44,10 +44,18 @@ int num_sms() {
   return n;
 }
 
+// loss_scale_state (device float[4], optional): {scale, good_steps, found_inf, growth_interval} -- dynamic fp16 loss
+// scaling.  found_inf is set by grad_check_kernel; a step that saw a non-finite gradient leaves p / m / v and the
+// iteration counter untouched and halves the scale (scale_update_kernel).
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const long long* __restrict__ step, float lr, float b1, float b2,
-                            float eps, float decay, float gmult) {
+                            float eps, float decay, float gmult, const float* __restrict__ mask,
+                            const float* __restrict__ ls_state) {
   pdl_prologue();
+  if (ls_state) {
+    if (ls_state[2] != 0.f) return;           // overflow somewhere in this step's gradients: skip the update
+    gmult = gmult / ls_state[0];
+  }
   const long long it = *step;                 // iterations before this update
   const float t = static_cast<float>(it) + 1.f;
   float lr_t = lr;
@@ -55,6 +63,8 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
   lr_t = lr_t * (sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t)));
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // frozen (trainable=False) weights are not part of the update at all in Keras: no m / v decay, no step
+    if (mask && mask[i] == 0.f) continue;
     const float gi = g[i] * gmult;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -62,8 +72,30 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
   }
 }
-__global__ void step_inc_kernel(long long* step) {
-  pdl_prologue(); *step += 1; }
+__global__ void step_inc_kernel(long long* step, float* ls_state) {
+  pdl_prologue();
+  if (!ls_state) { *step += 1; return; }
+  if (ls_state[2] != 0.f) {                   // overflow: halve, retry with the next batch
+    ls_state[0] = fmaxf(ls_state[0] * 0.5f, 1.f);
+    ls_state[1] = 0.f; ls_state[2] = 0.f;
+  } else {
+    *step += 1;
+    ls_state[1] += 1.f;
+    if (ls_state[3] > 0.f && ls_state[1] >= ls_state[3]) { ls_state[0] = fminf(ls_state[0] * 2.f, 65536.f); ls_state[1] = 0.f; }
+  }
+}
+__global__ void __launch_bounds__(256) grad_check_kernel(long long n4, const float4* __restrict__ g, float* ls_state) {
+  pdl_prologue();
+  bool bad = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 q = g[i];
+    // x - x is 0 for finite x and NaN for +-inf / NaN
+    const float z = (q.x - q.x) + (q.y - q.y) + (q.z - q.z) + (q.w - q.w);
+    bad |= !(z == 0.f);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) ls_state[2] = 1.f;
+}
 
 template <typename T>
 __global__ void cast_weight_kernel(int K, int N, const float* __restrict__ w, T* __restrict__ w_kn, T* __restrict__ w_nk) {
@@ -131,16 +163,29 @@ extern "C" int dlb_device_ok(void) {
 
 extern "C" int dlb_adam_step(int64_t n, float* param, const float* grad, float* m, float* v, int64_t* step_dev,
                              float lr, float beta1, float beta2, float eps, float decay, float grad_mult,
-                             void* stream) {
+                             const float* train_mask, float* loss_scale_state, void* stream) {
   DLB_REQUIRE(n > 0 && param && grad && m && v && step_dev, "adam_step: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
-  launch_k(adam_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, 
-      n, param, grad, m, v, reinterpret_cast<const long long*>(step_dev), lr, beta1, beta2, eps, decay, grad_mult);
-  launch_k(step_inc_kernel, 1, 1, 0, st, reinterpret_cast<long long*>(step_dev));
+  launch_k(adam_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st,
+      n, param, grad, m, v, reinterpret_cast<const long long*>(step_dev), lr, beta1, beta2, eps, decay, grad_mult,
+      train_mask, static_cast<const float*>(loss_scale_state));
+  launch_k(step_inc_kernel, 1, 1, 0, st, reinterpret_cast<long long*>(step_dev), loss_scale_state);
   g_launches += 2;
   return check_launch("adam_kernel");
+}
+
+extern "C" int dlb_grad_finite_check(int64_t n, const float* grad, float* loss_scale_state, void* stream) {
+  DLB_REQUIRE(n > 0 && n % 4 == 0 && grad && loss_scale_state, "grad_finite_check: bad arguments (n must be a multiple of 4)");
+  DLB_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad_finite_check: grad must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  launch_k(grad_check_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, static_cast<long long>(n / 4),
+           reinterpret_cast<const float4*>(grad), loss_scale_state);
+  g_launches++;
+  return check_launch("grad_check_kernel");
 }
 
 extern "C" int dlb_cast_weight(int K, int N, const float* w, int dtype, void* w_kn, void* w_nk, void* stream) {

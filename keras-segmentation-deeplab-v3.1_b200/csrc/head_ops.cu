@@ -272,11 +272,13 @@ __global__ void count_nonzero_kernel(long long n, const float* sw, double* count
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(count, static_cast<double>(s_cnt));
 }
-__global__ void grad_scale_kernel(long long n, int has_sw, double* count, float* grad_scale) {
+__global__ void grad_scale_kernel(long long n, int has_sw, double* count, float* grad_scale, float loss_scale,
+                                  const float* ls_state) {
   pdl_prologue();
   if (!has_sw) *count = static_cast<double>(n);
   const double c = *count;
-  *grad_scale = c > 0.0 ? static_cast<float>(1.0 / c) : 0.f;
+  const double ls = static_cast<double>(loss_scale) * (ls_state ? static_cast<double>(ls_state[0]) : 1.0);
+  *grad_scale = c > 0.0 ? static_cast<float>(ls / c) : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,22 +467,19 @@ extern "C" int dlb_resize_softmax_ce(const dlb_softmax_ce_params* p, void* strea
   CeArgs a{p->B, p->h, p->w, p->ldl, p->H, p->W, p->H / p->h, p->logits, p->labels, p->sample_w,
            p->grad_scale_dev, p->dlogits, p->loss_sum, p->argmax};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (p->C) {
-    case 21: return launch_ce<21>(a, st);
-    case 2: return launch_ce<2>(a, st);
-    case 3: return launch_ce<3>(a, st);
-    case 4: return launch_ce<4>(a, st);
-    case 5: return launch_ce<5>(a, st);
-    case 8: return launch_ce<8>(a, st);
-    case 19: return launch_ce<19>(a, st);
+  switch (p->C) {     // the same 2..24 range as dlb_resize_softmax_fwd: create_seg_model(n=...) accepts any class count
+#define CASE(CC) case CC: return launch_ce<CC>(a, st);
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+    CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
+#undef CASE
     default:
-      set_last_error("resize_softmax_ce: classes=%d not instantiated", p->C);
+      set_last_error("resize_softmax_ce: classes=%d unsupported (2..24)", p->C);
       return DLB_ERR_UNSUPPORTED;
   }
 }
 
 extern "C" int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_scale_dev, double* wcount,
-                                 void* stream) {
+                                 float loss_scale, const float* loss_scale_state, void* stream) {
   DLB_REQUIRE(grad_scale_dev && wcount && n > 0, "ce_grad_scale: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DLB_CUDA(cudaMemsetAsync(wcount, 0, sizeof(double), st));
@@ -490,7 +489,7 @@ extern "C" int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_s
     launch_k(count_nonzero_kernel, static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st, n, sample_w, wcount);
     g_launches++;
   }
-  launch_k(grad_scale_kernel, 1, 1, 0, st, n, sample_w != nullptr, wcount, grad_scale_dev);
+  launch_k(grad_scale_kernel, 1, 1, 0, st, n, sample_w != nullptr, wcount, grad_scale_dev, loss_scale, loss_scale_state);
   g_launches++;
   return check_launch("grad_scale_kernel");
 }

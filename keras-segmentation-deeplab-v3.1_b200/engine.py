@@ -99,13 +99,31 @@ class Engine:
         self._alloc_params(seed)
         self._ws: Dict[Tuple, dict] = {}
         self._graphs: Dict[Tuple, object] = {}
-        self.loss_scale = 1024.0 if compute_dtype == torch.float16 else 1.0
+        # fp16: dynamic loss scaling on the device (dlb_adam_step): {scale, good steps, found_inf, growth interval}.
+        # Starts at 1024 (never overflowed on this network), halves on an inf/NaN gradient (that update is skipped),
+        # doubles every 2000 clean steps.  bf16 / fp32 do not scale.
+        self.ls_state = (torch.tensor([1024.0, 0.0, 0.0, 2000.0], device=self.device)
+                         if compute_dtype == torch.float16 else None)
         self.dropout_rate = 0.1
         self.dropout_seed = 0x5EED + seed
         self.adam_cfg = dict(lr=7e-4, beta1=0.9, beta2=0.999, eps=1e-8, decay=1e-6)
         self.world_size = 1
         self.grad_hook = None                  # called with the flat grad buffer before the optimizer step
         self._weights_dirty = True
+        self._any_frozen = False
+
+    @property
+    def loss_scale(self) -> float:
+        """the factor currently folded into d loss / d logits (reads the device state: a host sync)."""
+        return float(self.ls_state[0].item()) if self.ls_state is not None else 1.0
+
+    @loss_scale.setter
+    def loss_scale(self, v: float):
+        if self.ls_state is None:
+            if float(v) != 1.0:
+                raise ValueError("loss scaling is an fp16 feature")
+            return
+        self.ls_state[0] = float(v)
 
     # ------------------------------------------------------------------------------------------------
     # graph spec (weighted layers in Keras model order)
@@ -296,6 +314,7 @@ class Engine:
         for p in rec.params:
             if p.trainable_kind:
                 self.train_mask[p.offset:p.offset + p.size] = 1.0 if flag else 0.0
+        self._any_frozen = any(not r.trainable for r in self.layers)
         self._graphs.clear()
 
     def refresh_weight_copies(self):
@@ -548,9 +567,7 @@ class Engine:
         """softmax + void-ignoring weighted CE (utils.py:127-130) and d loss / d logits, loss-scaled."""
         npix = B * self.H * self.W
         sw = ws["sample_w"] if use_sample_w else None
-        ops.ce_grad_scale(npix, sw, ws["grad_scale"], ws["wcount"])
-        if self.loss_scale != 1.0:
-            ws["grad_scale"].mul_(self.loss_scale)       # device-side scalar op, graph-capturable
+        ops.ce_grad_scale(npix, sw, ws["grad_scale"], ws["wcount"], 1.0, self.ls_state)
         ops.fill_zero(ws["loss_sum"])
         if self.head != "subpixel":
             ops.fill_zero(ws["dlogits"])
@@ -716,10 +733,12 @@ class Engine:
 
     def _update_body(self):
         c = self.adam_cfg
-        self.grads.mul_(self.train_mask)       # frozen layers (trainable=False) receive no update
+        if self.ls_state is not None:
+            ops.grad_finite_check(self.grads, self.ls_state)
+        # frozen layers (trainable=False) are left out of the update inside the kernel: p, m and v untouched
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, self.adam_step, lr=c["lr"], beta1=c["beta1"],
-                      beta2=c["beta2"], eps=c["eps"], decay=c["decay"],
-                      grad_mult=1.0 / (self.loss_scale * self.world_size))
+                      beta2=c["beta2"], eps=c["eps"], decay=c["decay"], grad_mult=1.0 / self.world_size,
+                      train_mask=self.train_mask if self._any_frozen else None, loss_scale_state=self.ls_state)
         self.refresh_weight_copies()
 
     def _capture(self, fn):

@@ -244,8 +244,8 @@ def load_keras_weights(path: str):
 # writer (same subset)
 # ---------------------------------------------------------------------------------------------------------
 class _Writer:
-    """Sequential HDF5 writer: superblock v0, one symbol-table group per layer (B-tree with a single leaf chain),
-    contiguous float32 datasets, fixed-length string attributes."""
+    """Sequential HDF5 writer: superblock v0, one symbol-table group per layer (v1 B-tree, as many levels as the
+    number of entries needs), contiguous float32 datasets, fixed-length string attributes."""
 
     def __init__(self):
         self.buf = bytearray(b"\0" * 96)    # superblock (56) + root symbol table entry (40)
@@ -286,6 +286,8 @@ class _Writer:
         pad8 = lambda b: b + b"\0" * ((-len(b)) % 8)
         body = struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(ds)) + pad8(nm) + pad8(dt) + pad8(ds)
         body += b"".join(v.ljust(sz, b"\0") for v in values)
+        if len(body) > 65528:      # object-header messages carry a 16-bit size (Keras splits such attributes into chunks)
+            raise ValueError(f"attribute {name!r} needs {len(body)} bytes; HDF5 object-header messages hold < 64 KiB")
         return self._msg(0x0C, body)
 
     def _object_header(self, msgs: List[bytes]) -> int:
@@ -326,15 +328,37 @@ class _Writer:
             body += b"\0" * (40 * (2 * K_LEAF - len(chunk)))
             snods.append(self._alloc(body))
             keys.append(offs[chunk[-1]] if chunk else 0)
+        # B-tree v1 over the symbol nodes: up to 2 * K_INT children per node; more than 32 symbol nodes (> 256 entries,
+        # e.g. the 299 layers of the Xception model) get further levels.  A node is
+        #   "TREE" type(0) level used left right  key0 child0 key1 ... child(n-1) key(n)
+        # where key(i+1) is the heap offset of the largest name below child i and key0 that of the smallest bound.
         K_INT = 16
-        if len(snods) > 2 * K_INT:
-            raise ValueError("group too large for a single-level B-tree")
-        tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF)
-        tree += struct.pack("<Q", keys[0])
-        for s, k in zip(snods, keys[1:]):
-            tree += struct.pack("<QQ", s, k)
-        tree += b"\0" * (16 * (2 * K_INT - len(snods)))
-        tree_addr = self._alloc(tree)
+        UNDEF = 0xFFFFFFFFFFFFFFFF
+        level = 0
+        nodes = [(a, keys[i], keys[i + 1]) for i, a in enumerate(snods)]      # (address, low key, high key)
+        while True:
+            groups = [nodes[i:i + 2 * K_INT] for i in range(0, len(nodes), 2 * K_INT)]
+            size = 24 + 8 + 16 * 2 * K_INT
+            self._align()
+            base = len(self.buf)
+            addrs = [base + i * ((size + 7) // 8 * 8) for i in range(len(groups))]
+            out = []
+            for gi, grp in enumerate(groups):
+                left = addrs[gi - 1] if gi > 0 else UNDEF
+                right = addrs[gi + 1] if gi + 1 < len(groups) else UNDEF
+                tree = b"TREE" + struct.pack("<BBHQQ", 0, level, len(grp), left, right)
+                tree += struct.pack("<Q", grp[0][1])
+                for a, _, hi in grp:
+                    tree += struct.pack("<QQ", a, hi)
+                tree += b"\0" * (16 * (2 * K_INT - len(grp)))
+                got = self._alloc(tree)
+                assert got == addrs[gi]
+                out.append((got, grp[0][1], grp[-1][2]))
+            nodes = out
+            level += 1
+            if len(nodes) == 1:
+                break
+        tree_addr = nodes[0][0]
         msgs = [self._msg(0x11, struct.pack("<QQ", tree_addr, heap_addr))] + attr_msgs
         return self._object_header(msgs), tree_addr, heap_addr
 

@@ -233,9 +233,9 @@ def resize_softmax_ce(logits, C_, H, W, labels, sample_w, grad_scale, dlogits, l
     L.check(L.lib().dlb_resize_softmax_ce(C.byref(p), L.stream_ptr()), "resize_softmax_ce")
 
 
-def ce_grad_scale(n: int, sample_w, grad_scale, wcount):
-    L.check(L.lib().dlb_ce_grad_scale(n, L.ptr(sample_w), grad_scale.data_ptr(), wcount.data_ptr(), L.stream_ptr()),
-            "ce_grad_scale")
+def ce_grad_scale(n: int, sample_w, grad_scale, wcount, loss_scale: float = 1.0, loss_scale_state=None):
+    L.check(L.lib().dlb_ce_grad_scale(n, L.ptr(sample_w), grad_scale.data_ptr(), wcount.data_ptr(), float(loss_scale),
+                                      L.ptr(loss_scale_state), L.stream_ptr()), "ce_grad_scale")
 
 
 def phase_shift(x: torch.Tensor, out: torch.Tensor, r: int, inverse: bool = False):
@@ -247,10 +247,17 @@ def phase_shift(x: torch.Tensor, out: torch.Tensor, r: int, inverse: bool = Fals
     return out
 
 
-def adam_step(param, grad, m, v, step_dev, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, decay=0.0, grad_mult=1.0):
+def adam_step(param, grad, m, v, step_dev, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, decay=0.0, grad_mult=1.0,
+              train_mask=None, loss_scale_state=None):
     L.check(L.lib().dlb_adam_step(param.numel(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                  step_dev.data_ptr(), lr, beta1, beta2, eps, decay, grad_mult, L.stream_ptr()),
-            "adam_step")
+                                  step_dev.data_ptr(), lr, beta1, beta2, eps, decay, grad_mult, L.ptr(train_mask),
+                                  L.ptr(loss_scale_state), L.stream_ptr()), "adam_step")
+
+
+def grad_finite_check(grad, loss_scale_state):
+    """loss_scale_state[2] = 1 if any gradient is inf / NaN (dynamic fp16 loss scaling, see dlb_adam_step)."""
+    L.check(L.lib().dlb_grad_finite_check(grad.numel(), grad.data_ptr(), loss_scale_state.data_ptr(), L.stream_ptr()),
+            "grad_finite_check")
 
 
 def cast_weight(w: torch.Tensor, K: int, N: int, w_kn=None, w_nk=None):

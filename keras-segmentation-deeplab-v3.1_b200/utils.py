@@ -40,20 +40,17 @@ def _as_cuda(t):
 
 
 def sparse_crossentropy_ignoring_last_label(y_true, y_pred):
-    """utils.py:127-130 -> per-pixel loss [B, T].  Runs the CE kernel on log-probabilities (softmax of log p == p)."""
+    """utils.py:127-130 -> per-pixel loss [B, T] on CUDA tensors.
+
+    Convenience entry point for user code that evaluates the loss on its own probabilities (a gather + log, a few
+    torch device ops).  The training step never calls it: there the same definition is fused with the bilinear
+    resize, the softmax and the backward pass in dlb_resize_softmax_ce (head_ops.cu)."""
     y_true, y_pred = _as_cuda(y_true), _as_cuda(y_pred)
-    B, T, Cn = y_pred.shape
-    logits = torch.log(y_pred.clamp_min(1e-30)).view(B * T, 1, 1, Cn).contiguous()
-    loss = torch.empty(B * T, device="cuda", dtype=torch.float64)
-    gs = torch.zeros(1, device="cuda")
-    dlog = torch.empty_like(logits)
-    out = torch.empty(B, T, device="cuda")
-    # one launch per call with per-pixel accumulation would need T accumulators; evaluate pixel losses via probs
+    Cn = y_pred.shape[-1]
     lab = y_true[:, :, 0].long()
     valid = (lab >= 0) & (lab < Cn)
     p = (y_pred / y_pred.sum(-1, keepdim=True)).gather(2, lab.clamp(0, Cn - 1).unsqueeze(-1)).squeeze(-1)
-    out = torch.where(valid, -torch.log(p.clamp(1e-7, 1 - 1e-7)), torch.zeros_like(p))
-    return out
+    return torch.where(valid, -torch.log(p.clamp(1e-7, 1 - 1e-7)), torch.zeros_like(p))
 
 
 def _confusion(y_true, y_pred):
@@ -251,18 +248,20 @@ def calculate_iou(model, nb_classes=21, data=None, batch_size=16):
     if data is None:
         raise ValueError("calculate_iou needs data=(X, label): the notebook's global SegClass generator is not part of this package")
     X, label = data
+    e = model.engine
+    if nb_classes != e.n_out:
+        raise ValueError(f"nb_classes={nb_classes} but the model predicts {e.n_out} classes")
     X = torch.as_tensor(X)
     label = torch.as_tensor(label).reshape(X.shape[0], -1)
     conf = torch.zeros(nb_classes + 1, nb_classes, device="cuda", dtype=torch.int64)
     for i in range(0, X.shape[0], batch_size):
-        xb = X[i:i + batch_size]
-        probs = model.predict_on_batch(xb)
-        probs = _as_cuda(probs).reshape(xb.shape[0], -1, nb_classes)
-        Bb, T, Cn = probs.shape
-        am = torch.empty(Bb, T, device="cuda", dtype=torch.uint8)
-        ops.resize_softmax_fwd(torch.log(probs.clamp_min(1e-30)).view(Bb, T, 1, Cn).contiguous(), Cn, T, 1, None, am)
-        cb = torch.zeros(Bb, Cn + 1, Cn, device="cuda", dtype=torch.int64)
-        ops.confusion(label[i:i + batch_size].float().cuda().contiguous().view(Bb, T, 1), am, Cn, cb)
+        xb = X[i:i + batch_size].to(torch.float32)
+        Bb = xb.shape[0]
+        ws = e.workspace(Bb, False)
+        ws["img"].copy_(xb, non_blocking=True)
+        am = e.forward_infer(ws["img"], want_probs=False)          # argmax straight from the head kernel, on the device
+        cb = torch.zeros(Bb, nb_classes + 1, nb_classes, device="cuda", dtype=torch.int64)
+        ops.confusion(label[i:i + batch_size].float().cuda().contiguous().view(Bb, -1, 1), am, nb_classes, cb)
         conf += cb.sum(0)
     c = conf[:nb_classes].cpu().numpy().astype(np.float64)     # void row dropped (reference: `if l == nb_classes: continue`)
     return np.roll(np.roll(c, -1, axis=0), -1, axis=1)          # conf_m[l-1, p-1]

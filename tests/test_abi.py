@@ -27,7 +27,8 @@ def test_header_symbols_are_exported(lib):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
-    assert L.dlb_version() == 1
+    m = re.search(r"#define\s+DLB_ABI_VERSION\s+(\d+)", open(os.path.join(ROOT, "include", "deeplab_b200.h")).read())
+    assert L.dlb_version() == int(m.group(1))
     assert L.dlb_launch_count() == 0
 
 

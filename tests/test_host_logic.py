@@ -32,6 +32,30 @@ def test_h5_writer_roundtrip(tmp_path):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n_layers", [257, 300, 1100])
+def test_h5_writer_multi_level_btree(tmp_path, n_layers):
+    """More than 256 entries per group need a second B-tree level (round-1 advice: the 299-layer Xception model could
+    not be saved); both the product's reader and the oracle's independent reader must get every layer back."""
+    import deeplab_b200  # noqa: F401
+    from deeplab_b200 import keras_h5 as P
+    from oracle import hdf5_reader as O
+    rng = np.random.RandomState(n_layers)
+    layers = OrderedDict()
+    for i in range(n_layers):
+        nm = "unit_%d_%d" % (rng.randint(0, 10 ** 6), i)
+        layers[nm] = [(nm + "/kernel:0", rng.randn(1, 1, 3, 2).astype(np.float32)),
+                      (nm + "/bias:0", rng.randn(2).astype(np.float32))] if i % 4 else []
+    path = str(tmp_path / "big.h5")
+    P.save_keras_weights(path, layers)
+    for reader in (P, O):
+        got, attrs = reader.load_keras_weights(path)
+        assert list(got) == list(layers)
+        for k, ws in layers.items():
+            assert [n for n, _ in got[k]] == [n for n, _ in ws]
+            for (_, a), (_, b) in zip(got[k], ws):
+                assert np.array_equal(a, b)
+
+
 def test_reader_roundtrips_reference_file_through_writer(tmp_path):
     import deeplab_b200  # noqa: F401
     from deeplab_b200 import keras_h5

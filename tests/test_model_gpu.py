@@ -216,7 +216,7 @@ def test_gradients_fp32_match_oracle_autograd():
     loss, grads, _, _ = T.loss_and_grads(W, tx, ty, tsw, dtype=torch.float64)
     _, g32, _, _ = T.loss_and_grads(W, tx, ty, tsw, dtype=torch.float32)
     assert abs(ws["loss_sum"].item() / ws["wcount"].item() - loss.item()) < 1e-4 * abs(loss.item())
-    # The forward pass matches the oracle to ~1e-5 (tools/debug_bwd.py), and every backward kernel matches an fp64
+    # The forward pass matches the oracle to ~1e-5, and every backward kernel matches an fp64
     # recomputation from its own inputs, but with 2 images at 64x64 the deep BatchNorms see only 128 samples per
     # channel: one ReLU6 mask that flips because z differs in the 6th digit moves a per-channel sum by ~1 %.  So:
     # strict max-norm check right behind the loss, direction check on the whole gradient, L2 check per tensor.
@@ -309,7 +309,7 @@ def test_train_step_16bit_close_to_oracle(dtype):
     assert abs(got - loss.item()) < (2e-2 if dtype == "float16" else 6e-2) * abs(loss.item())
     # Layers right behind the loss are well conditioned.  Deeper weight gradients are sums over pixels of
     # activation x (batch-norm-projected gradient): the projection removes the dominant (mean) component, so 16-bit
-    # storage rounding of the operands is amplified there (tools/diag_grads.py prints the per-layer picture); they
+    # storage rounding of the operands is amplified there; they
     # are covered by the flat-gradient direction instead.
     for name in ["conv_upsample", "concat_projection", "aspp0"]:
         p = e._by_name[name].params[0]
@@ -325,7 +325,7 @@ def test_train_step_16bit_close_to_oracle(dtype):
                 ref.append(grads[rec.name][i].double().flatten())
     flat, ref = torch.cat(flat), torch.cat(ref)
     cos = torch.dot(flat, ref) / (flat.norm() * ref.norm())
-    assert cos > (0.97 if dtype == "float16" else 0.75), cos.item()     # measured 0.99 / 0.83-0.92 (tools/diag_grads.py)
+    assert cos > (0.97 if dtype == "float16" else 0.75), cos.item()     # measured 0.99 / 0.83-0.92
 
 
 def test_graph_replay_equals_eager_and_mious_match():

@@ -193,3 +193,127 @@ def test_calculate_iou_conf_matches_literal_loop():
         if l < C and p < C:
             conf[l - 1, p - 1] += 1
     assert np.array_equal(R.calculate_iou_conf(pred, lab, C), conf)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# oracle independence (round-1 review): a second restatement written without anything shared with oracle/network.py,
+# an oracle-owned HDF5 reader, and a gradient check that does not use autograd.
+# ------------------------------------------------------------------------------------------------------------------
+def _np_weights(W):
+    return {k: [t.numpy() for t in v] for k, v in W.items()}
+
+
+def _dbl(W):
+    return {k: [t.double() for t in v] for k, v in W.items()}
+
+
+@pytest.mark.parametrize("net,training", [("original", False), ("original", True), ("subpixel", False), ("subpixel", True)])
+def test_second_restatement_agrees_mobilenetv2(net, training):
+    """oracle/network.py (torch NHWC, F.conv2d) vs oracle/network_np.py (numpy fp64 NCHW, tap loops, direct-index
+    resize / phase shift) on a non-square input: fp64 round-off level."""
+    from oracle import network as N
+    from oracle import network_np as NP
+    head = "conv_upsample" if net == "original" else "subpixel_1"
+    W = N.random_mobilenetv2_weights(seed=3, head=head, head_filters=21 * 64 if net == "subpixel" else 21)
+    x = np.random.RandomState(1).randint(0, 256, (2, 64, 96, 3)).astype(np.float32)
+    with torch.no_grad():
+        lg, pr, ctx = N.deeplabv3_forward(_dbl(W), torch.from_numpy(x).double(), net=net, training=training)
+    net2 = NP.Net(_np_weights(W), training=training)
+    lg2, pr2 = net2.forward(x, net=net)
+    assert np.abs(lg.numpy() - lg2).max() <= 1e-9 * np.abs(lg2).max()
+    assert np.abs(pr.numpy() - pr2).max() <= 1e-10
+    if training:      # batch statistics feeding the moving averages
+        for name, (mu, var, cnt) in ctx.bn_batch_stats.items():
+            mu2, var2, cnt2 = net2.batch_stats[name]
+            assert cnt == cnt2
+            assert np.abs(mu.numpy() - mu2).max() <= 1e-9 * max(1.0, np.abs(mu2).max()), name
+            assert np.abs(var.numpy() - var2).max() <= 1e-9 * max(1.0, np.abs(var2).max()), name
+
+
+@pytest.mark.parametrize("OS", [8, 16])
+def test_second_restatement_agrees_xception(OS):
+    """Xception path (explicit-padding stride-2 SepConvs, 1x1 stride-2 shortcuts, atrous ASPP, decoder)."""
+    from oracle import network as N
+    from oracle import network_np as NP
+    W = N.random_xception_weights(seed=5)
+    x = np.random.RandomState(2).randint(0, 256, (1, 64, 96, 3)).astype(np.float32)
+    with torch.no_grad():
+        lg, pr, _ = N.deeplabv3_forward(_dbl(W), torch.from_numpy(x).double(), backbone="xception", OS=OS)
+    lg2, pr2 = NP.Net(_np_weights(W)).forward(x, backbone="xception", OS=OS)
+    assert np.abs(lg.numpy() - lg2).max() <= 1e-9 * np.abs(lg2).max()
+    assert np.abs(pr.numpy() - pr2).max() <= 1e-10
+
+
+def test_second_restatement_reproduces_golden_logits_at_512():
+    """config 1 at its own size through the second restatement and the oracle-owned reader: the committed golden logits
+    (made by network.py + the product's reader) are reproduced by code that shares neither."""
+    from oracle import network_np as NP
+    from oracle.hdf5_reader import load_keras_weights
+    g = np.load(os.path.join(GOLD, "golden_mnv2.npz"))
+    layers, _ = load_keras_weights(os.path.join(GOLD, "mobilenetv2_original.h5"))
+    W = {k: [a for _, a in v] for k, v in layers.items() if v}
+    x = np.random.RandomState(0).randint(0, 256, (1, 512, 512, 3)).astype(np.float32)
+    lg, pr = NP.Net(W).forward(x, head="conv_upsample")
+    assert np.abs(lg - g["logits"]).max() < 1e-4 * np.abs(g["logits"]).max()      # goldens are fp32
+    assert (pr.argmax(-1).reshape(512, 512) == g["argmax"]).mean() > 0.9999
+
+
+def test_autograd_gradient_matches_finite_differences_of_second_restatement():
+    """Backward oracle pinned without autograd: d loss / d eps along random parameter directions, by central finite
+    differences of the fp64 numpy restatement's training loss, equals <autograd gradient of network.py, direction>."""
+    from oracle import network as N
+    from oracle import network_np as NP
+    from oracle import train as T
+    W = N.random_mobilenetv2_weights(seed=8, head="conv_upsample")
+    rng = np.random.RandomState(0)
+    B, H, Wd = 2, 32, 32
+    x = rng.randint(0, 256, (B, H, Wd, 3)).astype(np.float32)
+    y = rng.randint(0, 22, (B, H * Wd, 1)).astype(np.float32)           # label 21 = void
+    sw = rng.uniform(0.5, 2.0, (B, H * Wd)).astype(np.float32)
+    sw[rng.uniform(size=sw.shape) < 0.1] = 0.0
+    _, grads, _, _ = T.loss_and_grads(W, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw),
+                                      dtype=torch.float64)
+    Wn = _np_weights(W)
+    groups = [["Conv", "expanded_conv_depthwise", "expanded_conv_1_expand_BN"],
+              ["expanded_conv_7_depthwise", "expanded_conv_7_project", "expanded_conv_13_project_BN"],
+              ["aspp0", "image_pooling", "concat_projection", "conv_upsample", "image_pooling_BN"]]
+    for names in groups:
+        dirs, dot = {}, 0.0
+        for n in names:
+            for i, g in grads[n].items():
+                d = rng.standard_normal(Wn[n][i].shape)
+                d *= 1.0 / max(np.linalg.norm(d), 1e-12)
+                dirs[(n, i)] = d
+                dot += float((g.numpy().reshape(d.shape) * d).sum())
+        # the loss is piecewise smooth (about 10^5 ReLU6 kinks): a step of 1e-4 crosses enough of them to be off by
+        # tens of percent in the early layers; steps of 1e-8..1e-9 usually cross none and leave ~1e-7 of fp64
+        # round-off.  The intervals are nested, so the best of three steps is taken.
+        errs = []
+        for eps in (1e-8, 3e-9, 1e-9):
+            vals = []
+            for sgn in (+1, -1):
+                Wp = {k: [a.astype(np.float64).copy() for a in v] for k, v in Wn.items()}
+                for (n, i), d in dirs.items():
+                    Wp[n][i] += sgn * eps * d
+                vals.append(NP.training_loss(Wp, x, y, sw))
+            errs.append(abs((vals[0] - vals[1]) / (2 * eps) - dot))
+        assert min(errs) <= 1e-5 * abs(dot) + 2e-6, (names, errs, dot)
+
+
+def test_oracle_reader_is_independent_and_agrees_with_product_reader():
+    """oracle/hdf5_reader.py shares no code with deeplab_b200.keras_h5; both parse the reference's file identically."""
+    import inspect
+    import deeplab_b200  # noqa: F401
+    from deeplab_b200 import keras_h5 as P
+    from oracle import hdf5_reader as O
+    src = inspect.getsource(O)
+    assert "importlib" not in src and "deeplab_b200 import" not in src
+    path = os.path.join(GOLD, "mobilenetv2_original.h5")
+    lo, ao = O.load_keras_weights(path)
+    lp, ap = P.load_keras_weights(path)
+    assert list(lo) == list(lp)
+    for k in lo:
+        assert [n for n, _ in lo[k]] == [n for n, _ in lp[k]]
+        for (_, a), (_, b) in zip(lo[k], lp[k]):
+            assert a.dtype == b.dtype == np.float32 and np.array_equal(a, b)
+    assert ao["backend"] == ap["backend"] and ao["keras_version"] == ap["keras_version"]
