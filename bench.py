@@ -10,8 +10,9 @@ weights, BatchNorm batch statistics, Dropout(0.1), void-ignoring CE, Keras Adam 
 "step".  Weak scaling: 16 images per GPU.
 
 JSON line (one, from rank 0): see the task contract; `value` = device-resident inputs (CUDA-graph replay),
-`e2e` = the same step through model.train_on_batch with pinned HOST inputs (H2D inside the timed region) and a D2H
-read of the loss; `roofline` = the dominant kernel family of the step, timed live with CUDA events around every
+`e2e` = the same step through model.fit_generator fed NUMPY host batches (staging into pinned memory + H2D inside the
+timed region) and a D2H read of the loss and confusion counts; `sustained` = the device-resident step for >= 2 s with
+its clocks; `crf` = BASELINE config 5 (dense CRF ms/img, roofline, single-thread C baseline); `roofline` = the dominant kernel family of the step, timed live with CUDA events around every
 C-ABI launch of an eager step; `cpu_baseline` = the oracle (torch-CPU restatement, all host threads) on a bounded
 sample.
 """
@@ -34,7 +35,7 @@ import torch
 H = W = 512
 CLASSES = 21
 PER_GPU_BATCH = 16
-METRIC = "images/sec fwd+bwd @512x512 MobileNetV2 OS=16"
+METRIC = "images/sec fwd+bwd @512\u00d7512 MobileNetV2 OS=16, 1/2/4/8 GPU; CRF ms/img"      # BASELINE.json, verbatim
 
 
 def synthetic_batch(B, seed):
@@ -147,18 +148,39 @@ WORKLOAD = ("MobileNetV2 DeepLabV3+ 'original' head, fwd+bwd+Adam, bs 16/GPU, 51
             "(BASELINE configs[1]); random-init weights")
 
 
-def cpu_train_sample(B, steps, warmup, seed=0):
-    """The oracle's training step (torch-CPU restatement + autograd + Keras Adam) on B images per step."""
+def _config(world):
+    return {"workload": WORKLOAD, "global_batch": world * PER_GPU_BATCH, "parallelism": f"dp{world}",
+            "l2": "no flush needed: per-step activation working set (~7 GB) >> 126 MB L2"}
+
+
+def cpu_train_sample(B, steps, warmup, seed=0, micro=2):
+    """The oracle's training step (torch-CPU restatement + autograd + Keras Adam) on B images per step.  Autograd keeps
+    ~5.5 GB of activations per 512x512 image, so a step runs as B/micro micro-batches whose gradients are accumulated
+    before ONE Adam update (the arithmetic per image is that of the full-batch step; BatchNorm sees `micro` images)."""
     from oracle import network as N
+    from oracle import ref_ops as R
     from oracle import train as T
     torch.set_num_threads(cpu_threads())
     Wt = N.random_mobilenetv2_weights(seed=seed, head="conv_upsample", perturb_bn=False)
     x, y, sw = synthetic_batch(B, seed)
     xt, yt, swt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(sw)
-    state, it, times = None, 0, []
+    micro = min(micro, B)
+    state, it, times = {}, 0, []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        _, Wt, state = T.train_step(Wt, xt, yt, swt, net="original", iterations=it, adam_state=state, dtype=torch.float32)
+        acc = {}
+        for i in range(0, B, micro):
+            _, grads, _, _ = T.loss_and_grads(Wt, xt[i:i + micro], yt[i:i + micro], swt[i:i + micro], net="original",
+                                              dtype=torch.float32)
+            for name, d in grads.items():
+                for k, g in d.items():
+                    acc[(name, k)] = g * (micro / B) if (name, k) not in acc else acc[(name, k)] + g * (micro / B)
+        for (name, k), g in acc.items():
+            w = Wt[name][k]
+            m, v = state.get((name, k), (torch.zeros_like(w), torch.zeros_like(w)))
+            p_new, m, v = R.keras_adam(w, g, m, v, it, lr=7e-4, eps=1e-8, decay=1e-6)
+            state[(name, k)] = (m, v)
+            Wt[name][k] = p_new
         it += 1
         if s >= warmup:
             times.append(time.perf_counter() - t0)
@@ -169,30 +191,85 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 2
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 2))
-    # bound the run to a few minutes whatever K the driver passes
-    t_probe = cpu_train_sample(B, 1, 0)[0]
+    from oracle import ref_probe
+    B = PER_GPU_BATCH                      # the measured arm's per-GPU batch: one step = the same 16 images
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    # bound the run to a few minutes whatever K the driver passes: probe with one micro-batch
+    t_probe = cpu_train_sample(2, 1, 0)[0] * (B / 2)
     steps = max(1, min(steps, int(150.0 / max(t_probe, 1e-3))))
     times = cpu_train_sample(B, steps, warmup)
     ms = 1e3 * float(np.mean(times))
     v = B / (ms / 1e3)
     cores = cpu_threads()
+    sample = (f"{B} images/step (one GPU's share of the global batch) x {steps} steps (as {B // 2} micro-batches of 2 with gradient accumulation: autograd "
+              f"needs ~5.5 GB of host memory per image), torch-CPU fp32 restatement of the reference graph, "
+              f"{cores} of {os.cpu_count()} host threads; {ref_probe.summary()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        # the measured arm's config (same workload / global batch); the CPU steps on a bounded sample of it
-        "config": {"workload": WORKLOAD, "global_batch": max(1, args.gpus) * PER_GPU_BATCH,
-                   "parallelism": f"dp{max(1, args.gpus)}",
-                   "l2": "n/a (host arm)", "sample": f"{B} images/step on the host cores"},
-        "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
-                         "sample": f"{B} images/step x {steps} steps, torch-CPU fp32 restatement of the reference graph "
-                                   "(Keras/TF cannot be installed here), all host threads"},
+        # the measured arm's config, key for key (same workload / batch); what the host actually steps is in `sample`
+        "config": _config(max(1, args.gpus)),
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+# ------------------------------------------------------------------------------------------------ dense CRF (config 5)
+def crf_record(rank, world, dev, peaks, with_cpu=True):
+    """BASELINE config 5: 10 mean-field iterations on 1024x1024x21 unaries, batch 8 (sharded over the ranks: images are
+    independent, no collective).  ms/img = max-over-ranks device time / images; roofline on SURVEY 8(d)'s algorithmic
+    bytes (12*N*M + 72*N per iteration)."""
+    import scipy.ndimage as ndi
+    from deeplab_b200.utils import dense_crf
+    Hc = Wc = 1024
+    M, iters, Btot = 21, 10, 8
+    nb = max(1, Btot // world)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    logits = torch.randn(nb, M, Hc * Wc, device=dev, generator=g) * 3.0
+    un = -torch.log_softmax(logits, dim=1)
+    del logits
+    rng = np.random.RandomState(7 + rank)
+    base = ndi.gaussian_filter(rng.rand(Hc, Wc, 3), (8, 8, 0))
+    base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+    img = torch.from_numpy(np.stack([np.roll(base, 61 * b, axis=(0, 1)) for b in range(nb)])).to(dev)
+    for _ in range(2):
+        dense_crf(un, img, iters=iters)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        Q = dense_crf(un, img, iters=iters)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_img = t.item() / nb
+    n_img = nb * world
+    N_ = Hc * Wc
+    algo = iters * (12 * N_ * M + 72 * N_) + 92 * N_          # + one-off lattice build
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    rec = {"workload": f"dense CRF, {iters} mean-field iterations, {Hc}x{Wc}x{M} unaries, batch {n_img} "
+                       f"({nb}/GPU) (BASELINE configs[4])",
+           "ms_per_img": ms_img, "img_per_s": world / (ms_img / 1e3), "dtype": "f32",
+           "roofline": {"bound": "hbm", "achieved": algo / (ms_img * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": algo / (ms_img * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_img": algo}}
+    if with_cpu and rank == 0:
+        from oracle import crf as O
+        hs = 512                                                      # bounded sample: one 512x512 crop, same M / iterations
+        u1 = un[0].view(M, Hc, Wc)[:, :hs, :hs].reshape(M, -1).cpu().numpy()
+        t0 = time.perf_counter()
+        O.dense_crf(u1, base[:hs, :hs].copy(), iters=iters)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": dt * 1e3 * (Hc * Wc) / (hs * hs), "unit": "ms/img (scaled to 1024x1024)",
+                               "cores": 1, "kind": "port",
+                               "sample": f"one {hs}x{hs}x{M} crop, {iters} iterations, single-threaded C restatement of "
+                                         f"densecrf ({dt:.1f} s), scaled by the pixel ratio"}
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------ roofline probe
@@ -296,6 +373,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-crf", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true")
     ap.add_argument("--profile-eager", action="store_true", help="run eager (un-captured) steps only; for ncu")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -367,9 +446,26 @@ def main():
     final_loss = (loss_sum / wcount).item()
     launches_per_step = e.graph_launches_per_step()
 
-    # ---- end-to-end arm: the user's call, model.fit_generator over a Sequence of pinned HOST batches.  Every step's
-    # inputs are copied host->device inside the timed region (copy stream, overlapped with the previous step) and
-    # every step's loss + confusion counts are read back to the host.
+    # ---- sustained run: the same device-resident step for >= 2 s (the 20-step region above lasts ~0.2 s), with clocks
+    n_sus = max(args.steps, int(2500.0 / max(ms_step, 1e-3)))
+    sync_all()
+    with ClockSampler(local) as clk_sus:
+        ev0.record()
+        for _ in range(n_sus):
+            e.train_step(xd, yd, swd)
+        ev1.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sus_ms = t.item() / n_sus
+    sustained = {"value": world * B / (sus_ms / 1e3), "unit": "img/s", "steps": n_sus, "seconds": t.item() / 1e3,
+                 "ms_per_step": sus_ms, "clocks": clk_sus.summary()}
+
+    # ---- end-to-end arm: the user's call, model.fit_generator over a keras.utils.Sequence-like object that yields
+    # NUMPY float32 batches (what the reference's SegmentationGenerator yields, utils.py:277-279).  Inside the timed
+    # region, every step: numpy -> pinned staging buffers (worker threads, one batch ahead), host->device copy on the
+    # copy stream, the captured step, and the loss + confusion counts read back to the host.
     class _Seq:
         def __init__(self, n):
             self.n = n
@@ -378,7 +474,7 @@ def main():
             return self.n
 
         def __getitem__(self, i):
-            return xp, yp, {"pred_mask": swp}
+            return x, y, {"pred_mask": sw}          # numpy arrays in pageable host memory
 
     model.fit_generator(_Seq(3), steps_per_epoch=3, epochs=1, verbose=0)
     sync_all()
@@ -394,6 +490,38 @@ def main():
     h2d = xp.numel() * 4 + yp.numel() * 4 + swp.numel() * 4
     d2h = 2 * 8 + B * (CLASSES + 1) * CLASSES * 8
 
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+
+    # ---- BASELINE configs[3] names bf16 for the multi-GPU run: the same step in bf16 storage, timed next to the fp16 line
+    bf16 = None
+    if world > 1 and args.dtype != "bfloat16" and not args.no_bf16:
+        sm2 = SegModel(image_size=(H, W), compute_dtype="bfloat16")
+        m2 = sm2.create_seg_model("original", n=CLASSES, seed=0)
+        m2.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+        make_data_parallel(m2)
+        for _ in range(args.warmup):
+            m2.engine.train_step(xd, yd, swd)
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            m2.engine.train_step(xd, yd, swd)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        bf16 = {"value": world * B / (t.item() / args.steps / 1e3), "unit": "img/s", "dtype": "bf16",
+                "ms_per_step": t.item() / args.steps, "global_batch": world * B}
+        del m2, sm2
+        torch.cuda.empty_cache()
+
+    # ---- the metric's second half: dense CRF ms/img (config 5), images sharded over the ranks
+    crf = None
+    if not args.no_crf:
+        crf = crf_record(rank, world, dev, peaks, with_cpu=not args.no_cpu_baseline)
+
     if rank != 0:
         return
 
@@ -403,10 +531,6 @@ def main():
     agg = profile_eager_step(e, ws, B)
     tot_ms = sum(v[0] for v in agg.values())
     top = max(agg.items(), key=lambda kv: kv[1][0])
-    peaks = {}
-    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk_path):
-        peaks = json.load(open(pk_path))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     name, (ms_k, bytes_k, n_k) = top
@@ -428,6 +552,15 @@ def main():
                 "per_family_ms": {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
                 "per_family_gbs": {k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[0] > 0 and v[1] > 0}}
 
+    # whole-step view: every family's algorithmic bytes over the graph-replayed step time, and SURVEY 8(d)'s layer-wise
+    # figure (346 MB fp16 per image forward, x3 for forward + backward) over the same time
+    step_bytes = sum(v[1] for v in agg.values())
+    survey_bytes = 346e6 * B * 3 * (2 if args.dtype == "float32" else 1)
+    roofline["step"] = {"algorithmic_bytes": step_bytes, "ms": ms_step,
+                        "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                        "survey_8d_bytes": survey_bytes, "survey_8d_frac": survey_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                        "bn_family_share": sum(v[0] for k, v in agg.items() if k.startswith("bn_")) / tot_ms}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cb = 1
@@ -440,17 +573,18 @@ def main():
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[args.dtype], "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": world * B, "parallelism": f"dp{world}",
-                   "l2": "no flush needed: per-step activation working set (~7 GB) >> 126 MB L2",
-                   "loss_after": final_loss},
+        "config": _config(world), "loss_after": final_loss,
         "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "sustained": sustained,
+        "crf": crf,
     }
+    if bf16 is not None:
+        line["bf16"] = bf16
     _emit(line)
 
 

@@ -473,6 +473,31 @@ class Engine:
                                    ws["argmax"] if want_argmax or not want_probs else None)
         return ws["probs"] if want_probs else ws["argmax"]
 
+    def eval_batch(self, img: torch.Tensor, labels: torch.Tensor, sample_w: Optional[torch.Tensor] = None):
+        """Inference-mode forward (moving BatchNorm statistics, no dropout) + the training step's fused loss kernel:
+        -> device scalars (loss_sum, wcount) and the uint8 argmax [B, H*W] (Keras `test_on_batch` / validation)."""
+        B = img.shape[0]
+        self.forward_infer(img, want_probs=False)
+        ws = self.workspace(B, False)
+        if "ev_labels" not in ws:
+            dev = self.device
+            ws["ev_labels"] = torch.empty(B, self.H * self.W, 1, device=dev)
+            ws["ev_sw"] = torch.empty(B, self.H * self.W, device=dev)
+            ws["ev_dlogits"] = torch.zeros_like(ws["logits"])
+            ws["ev_scale"] = torch.zeros(1, device=dev)
+            ws["ev_wcount"] = torch.zeros(1, device=dev, dtype=torch.float64)
+            ws["ev_loss"] = torch.zeros(1, device=dev, dtype=torch.float64)
+        ws["ev_labels"].copy_(labels.view(B, -1, 1), non_blocking=True)
+        sw = None
+        if sample_w is not None:
+            ws["ev_sw"].copy_(sample_w.view(B, -1), non_blocking=True)
+            sw = ws["ev_sw"]
+        ops.ce_grad_scale(B * self.H * self.W, sw, ws["ev_scale"], ws["ev_wcount"])
+        ops.fill_zero(ws["ev_loss"])
+        ops.resize_softmax_ce(ws["logits"], self.n_out, self.H, self.W, ws["ev_labels"], sw, ws["ev_scale"],
+                              ws["ev_dlogits"], ws["ev_loss"], ws["ev_wcount"], ws["argmax"])
+        return ws["ev_loss"], ws["ev_wcount"], ws["argmax"]
+
     def _aspp_head_infer(self, ws, x16, B):
         fh, fw = self.fh, self.fw
         # image pooling branch (deeplabv3p.py:375-382); the 1x1 -> HxW bilinear resize is a broadcast
