@@ -77,8 +77,11 @@ typedef struct {
 } dlb_pw_gemm_params;
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
 /* Tiling plan dlb_pw_gemm would use for a 16-bit GEMM of this shape (host arithmetic only, no device needed):
- * plan[10] = {epilogue warp sets, chunk_n, n_chunks, chunks_per_group, n_groups, accumulator columns per stage,
- *             accumulator stages, alt_tiles, smem pipeline stages, dynamic shared memory bytes}.  0 or DLB_ERR_INVALID. */
+ * plan[19] = {epilogue warp sets, chunk_n, n_chunks, chunks_per_group, n_groups, accumulator columns per stage,
+ *             accumulator stages, alt_tiles, smem pipeline stages, dynamic shared memory bytes, grid size,
+ *             CTAs serving column group 0..7}.  A CTA serves ONE column group for the whole kernel (its epilogue
+ *             warps keep that group's BatchNorm statistics in registers); groups start on multiples of 64 columns so
+ *             the staged 32 x 64 output tiles leave through bulk tensor stores.  0 or DLB_ERR_INVALID. */
 int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_r, int* plan);
 
 /* Weight gradient of a 1x1 convolution: dW[K, N] (+)= A[M, K]^T * dY[M, N]  (fp32 out, ld = N).

@@ -59,6 +59,13 @@ struct GemmArgs {
   uint32_t idesc;
   uint32_t stage_bytes;
   int alt_tiles;   // narrow outputs: epilogue warp set s owns accumulator stage s and drains whole M tiles alone
+  int b_resident;  // the CTA's weight slice [acc_cols, K] stays in shared memory for the whole kernel (b_res_bytes), the
+  uint32_t b_res_bytes;   // pipeline stages then carry the A tile only
+  int tma_store;   // 16-bit row-major output without residual: staged 32x64 tiles leave through cp.async.bulk.tensor
+  // CTA -> column group: group gi is served by CTAs [grp_cta0[gi], grp_cta0[gi] + grp_ctas[gi]) which stride over the M
+  // tiles.  A CTA never changes its group, so an epilogue warp always owns the same output columns and keeps their
+  // BatchNorm statistics in registers for the whole kernel.
+  int grp_cta0[8], grp_ctas[8];
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
@@ -85,6 +92,14 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity)
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 template <typename OutT> __device__ __forceinline__ float2 word_to_float2(uint32_t w);
 template <> __device__ __forceinline__ float2 word_to_float2<__half>(uint32_t w) {
   return __half22float2(*reinterpret_cast<const __half2*>(&w));
@@ -98,10 +113,12 @@ template <> __device__ __forceinline__ float2 word_to_float2<float>(uint32_t w) 
 // instance (host guarantees: 16-bit OutT, no phase-shift store); kSets == 2 also carries the fp32 / phase-shift stores.
 // kLean: no BN-affine and no per-image bias (every training-step GEMM but concat_projection) -- the drain is then
 // tcgen05.ld -> pack -> st.shared with no option tests.
-template <typename OutT, int kSets, bool kLean>
+// kTma: the staged tile leaves through one cp.async.bulk.tensor store per 32 x 64 block (host guarantees: kSets == 4, no
+// residual, no post-statistics activation); the manual coalesced write-back and its registers are compiled out.
+template <typename OutT, int kSets, bool kLean, bool kTma>
 __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const GemmArgs g) {
+                  const __grid_constant__ CUtensorMap tmap_c, const GemmArgs g) {
   constexpr int kThreads = 64 + 128 * kSets;
   constexpr int kEpiThreads = 128 * kSets;
   constexpr bool kStagedOnly = kSets == 4;
@@ -114,24 +131,30 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  uint8_t* tail = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;
+  // tail: per-warp staging tiles first (stage_bytes is a multiple of 2 KB, so they stay 1024-byte aligned: the swizzle of
+  // the TMA store is a function of the shared-memory address), then barriers and per-column tables
+  uint8_t* s_bres = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;      // resident weights (may be empty)
+  uint8_t* s_stage = s_bres + g.b_res_bytes;
+  uint8_t* tail = s_stage + static_cast<size_t>(4 * kSets) * kStageTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + kMaxAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAccStages);
+  uint64_t* bres_bar = tempty_bar + kMaxAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 2);   // (+2: the float4 tables below stay 16-byte aligned)
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
   const int npad = g.n_chunks * g.chunk_n;
   float* s_shift = s_scale + npad;
   float* s_sum = s_shift + npad;
   float* s_sqs = s_sum + npad;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_sqs + npad);   // 4*kSets warps x 4 KB; 16-byte aligned (npad is a multiple of 16)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (kTma) tma_prefetch_desc(&tmap_c);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kMaxAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? 4 : 4 * kSets); }
+    mbar_init(bres_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -148,31 +171,39 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int group_rows = g.chunks_per_group * g.chunk_n;
-  // Work unit = (M tile, column group), strided over the CTAs: the 64x64-resolution layers have 512 M tiles = 3.46 per SM
-  // (a quarter-empty fourth round); with the column groups of the wide outputs flattened in, 1024-2048 units leave a
-  // 1-2 % tail.  A is fetched per (tile, group) either way.
-  const int n_units = g.num_m_tiles * g.n_groups;
+  // this CTA's column group and its share of the M tiles (constant indices: the table lives in the parameter space)
+  int grp = 0, cta0 = 0, tstep = g.grp_ctas[0];
+#pragma unroll
+  for (int gi = 1; gi < 8; ++gi)
+    if (gi < g.n_groups && static_cast<int>(blockIdx.x) >= g.grp_cta0[gi]) { grp = gi; cta0 = g.grp_cta0[gi]; tstep = g.grp_ctas[gi]; }
+  const int tile0 = static_cast<int>(blockIdx.x) - cta0;
+  const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
+      if (g.b_resident && tile0 < g.num_m_tiles) {
+        // weight residency: this CTA's [acc_cols, K] slice is fetched once (k-block major, like a pipeline stage)
+        mbar_expect_tx(bres_bar, g.num_k_blocks * chunks * g.chunk_n * kSwzBytes);
+        for (int kb = 0; kb < g.num_k_blocks; ++kb)
+          for (int c = 0; c < chunks; ++c)
+            tma_load_2d(s_bres + (kb * g.acc_cols + c * g.chunk_n) * kSwzBytes, &tmap_b, bres_bar,
+                        kb * g.k_elems_per_block, (grp * g.chunks_per_group + c) * g.chunk_n);
+      }
+      for (int tile = tile0; tile < g.num_m_tiles; tile += tstep) {
         const int m0 = tile * kBlockM;
-        for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
-          const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
-          for (int kb = 0; kb < g.num_k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[stage], kABytes + chunks * g.chunk_n * kSwzBytes);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * g.k_elems_per_block, m0);
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kABytes + (g.b_resident ? 0 : chunks * g.chunk_n * kSwzBytes));
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * g.k_elems_per_block, m0);
+          if (!g.b_resident)
             for (int c = 0; c < chunks; ++c)
               tma_load_2d(sb + c * g.chunk_n * kSwzBytes, &tmap_b, &full_bar[stage], kb * g.k_elems_per_block,
                           (grp * g.chunks_per_group + c) * g.chunk_n);
-            if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
-          }
+          if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -181,34 +212,31 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // ===================== MMA issuer =====================
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
-        for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
-          const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
-          mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (g.b_resident && tile0 < g.num_m_tiles) mbar_wait(bres_bar, 0);
+      for (int tile = tile0; tile < g.num_m_tiles; tile += tstep) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          for (int kb = 0; kb < g.num_k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
-            const uint32_t sb = sa + kABytes;
-            const int k_left = g.K - kb * g.k_elems_per_block;
-            const int ksteps = min(g.k_elems_per_block / g.umma_k, (k_left + g.umma_k - 1) / g.umma_k);
-            for (int c = 0; c < chunks; ++c) {
-              const uint32_t d_tmem = tmem_base + as * g.acc_cols + c * g.chunk_n;
-              for (int k = 0; k < ksteps; ++k) {
-                // +32 B per UMMA_K step inside the 128-byte swizzle atom
-                const uint64_t adesc = make_sw128_desc(sa + k * 32, 16, 1024);
-                const uint64_t bdesc = make_sw128_desc(sb + c * g.chunk_n * kSwzBytes + k * 32, 16, 1024);
-                umma_f16(d_tmem, adesc, bdesc, g.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              }
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+          const uint32_t sb = g.b_resident ? smem_u32(s_bres) + kb * g.acc_cols * kSwzBytes : sa + kABytes;
+          const int k_left = g.K - kb * g.k_elems_per_block;
+          const int ksteps = min(g.k_elems_per_block / g.umma_k, (k_left + g.umma_k - 1) / g.umma_k);
+          for (int c = 0; c < chunks; ++c) {
+            const uint32_t d_tmem = tmem_base + as * g.acc_cols + c * g.chunk_n;
+            for (int k = 0; k < ksteps; ++k) {
+              // +32 B per UMMA_K step inside the 128-byte swizzle atom
+              const uint64_t adesc = make_sw128_desc(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = make_sw128_desc(sb + c * g.chunk_n * kSwzBytes + k * 32, 16, 1024);
+              umma_f16(d_tmem, adesc, bdesc, g.idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs retire
-            if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[as]);          // accumulator group complete -> epilogue
-          if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
+          umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs retire
+          if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
         }
+        umma_commit(&tfull_bar[as]);          // accumulator group complete -> epilogue
+        if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
@@ -227,7 +255,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool affine = !kLean && (g.col_scale != nullptr || g.col_shift != nullptr);
     const bool staged = kStagedOnly || (kCanStage && g.shuffle_r == 0);
     const uint32_t stg = smem_u32(s_stage) + static_cast<uint32_t>(warp - 2) * kStageTileBytes;   // [32 rows][8 chunks of 16 B]
-    // drain: chunk q of row `lane` -> slot q ^ (lane & 7)
+    // drain: chunk q of row `lane` -> slot q ^ (lane & 7)   (= the SWIZZLE_128B pattern of the output tensor map)
     const uint32_t stg_row = stg + lane * 128;
     const uint32_t lane7 = lane & 7;
     // statistics walk: lane owns word `lane` (columns 2*lane, 2*lane+1) of every row; rows r and r + 8k share a swizzle
@@ -236,14 +264,22 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int cchunk = lane & 7, rsub = lane >> 3;
     const uint32_t wb0 = stg + rsub * 128 + ((cchunk ^ rsub) << 4);
     const uint32_t wb1 = stg + (rsub + 4) * 128 + ((cchunk ^ (rsub + 4)) << 4);
-    const bool wb_plain = g.R == nullptr && g.act == DLB_ACT_NONE;
+    // without statistics the activation is applied to the accumulators in registers, so the staged tile is final
+    const bool act_in_drain = staged && !do_stats && g.act != DLB_ACT_NONE;
+    const bool wb_plain = g.R == nullptr && (g.act == DLB_ACT_NONE || act_in_drain);
+    constexpr bool use_tma = kTma;
     const int red_col = reduce16_col_of_lane(lane);
     const uint32_t tfull_a = smem_u32(tfull_bar);
     const int j_first = g.alt_tiles ? 0 : set * 64;
     const int j_step = g.alt_tiles ? 64 : 64 * kSets;
+    const int col_base = grp * group_rows;
+    // valid accumulator columns of this group (the last chunk of a 64-aligned split may be partly padding)
+    const int gcols = min(chunks * g.chunk_n, ((g.N + 15) & ~15) - col_base);
+    // BatchNorm statistics of this warp's (up to three) 64-column blocks, two packed fp32 columns per lane, kept in
+    // registers across all M tiles of the CTA
+    unsigned long long S0 = 0ull, Q0 = 0ull, S1 = 0ull, Q1 = 0ull, S2 = 0ull, Q2 = 0ull;
     int as = 0; uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int tile = unit / g.n_groups, grp0 = unit - tile * g.n_groups;
+    for (int tile = tile0; tile < g.num_m_tiles; tile += tstep) {
       const int m_base = tile * kBlockM + quad * 32;
       const int m = m_base + lane;
       const bool row_ok = m < g.M;
@@ -260,157 +296,179 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                          static_cast<size_t>(bb) * g.shuffle_r) *
                         g.shuffle_cs;
       }
-      for (int grp = grp0; grp == grp0; ++grp) {     // one (M tile, column group) unit
-        const int chunks = min(g.chunks_per_group, g.n_chunks - grp * g.chunks_per_group);
-        const int as_cur = as;
-        const uint32_t aphase_cur = aphase;
-        if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
-        if (g.alt_tiles && as_cur != set) continue;     // narrow outputs: this warp set owns accumulator stage `set`
-        mbar_wait_s(tfull_a + as_cur * 8, aphase_cur);
-        tc_fence_after();
-        const int gcols = chunks * g.chunk_n;
-        const int col_base = grp * group_rows;
-        for (int j64 = j_first; j64 < gcols; j64 += j_step) {
+      const int as_cur = as;
+      const uint32_t aphase_cur = aphase;
+      if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
+      if (g.alt_tiles && as_cur != set) continue;     // narrow outputs: this warp set owns accumulator stage `set`
+      mbar_wait_s(tfull_a + as_cur * 8, aphase_cur);
+      tc_fence_after();
+      int bi = 0;
+      for (int j64 = j_first; j64 < gcols; j64 += j_step, ++bi) {
+        if (use_tma) {
+          // the previous block's bulk store must have finished READING the staging tile before it is refilled
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
 #pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            const int j = j64 + sub * 32;
-            if (j >= gcols) break;
-            const bool two = j + 16 < gcols;
-            uint32_t r[2][16];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as_cur * g.acc_cols + j;
-            tmem_ld16(taddr, r[0]);
-            if (two) tmem_ld16(taddr + 16, r[1]);
-            tmem_ld_wait();
-            float v[2][16];
+        for (int sub = 0; sub < 2; ++sub) {
+          const int j = j64 + sub * 32;
+          if (j >= gcols) break;
+          const bool two = j + 16 < gcols;
+          uint32_t r[2][16];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as_cur * g.acc_cols + j;
+          tmem_ld16(taddr, r[0]);
+          if (two) tmem_ld16(taddr + 16, r[1]);
+          tmem_ld_wait();
+          float v[2][16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[h][i] = __uint_as_float(r[h][i]);
-            // kernel-uniform options are tested once per 32 columns, not per element
-            if (!kLean && affine) {
+            for (int i = 0; i < 16; ++i) v[h][i] = __uint_as_float(r[h][i]);
+          // kernel-uniform options are tested once per 32 columns, not per element
+          if (!kLean && affine) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col_base + j + h * 16);
-                const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col_base + j + h * 16);
+            for (int h = 0; h < 2; ++h) {
+              const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col_base + j + h * 16);
+              const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col_base + j + h * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 a4 = sc4[q], b4 = sh4[q];
-                  v[h][4 * q + 0] = fmaf(v[h][4 * q + 0], a4.x, b4.x);
-                  v[h][4 * q + 1] = fmaf(v[h][4 * q + 1], a4.y, b4.y);
-                  v[h][4 * q + 2] = fmaf(v[h][4 * q + 2], a4.z, b4.z);
-                  v[h][4 * q + 3] = fmaf(v[h][4 * q + 3], a4.w, b4.w);
-                }
+              for (int q = 0; q < 4; ++q) {
+                const float4 a4 = sc4[q], b4 = sh4[q];
+                v[h][4 * q + 0] = fmaf(v[h][4 * q + 0], a4.x, b4.x);
+                v[h][4 * q + 1] = fmaf(v[h][4 * q + 1], a4.y, b4.y);
+                v[h][4 * q + 2] = fmaf(v[h][4 * q + 2], a4.z, b4.z);
+                v[h][4 * q + 3] = fmaf(v[h][4 * q + 3], a4.w, b4.w);
               }
             }
-            if (!kLean && rb) {
+          }
+          if (!kLean && rb) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int n0 = col_base + j + h * 16;
+            for (int h = 0; h < 2; ++h) {
+              const int n0 = col_base + j + h * 16;
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (n0 + i < g.N) v[h][i] += rb[n0 + i];
-              }
+              for (int i = 0; i < 16; ++i)
+                if (n0 + i < g.N) v[h][i] += rb[n0 + i];
             }
-            if (!two || (do_stats && !row_ok)) {
-              const bool all = do_stats && !row_ok;       // rows past M must not reach the statistics
+          }
+          if (!two || (do_stats && !row_ok)) {
+            const bool all = do_stats && !row_ok;       // rows past M must not reach the statistics
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { v[1][i] = 0.f; if (all) v[0][i] = 0.f; }
+            for (int i = 0; i < 16; ++i) { v[1][i] = 0.f; if (all) v[0][i] = 0.f; }
+          }
+          if (staged) {
+            if (act_in_drain) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[h][i] = apply_act(v[h][i], g.act);
             }
-            if (staged) {
-              // pack to 16 bit and park in the swizzled staging tile
+            // pack to 16 bit and park in the swizzled staging tile
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float o[8];
+            for (int c = 0; c < 4; ++c) {
+              float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = v[c >> 1][(c & 1) * 8 + i];
-                uint4 pk;
-                Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
-                sts128(stg_row + (((sub * 4 + c) ^ lane7) << 4), pk);
-              }
+              for (int i = 0; i < 8; ++i) o[i] = v[c >> 1][(c & 1) * 8 + i];
+              uint4 pk;
+              Vec8<OutT>::st(reinterpret_cast<OutT*>(&pk), o);
+              sts128(stg_row + (((sub * 4 + c) ^ lane7) << 4), pk);
             }
-            if constexpr (!kStagedOnly) {
-              if (!staged) {
-                if (do_stats) {
-                  float s1[2][16], s2[2][16];
+          }
+          if constexpr (!kStagedOnly) {
+            if (!staged) {
+              if (do_stats) {
+                float s1[2][16], s2[2][16];
 #pragma unroll
-                  for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                      const float q = v[h][i];
-                      s1[h][i] = q; s2[h][i] = q * q;
-                    }
-                  const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
-                  const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
-                  if ((lane & 1) == 0) {
-                    const int n0 = col_base + j;
-                    atomicAdd(&s_sum[n0 + red_col], t1a);
-                    atomicAdd(&s_sqs[n0 + red_col], t2a);
-                    if (two) {
-                      atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
-                      atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
-                    }
+                  for (int i = 0; i < 16; ++i) {
+                    const float q = v[h][i];
+                    s1[h][i] = q; s2[h][i] = q * q;
+                  }
+                const float t1a = warp_reduce16(s1[0], lane), t2a = warp_reduce16(s2[0], lane);
+                const float t1b = warp_reduce16(s1[1], lane), t2b = warp_reduce16(s2[1], lane);
+                if ((lane & 1) == 0) {
+                  const int n0 = col_base + j;
+                  atomicAdd(&s_sum[n0 + red_col], t1a);
+                  atomicAdd(&s_sqs[n0 + red_col], t2a);
+                  if (two) {
+                    atomicAdd(&s_sum[n0 + 16 + red_col], t1b);
+                    atomicAdd(&s_sqs[n0 + 16 + red_col], t2b);
                   }
                 }
-                if (row_ok) {
+              }
+              if (row_ok) {
 #pragma unroll
-                  for (int h8 = 0; h8 < 4; ++h8) {
-                    const int n = col_base + j + h8 * 8;
-                    if (n >= g.n_store || (h8 >= 2 && !two)) continue;
-                    float o[8];
+                for (int h8 = 0; h8 < 4; ++h8) {
+                  const int n = col_base + j + h8 * 8;
+                  if (n >= g.n_store || (h8 >= 2 && !two)) continue;
+                  float o[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
-                    if (g.R) {
-                      float rr[8];
-                      Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
+                  for (int i = 0; i < 8; ++i) o[i] = apply_act(v[h8 >> 1][(h8 & 1) * 8 + i], g.act);
+                  if (g.R) {
+                    float rr[8];
+                    Vec8<OutT>::ld(reinterpret_cast<const OutT*>(g.R) + static_cast<size_t>(m) * g.ldr + n, rr);
 #pragma unroll
-                      for (int i = 0; i < 8; ++i) o[i] += rr[i];
-                    }
-                    OutT* dst;
-                    if (g.shuffle_r > 0) {
-                      const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
-                      const int jj = n / rowlen, rem = n - jj * rowlen;
-                      dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
-                            static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
-                    } else {
-                      dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
-                    }
-                    if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
-                      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
-                    } else {
-                      Vec8<OutT>::st(dst, o);
-                    }
+                    for (int i = 0; i < 8; ++i) o[i] += rr[i];
+                  }
+                  OutT* dst;
+                  if (g.shuffle_r > 0) {
+                    const int rowlen = g.shuffle_r * g.shuffle_cs;       // (i, k) run contiguous in the output
+                    const int jj = n / rowlen, rem = n - jj * rowlen;
+                    dst = reinterpret_cast<OutT*>(g.C) + shuf_row_base +
+                          static_cast<size_t>(jj) * (static_cast<size_t>(g.shuffle_w) * g.shuffle_r) * g.shuffle_cs + rem;
+                  } else {
+                    dst = reinterpret_cast<OutT*>(g.C) + static_cast<size_t>(m) * g.ldc + n;
+                  }
+                  if (sizeof(OutT) == 4 && n + 8 > g.n_store) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);   // fp32 rows may end on a multiple of 4
+                  } else {
+                    Vec8<OutT>::st(dst, o);
                   }
                 }
               }
             }
           }
-          if (staged) {
-            if constexpr (kCanStage) {
-              __syncwarp();
-              if (do_stats) {
-                // BatchNorm statistics of the (rounded, pre-activation) tile: conflict-free, a warp reads one
-                // 128-byte row per step
-                unsigned long long acc_s = 0ull, acc_q = 0ull, acc_s2 = 0ull, acc_q2 = 0ull;   // two chains per statistic
+        }
+        if (staged) {
+          if constexpr (kCanStage) {
+            if (use_tma) fence_proxy_async();       // this lane's st.shared -> visible to the bulk-copy engine
+            __syncwarp();
+            if (use_tma && lane == 0) {
+              // one instruction writes the 32 x 64 tile; rows past M and columns past n_store are clipped by the map
+              tma_store_2d(&tmap_c, stg, col_base + j64, m_base);
+              bulk_commit();
+            }
+            if (do_stats) {
+              // BatchNorm statistics of the (rounded, pre-activation) tile: conflict-free, a warp reads one
+              // 128-byte row per step
+              unsigned long long acc_s = 0ull, acc_q = 0ull, acc_s2 = 0ull, acc_q2 = 0ull;   // two chains per statistic
 #pragma unroll
-                for (int r8 = 0; r8 < 8; ++r8) {
-                  const uint32_t a0 = stg + r8 * 128 + (((st_chunk ^ r8) << 4) | st_word);
+              for (int r8 = 0; r8 < 8; ++r8) {
+                const uint32_t a0 = stg + r8 * 128 + (((st_chunk ^ r8) << 4) | st_word);
 #pragma unroll
-                  for (int k = 0; k < 4; k += 2) {
-                    const float2 f = word_to_float2<OutT>(lds32(a0 + k * 1024));
-                    const float2 h = word_to_float2<OutT>(lds32(a0 + (k + 1) * 1024));
-                    f32x2_acc(acc_s, acc_q, f.x, f.y);
-                    f32x2_acc(acc_s2, acc_q2, h.x, h.y);
-                  }
-                }
-                acc_s = f32x2_add(acc_s, acc_s2);
-                acc_q = f32x2_add(acc_q, acc_q2);
-                const int jc = j64 + 2 * lane;
-                if (jc < gcols) {
-                  const float2 s = f32x2_unpack(acc_s), q = f32x2_unpack(acc_q);
-                  atomicAdd(&s_sum[col_base + jc], s.x); atomicAdd(&s_sum[col_base + jc + 1], s.y);
-                  atomicAdd(&s_sqs[col_base + jc], q.x); atomicAdd(&s_sqs[col_base + jc + 1], q.y);
+                for (int k = 0; k < 4; k += 2) {
+                  const float2 f = word_to_float2<OutT>(lds32(a0 + k * 1024));
+                  const float2 h = word_to_float2<OutT>(lds32(a0 + (k + 1) * 1024));
+                  f32x2_acc(acc_s, acc_q, f.x, f.y);
+                  f32x2_acc(acc_s2, acc_q2, h.x, h.y);
                 }
               }
+              acc_s = f32x2_add(acc_s, acc_s2);
+              acc_q = f32x2_add(acc_q, acc_q2);
+              if constexpr (kTma) {
+                if (bi == 0) { S0 = f32x2_add(S0, acc_s); Q0 = f32x2_add(Q0, acc_q); }
+                else if (bi == 1) { S1 = f32x2_add(S1, acc_s); Q1 = f32x2_add(Q1, acc_q); }
+                else { S2 = f32x2_add(S2, acc_s); Q2 = f32x2_add(Q2, acc_q); }
+              } else {
+                // fallback instance (unaligned output / DLB_GEMM_TMA_STORE=0): per-block shared-memory atomics
+                const int jc = j64 + 2 * lane;
+                if (jc < gcols) {
+                  const float2 sv = f32x2_unpack(acc_s), qv = f32x2_unpack(acc_q);
+                  atomicAdd(&s_sum[col_base + jc], sv.x); atomicAdd(&s_sum[col_base + jc + 1], sv.y);
+                  atomicAdd(&s_sqs[col_base + jc], qv.x); atomicAdd(&s_sqs[col_base + jc + 1], qv.y);
+                }
+              }
+            }
+            if constexpr (!use_tma) {
               // coalesced write-back
               const int n = col_base + j64 + cchunk * 8;
               if (n < g.n_store && j64 + cchunk * 8 < gcols) {
@@ -445,8 +503,10 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                       const uint4 pk = lds128(((ii & 1) ? wb1 : wb0) + (ii >> 1) * 1024);
                       float o[8];
                       Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&pk), o);
+                      if (!act_in_drain) {
 #pragma unroll
-                      for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                        for (int q = 0; q < 8; ++q) o[q] = apply_act(o[q], g.act);
+                      }
                       if (res) {
                         float rf[8];
                         Vec8<OutT>::ld(reinterpret_cast<const OutT*>(&rr[i]), rf);
@@ -462,14 +522,28 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as_cur]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as_cur]);
     }
+    if (use_tma && lane == 0) bulk_wait_read0();     // the staging tile must outlive the last bulk store's read
     if (do_stats) {
+      if constexpr (kTma) {
+        // register-resident partial sums -> the CTA's per-column table (once per kernel), then fp64 to global
+#pragma unroll
+        for (int b3 = 0; b3 < 3; ++b3) {
+          const int jc = j_first + b3 * j_step + 2 * lane;
+          if (jc < gcols) {
+            const float2 sv = f32x2_unpack(b3 == 0 ? S0 : (b3 == 1 ? S1 : S2));
+            const float2 qv = f32x2_unpack(b3 == 0 ? Q0 : (b3 == 1 ? Q1 : Q2));
+            atomicAdd(&s_sum[col_base + jc], sv.x); atomicAdd(&s_sum[col_base + jc + 1], sv.y);
+            atomicAdd(&s_sqs[col_base + jc], qv.x); atomicAdd(&s_sqs[col_base + jc + 1], qv.y);
+          }
+        }
+      }
       named_bar_sync(1, kEpiThreads);
-      for (int n = threadIdx.x - 64; n < g.N; n += kEpiThreads) {
+      for (int n = col_base + threadIdx.x - 64; n < min(col_base + gcols, g.N); n += kEpiThreads) {
         atomicAdd(&g.stat_sum[n], static_cast<double>(s_sum[n]));
         atomicAdd(&g.stat_sqs[n], static_cast<double>(s_sqs[n]));
       }
@@ -670,20 +744,29 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, GemmArgs* 
   // 16-bit row-major outputs take the 4-set (16 epilogue warps) staged instance; fp32 / phase-shift stores the 2-set one
   const int sets = (out_dtype != DLB_F32 && shuffle_r == 0) ? 4 : 2;
   const int npad = (N + 15) / 16 * 16;
-  g.n_chunks = (npad + 255) / 256;
-  g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
   g.k_elems_per_block = 64; g.umma_k = 16;
   g.num_k_blocks = (K + 63) / 64;
   g.num_m_tiles = (M + kBlockM - 1) / kBlockM;
-  const size_t tail = (2 * kMaxStages + 2 * kMaxAccStages) * 8 + 16 + 4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 +
-                      static_cast<size_t>(4 * sets) * kStageTileBytes;
-  *tail_out = tail;
   static const int tune_cpg = [] { const char* e = getenv("DLB_GEMM_CPG"); return e ? atoi(e) : 0; }();   // tuning aid
   // Two chunks per accumulator group share one A fetch (matters when K is large); for small K prefer one chunk per
   // group so the group fits twice in TMEM and the epilogue of one group overlaps the MMAs of the next.
-  for (int cpg = (g.n_chunks >= 2 && K > 256 && 2 * g.chunk_n <= 512 && tune_cpg != 1) ? 2 : 1; cpg >= 1; --cpg) {
+  for (int pass = 0; pass < 2; ++pass) {
+    g.n_chunks = (npad + 255) / 256;
+    g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
+    int cpg = (pass == 0 && g.n_chunks >= 2 && K > 256 && 2 * g.chunk_n <= 512 && tune_cpg != 1) ? 2 : 1;
+    int n_groups = (g.n_chunks + cpg - 1) / cpg;
+    if (n_groups > 1) {
+      // several column groups (each served by its own CTAs): group boundaries on multiples of 64 columns, so every
+      // 64-column epilogue block lies inside one group (960 = 256 + 256 + 256 + 192; the padding rows of the last
+      // weight chunk are zero-filled by TMA and never drained)
+      g.chunk_n = (g.chunk_n + 63) / 64 * 64;
+      g.n_chunks = (npad + g.chunk_n - 1) / g.chunk_n;
+      if (cpg == 2 && 2 * g.chunk_n > 512) cpg = 1;
+      n_groups = (g.n_chunks + cpg - 1) / cpg;
+    }
+    if (n_groups > 8) return 0;
     g.chunks_per_group = cpg;
-    g.n_groups = (g.n_chunks + cpg - 1) / cpg;
+    g.n_groups = n_groups;
     g.acc_cols = cpg * g.chunk_n;
     g.acc_stages = g.acc_cols <= 256 ? 2 : 1;
     g.alt_tiles = 0;
@@ -695,13 +778,84 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, GemmArgs* 
       const int cost_split = (blocks + sets - 1) / sets * 64;
       if (alt_stages >= 2 && g.acc_cols < cost_split * alt_stages) { g.alt_tiles = 1; g.acc_stages = alt_stages; }
     }
+    const size_t tail = static_cast<size_t>(4 * sets) * kStageTileBytes + (2 * kMaxStages + 2 * kMaxAccStages + 2) * 8 + 16 +
+                        4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16;
+    *tail_out = tail;
+    // Weight residency: a CTA serves one column group for the whole kernel, so its weight slice (k-blocks x acc_cols
+    // x 128 B) can be fetched once instead of once per M tile (ncu, round 2: the epilogue warps wait on the
+    // accumulator barrier -- the kernel is bound by shared-memory fill traffic, two thirds of it weights coming back
+    // from L2 for every tile).  Taken when it leaves >= 3 A-only stages (narrow inputs: A is small and shared through
+    // L2 by the CTAs of the other column groups) or >= 5 (K > 256: A streams from HBM and needs bytes in flight).
+    static const bool bres_on = [] { const char* e = getenv("DLB_GEMM_BRES"); return !(e && e[0] == '0'); }();
+    const size_t bres = static_cast<size_t>(g.num_k_blocks) * g.acc_cols * kSwzBytes;
+    g.b_resident = 0; g.b_res_bytes = 0;
+    const size_t need_stages = K > 256 ? 5 : 3;
+    if (bres_on && static_cast<size_t>(kMaxSmem) >= 1024 + tail + bres + need_stages * static_cast<size_t>(kABytes)) {
+      g.b_resident = 1; g.b_res_bytes = static_cast<uint32_t>(bres);
+      g.stage_bytes = kABytes;
+      g.num_stages = static_cast<int>((kMaxSmem - 1024 - tail - bres) / kABytes);
+      if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+      return sets;
+    }
     g.stage_bytes = kABytes + g.acc_cols * kSwzBytes;
-    if (static_cast<size_t>(kMaxSmem) < 1024 + tail + 2 * static_cast<size_t>(g.stage_bytes)) continue;
+    if (static_cast<size_t>(kMaxSmem) < 1024 + tail + 2 * static_cast<size_t>(g.stage_bytes)) {
+      if (cpg == 1) return 0;
+      continue;          // retry with one chunk per group
+    }
     g.num_stages = static_cast<int>((kMaxSmem - 1024 - tail) / g.stage_bytes);
     if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
     return sets;
   }
   return 0;
+}
+
+// CTAs per column group, proportional to the group's valid width (a narrower last group gets fewer CTAs, each of
+// which then walks more M tiles: equal epilogue work per CTA).  Returns the grid size.
+static int split_ctas(GemmArgs* gp, int N) {
+  GemmArgs& g = *gp;
+  const int group_cols = g.chunks_per_group * g.chunk_n;
+  const int n16 = (N + 15) / 16 * 16;
+  int width[8], total_w = 0;
+  for (int gi = 0; gi < g.n_groups; ++gi) {
+    width[gi] = n16 - gi * group_cols;
+    if (width[gi] > group_cols) width[gi] = group_cols;
+    total_w += width[gi];
+  }
+  const int sms = num_sms();
+  const long long n_units = static_cast<long long>(g.num_m_tiles) * g.n_groups;
+  int grid = n_units < sms ? static_cast<int>(n_units) : sms;
+  if (grid < g.n_groups) grid = g.n_groups;
+  int used = 0;
+  for (int gi = 0; gi < g.n_groups; ++gi) {
+    int c = static_cast<int>(static_cast<long long>(grid) * width[gi] / total_w);
+    if (c < 1) c = 1;
+    if (c > g.num_m_tiles) c = g.num_m_tiles;
+    g.grp_ctas[gi] = c;
+    used += c;
+  }
+  // hand the rounding remainder to the groups with the most work per CTA
+  while (used < grid) {
+    int best = -1; double worst = 0.0;
+    for (int gi = 0; gi < g.n_groups; ++gi) {
+      if (g.grp_ctas[gi] >= g.num_m_tiles) continue;
+      const double load = static_cast<double>(width[gi]) * ((g.num_m_tiles + g.grp_ctas[gi] - 1) / g.grp_ctas[gi]);
+      if (load > worst) { worst = load; best = gi; }
+    }
+    if (best < 0) break;
+    g.grp_ctas[best]++; used++;
+  }
+  while (used > grid) {        // (only when a group was clamped up to 1)
+    int best = 0;
+    for (int gi = 1; gi < g.n_groups; ++gi) if (g.grp_ctas[gi] > g.grp_ctas[best]) best = gi;
+    if (g.grp_ctas[best] <= 1) break;
+    g.grp_ctas[best]--; used--;
+  }
+  int c0 = 0;
+  for (int gi = 0; gi < 8; ++gi) {
+    if (gi >= g.n_groups) { g.grp_cta0[gi] = 1 << 30; g.grp_ctas[gi] = 1; continue; }
+    g.grp_cta0[gi] = c0; c0 += g.grp_ctas[gi];
+  }
+  return c0;
 }
 
 static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
@@ -720,27 +874,38 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
   g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 0, 0);
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, kBlockM, 64);
   if (rc) return rc;
   rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, 64);
   if (rc) return rc;
+  // output map for the bulk tensor store of staged 32-row x 64-column tiles (16-bit row-major outputs without residual)
+  static const bool tma_store_on = [] { const char* e = getenv("DLB_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  g.tma_store = 0;
+  tc = ta;
+  if (tma_store_on && sets == 4 && p->R == nullptr && (p->act == DLB_ACT_NONE || p->stat_sum == nullptr) &&
+      (reinterpret_cast<uintptr_t>(p->C) & 15) == 0 && p->ldc % 8 == 0) {
+    rc = make_tmap_2d(&tc, p->out_dtype, p->C, p->M, p->n_store, p->ldc, 32, 64);
+    if (rc) return rc;
+    g.tma_store = 1;
+  }
 
-  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail;
-  const int n_units = g.num_m_tiles * g.n_groups;
-  const int grid = n_units < num_sms() ? n_units : num_sms();
+  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + g.b_res_bytes + tail;
+  const int grid = split_ctas(&g, p->N);
 
   const bool lean = !p->col_scale && !p->col_shift && !p->row_bias;
-#define LAUNCH(OT, SETS, LEAN)                                                                                   \
-  do {                                                                                                           \
-    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem_bytes));                                                             \
-    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, g);                     \
+#define LAUNCH(OT, SETS, LEAN, TMA)                                                                                   \
+  do {                                                                                                                \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem_bytes));                                                                  \
+    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, tc, g);                 \
   } while (0)
-#define LAUNCH2(OT, SETS) do { if (lean) LAUNCH(OT, SETS, true); else LAUNCH(OT, SETS, false); } while (0)
-  if (p->out_dtype == DLB_F16) { if (sets == 4) LAUNCH2(__half, 4); else LAUNCH2(__half, 2); }
-  else if (p->out_dtype == DLB_BF16) { if (sets == 4) LAUNCH2(__nv_bfloat16, 4); else LAUNCH2(__nv_bfloat16, 2); }
-  else LAUNCH2(float, 2);
+#define LAUNCH2(OT, SETS, TMA) do { if (lean) LAUNCH(OT, SETS, true, TMA); else LAUNCH(OT, SETS, false, TMA); } while (0)
+#define LAUNCH3(OT) do { if (sets == 4) { if (g.tma_store) LAUNCH2(OT, 4, true); else LAUNCH2(OT, 4, false); } else LAUNCH2(OT, 2, false); } while (0)
+  if (p->out_dtype == DLB_F16) LAUNCH3(__half);
+  else if (p->out_dtype == DLB_BF16) LAUNCH3(__nv_bfloat16);
+  else LAUNCH2(float, 2, false);
+#undef LAUNCH3
 #undef LAUNCH2
 #undef LAUNCH
   g_launches++;
@@ -776,7 +941,9 @@ extern "C" int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_
   if (sets == 0) return DLB_ERR_INVALID;
   plan[0] = sets; plan[1] = g.chunk_n; plan[2] = g.n_chunks; plan[3] = g.chunks_per_group; plan[4] = g.n_groups;
   plan[5] = g.acc_cols; plan[6] = g.acc_stages; plan[7] = g.alt_tiles; plan[8] = g.num_stages;
-  plan[9] = static_cast<int>(1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + tail);
+  plan[9] = static_cast<int>(1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + g.b_res_bytes + tail);
+  plan[10] = split_ctas(&g, N);                                  // grid size
+  for (int i = 0; i < 8; ++i) plan[11 + i] = i < g.n_groups ? g.grp_ctas[i] : 0;   // CTAs per column group
   return DLB_OK;
 }
 

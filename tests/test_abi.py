@@ -94,9 +94,18 @@ def test_pw_gemm_plan_fits_every_layer_shape(lib):
     for k, n in chans:
         for (kk, nn) in ((k, n), (n, k)):           # forward and backward-data
             for od, shuf in ((F16, 0), (F32, 0), (F16, 8 if nn == 1344 else 0)):
-                plan = (C.c_int * 10)()
+                plan = (C.c_int * 19)()
                 assert L.dlb_pw_gemm_plan(M, nn, kk, od, shuf, plan) == 0, (kk, nn, od, shuf)
-                sets, chunk_n, n_chunks, cpg, n_groups, acc_cols, acc_stages, alt, stages, smem = list(plan)
+                sets, chunk_n, n_chunks, cpg, n_groups, acc_cols, acc_stages, alt, stages, smem = list(plan)[:10]
+                grid, ctas = plan[10], list(plan)[11:]
+                # one column group per CTA, every group served, grid within one wave of the 148 SMs
+                assert 1 <= n_groups <= 8 and all(c >= 1 for c in ctas[:n_groups]) and not any(ctas[n_groups:])
+                assert sum(ctas) == grid <= 148
+                if n_groups > 1:      # group boundaries on 64-column blocks (bulk tensor store of staged tiles)
+                    assert (cpg * chunk_n) % 64 == 0, (kk, nn, list(plan))
+                # an epilogue warp sees at most three 64-column blocks per tile (register-resident statistics)
+                per_warp = -(-acc_cols // 64) if alt else -(-acc_cols // (64 * sets))
+                assert per_warp <= 3 or sets == 2, (kk, nn, list(plan))
                 assert sets == (4 if (od != F32 and shuf == 0) else 2)
                 assert chunk_n % 16 == 0 and 16 <= chunk_n <= 256 and chunk_n * n_chunks >= nn
                 assert acc_cols * acc_stages <= 512, (kk, nn, list(plan))
