@@ -74,6 +74,13 @@ typedef struct {
   const void* R;  int ldr;  /* residual or NULL */
   double* stat_sum; double* stat_sqs;   /* [N] fp64 accumulators (atomically added) or NULL */
   int shuffle_r, shuffle_h, shuffle_w;  /* Subpixel store: r, low-res H, W ; 0 = plain store */
+  /* A-operand transform (training forward of the project conv, deeplabv3p.py:189-196): the GEMM reads the RAW output of
+   * the previous layer and applies A := act(A * a_scale[k] + a_shift[k]) (BatchNorm affine + ReLU6) to every landed
+   * tile in shared memory, so the normalised activation never exists in HBM.  NULL = A is used as is.  16-bit path:
+   * needs a plain 16-bit output (no output affine / bias / residual / shuffle). */
+  const float* a_scale;     /* [K] or NULL */
+  const float* a_shift;     /* [K] (required with a_scale) */
+  int a_act;
 } dlb_pw_gemm_params;
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
 /* Tiling plan dlb_pw_gemm would use for a 16-bit GEMM of this shape (host arithmetic only, no device needed):
@@ -81,7 +88,8 @@ int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
  *             accumulator stages, alt_tiles, smem pipeline stages, dynamic shared memory bytes, grid size,
  *             CTAs serving column group 0..7}.  A CTA serves ONE column group for the whole kernel (its epilogue
  *             warps keep that group's BatchNorm statistics in registers); groups start on multiples of 64 columns so
- *             the staged 32 x 64 output tiles leave through bulk tensor stores.  0 or DLB_ERR_INVALID. */
+ *             the staged 32 x 64 output tiles leave through bulk tensor stores.  Bit 16 of shuffle_r selects the plan
+ *             of the A-operand-transform instance (one warp set rewrites A tiles).  0 or DLB_ERR_INVALID. */
 int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_r, int* plan);
 
 /* Weight gradient of a 1x1 convolution: dW[K, N] (+)= A[M, K]^T * dY[M, N]  (fp32 out, ld = N).
@@ -97,6 +105,10 @@ typedef struct {
   float beta;
   void* workspace;          /* unused since the partials are reduced in L2 (dlb_pw_wgrad_workspace_bytes() = 0); may be NULL */
   int64_t workspace_bytes;
+  /* A-operand transform, as in dlb_pw_gemm: A := act(A * a_scale[k] + a_shift[k]) on the landed tiles (or NULL) */
+  const float* a_scale;
+  const float* a_shift;
+  int a_act;
 } dlb_pw_wgrad_params;
 int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream);
 int64_t dlb_pw_wgrad_workspace_bytes(int M, int N, int K);

@@ -28,6 +28,7 @@ class PwGemmParams(C.Structure):
         ("col_scale", vp), ("col_shift", vp), ("row_bias", vp), ("rows_per_img", i32), ("ld_row_bias", i32),
         ("act", i32), ("R", vp), ("ldr", i32), ("stat_sum", vp), ("stat_sqs", vp),
         ("shuffle_r", i32), ("shuffle_h", i32), ("shuffle_w", i32),
+        ("a_scale", vp), ("a_shift", vp), ("a_act", i32),
     ]
 
 
@@ -35,6 +36,7 @@ class PwWgradParams(C.Structure):
     _fields_ = [
         ("M", i32), ("N", i32), ("K", i32), ("dtype", i32), ("A", vp), ("lda", i32), ("dY", vp), ("ldy", i32),
         ("dW", vp), ("ldw", i32), ("dbias", vp), ("beta", f32), ("workspace", vp), ("workspace_bytes", i64),
+        ("a_scale", vp), ("a_shift", vp), ("a_act", i32),
     ]
 
 

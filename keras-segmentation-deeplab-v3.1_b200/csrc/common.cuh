@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string>
 #include <atomic>
+#include <type_traits>
 
 #include "../../include/deeplab_b200.h"
 
@@ -339,6 +340,79 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   }
   a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
   return a1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A-operand transform: BatchNorm affine + activation applied IN PLACE to a landed SWIZZLE_128B tile (rows of 64
+// 16-bit channels = 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)) between the TMA load and tcgen05.mma.
+// Lets a GEMM consume the raw (pre-BatchNorm) output of the previous convolution, so the normalised activation is
+// never written to HBM (deeplabv3p.py:189-196: depthwise_BN + relu6 feeding the project conv).  The caller then
+// executes fence.proxy.async and signals the MMA issuer.  sc / sh: shared-memory addresses of this box's 64 scales /
+// shifts (fp32).  Lanes of a warp own consecutive rows, so chunk index i ^ (r & 7) is conflict-free.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lds128_u32(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+  return u;
+}
+__device__ __forceinline__ void sts128_u32(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+// one 32-bit word (two 16-bit channels): fp32 affine on a packed pair (FFMA2), rounded back, clamped on the packed
+// 16-bit pair -- 6 instructions per two channels
+template <int kAct> __device__ __forceinline__ uint32_t xform_word_h(uint32_t w, unsigned long long sc2, unsigned long long sh2) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  unsigned long long v = f32x2_pack(f.x, f.y);
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(sc2), "l"(sh2));
+  const float2 o = f32x2_unpack(v);
+  __half2 h = __floats2half2_rn(o.x, o.y);
+  if (kAct != DLB_ACT_NONE) h = __hmax2(h, __float2half2_rn(0.f));
+  if (kAct == DLB_ACT_RELU6) h = __hmin2(h, __float2half2_rn(6.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int kAct> __device__ __forceinline__ uint32_t xform_word_b(uint32_t w, unsigned long long sc2, unsigned long long sh2) {
+  unsigned long long v = f32x2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(sc2), "l"(sh2));
+  const float2 o = f32x2_unpack(v);
+  __nv_bfloat162 h = __floats2bfloat162_rn(o.x, o.y);
+  if (kAct != DLB_ACT_NONE) h = __hmax2(h, __float2bfloat162_rn(0.f));
+  if (kAct == DLB_ACT_RELU6) h = __hmin2(h, __float2bfloat162_rn(6.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// Rows r and r + dr (same r & 7) of one box, logical chunks c0 .. c0 + kChunks - 1: the per-channel tables are read once
+// for both rows (broadcast LDS are half of the transform's shared-memory instructions otherwise).
+template <typename T, int kAct, int kChunks>
+__device__ __forceinline__ void xform_rows2_act(uint32_t box_saddr, int r, int dr, int c0, uint32_t sc, uint32_t sh) {
+  auto pair = [](uint32_t lo, uint32_t hi) { return (static_cast<unsigned long long>(hi) << 32) | lo; };
+#pragma unroll
+  for (int i = c0; i < c0 + kChunks; ++i) {
+    const uint32_t a0 = box_saddr + r * 128 + (static_cast<uint32_t>(i ^ (r & 7)) << 4);
+    const uint32_t a1 = a0 + dr * 128;
+    uint4 u = lds128_u32(a0), w = lds128_u32(a1);
+    const uint4 s0 = lds128_u32(sc + i * 32), s1 = lds128_u32(sc + i * 32 + 16);
+    const uint4 h0 = lds128_u32(sh + i * 32), h1 = lds128_u32(sh + i * 32 + 16);
+    const unsigned long long sA = pair(s0.x, s0.y), sB = pair(s0.z, s0.w), sC = pair(s1.x, s1.y), sD = pair(s1.z, s1.w);
+    const unsigned long long hA = pair(h0.x, h0.y), hB = pair(h0.z, h0.w), hC = pair(h1.x, h1.y), hD = pair(h1.z, h1.w);
+    if constexpr (std::is_same<T, __half>::value) {
+      u.x = xform_word_h<kAct>(u.x, sA, hA); u.y = xform_word_h<kAct>(u.y, sB, hB);
+      u.z = xform_word_h<kAct>(u.z, sC, hC); u.w = xform_word_h<kAct>(u.w, sD, hD);
+      w.x = xform_word_h<kAct>(w.x, sA, hA); w.y = xform_word_h<kAct>(w.y, sB, hB);
+      w.z = xform_word_h<kAct>(w.z, sC, hC); w.w = xform_word_h<kAct>(w.w, sD, hD);
+    } else {
+      u.x = xform_word_b<kAct>(u.x, sA, hA); u.y = xform_word_b<kAct>(u.y, sB, hB);
+      u.z = xform_word_b<kAct>(u.z, sC, hC); u.w = xform_word_b<kAct>(u.w, sD, hD);
+      w.x = xform_word_b<kAct>(w.x, sA, hA); w.y = xform_word_b<kAct>(w.y, sB, hB);
+      w.z = xform_word_b<kAct>(w.z, sC, hC); w.w = xform_word_b<kAct>(w.w, sD, hD);
+    }
+    sts128_u32(a0, u);
+    sts128_u32(a1, w);
+  }
+}
+template <typename T, int kChunks>
+__device__ __forceinline__ void xform_rows2(uint32_t box_saddr, int r, int dr, int c0, uint32_t sc, uint32_t sh, int act) {
+  if (act == DLB_ACT_RELU6) xform_rows2_act<T, DLB_ACT_RELU6, kChunks>(box_saddr, r, dr, c0, sc, sh);
+  else if (act == DLB_ACT_RELU) xform_rows2_act<T, DLB_ACT_RELU, kChunks>(box_saddr, r, dr, c0, sc, sh);
+  else xform_rows2_act<T, DLB_ACT_NONE, kChunks>(box_saddr, r, dr, c0, sc, sh);
 }
 
 // ---------------------------------------------------------------------------------------------

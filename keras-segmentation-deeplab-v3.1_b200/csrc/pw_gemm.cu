@@ -59,6 +59,9 @@ struct GemmArgs {
   uint32_t idesc;
   uint32_t stage_bytes;
   int alt_tiles;   // narrow outputs: epilogue warp set s owns accumulator stage s and drains whole M tiles alone
+  const float* a_scale;   // A-operand transform (kXform): A := act(A * a_scale[k] + a_shift[k]) applied to the landed tile
+  const float* a_shift;
+  int a_act;
   int b_resident;  // the CTA's weight slice [acc_cols, K] stays in shared memory for the whole kernel (b_res_bytes), the
   uint32_t b_res_bytes;   // pipeline stages then carry the A tile only
   int tma_store;   // 16-bit row-major output without residual: staged 32x64 tiles leave through cp.async.bulk.tensor
@@ -115,12 +118,15 @@ template <> __device__ __forceinline__ float2 word_to_float2<float>(uint32_t w) 
 // tcgen05.ld -> pack -> st.shared with no option tests.
 // kTma: the staged tile leaves through one cp.async.bulk.tensor store per 32 x 64 block (host guarantees: kSets == 4, no
 // residual, no post-statistics activation); the manual coalesced write-back and its registers are compiled out.
-template <typename OutT, int kSets, bool kLean, bool kTma>
+// kXform: the last warp set does not drain accumulators but applies BatchNorm-affine + activation to every landed A tile
+// (xform_row_sw128) before the MMA issuer may read it: the project conv consumes the raw depthwise output.
+template <typename OutT, int kSets, bool kLean, bool kTma, bool kXform>
 __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c, const GemmArgs g) {
   constexpr int kThreads = 64 + 128 * kSets;
-  constexpr int kEpiThreads = 128 * kSets;
+  constexpr int kEpiSets = kXform ? kSets - 1 : kSets;
+  constexpr int kEpiThreads = 128 * kEpiSets;
   constexpr bool kStagedOnly = kSets == 4;
   constexpr bool kCanStage = sizeof(OutT) == 2;
   extern __shared__ uint8_t smem_dyn[];
@@ -141,20 +147,24 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + kMaxAccStages;
   uint64_t* bres_bar = tempty_bar + kMaxAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 2);   // (+2: the float4 tables below stay 16-byte aligned)
+  uint64_t* xf_bar = bres_bar + 2;          // (+2: the float4 tables below stay 16-byte aligned)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_bar + kMaxStages);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
   const int npad = g.n_chunks * g.chunk_n;
   float* s_shift = s_scale + npad;
   float* s_sum = s_shift + npad;
   float* s_sqs = s_sum + npad;
+  float* s_asc = s_sqs + npad;                              // kXform: per-input-channel scale / shift, padded to k-blocks
+  float* s_ash = s_asc + g.num_k_blocks * 64;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (kTma) tma_prefetch_desc(&tmap_c);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < kMaxAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? 4 : 4 * kSets); }
+    for (int i = 0; i < kMaxAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? 4 : 4 * kEpiSets); }
     mbar_init(bres_bar, 1);
+    if (kXform) for (int i = 0; i < g.num_stages; ++i) mbar_init(&xf_bar[i], 4);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -165,6 +175,11 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     s_sum[i] = 0.f;
     s_sqs[i] = 0.f;
   }
+  if (kXform)
+    for (int i = threadIdx.x; i < g.num_k_blocks * 64; i += kThreads) {
+      s_asc[i] = i < g.K ? g.a_scale[i] : 0.f;            // channels past K are TMA zero fill and must stay zero
+      s_ash[i] = i < g.K ? g.a_shift[i] : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -217,7 +232,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < g.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(kXform ? &xf_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
           const uint32_t sb = g.b_resident ? smem_u32(s_bres) + kb * g.acc_cols * kSwzBytes : sa + kABytes;
@@ -239,8 +254,27 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (++as == g.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (kXform && warp >= 2 + 4 * kEpiSets) {
+    // ===================== A-operand transform warps (the last warp set) =====================
+    // thread = rows r and r + 64 of the landed 128-row A tile, one half of their 16-byte chunks; waits for the TMA bytes,
+    // rewrites in place, makes the writes visible to the tensor-core (async) proxy, lane 0 arrives for the MMA issuer
+    const int t = threadIdx.x - (64 + kEpiThreads);
+    const int r = t & 63, c0 = (t >> 6) * 4;
+    const uint32_t asc = smem_u32(s_asc), ash = smem_u32(s_ash);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = tile0; tile < g.num_m_tiles; tile += tstep) {
+      for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+        xform_rows2<OutT, 4>(sa, r, 64, c0, asc + kb * 256, ash + kb * 256, g.a_act);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[stage]);
+        if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
-    // ===================== epilogue warps (2 .. 2 + 4*kSets) =====================
+    // ===================== epilogue warps (2 .. 2 + 4*kEpiSets) =====================
     // A warp set = 4 warps, one per TMEM lane quarter.  Wide outputs: all sets drain the same accumulator group and
     // take every kSets-th 64-column block.  Narrow outputs (alt_tiles): set s owns accumulator stage s, i.e. every
     // acc_stages-th M tile, and drains all of its blocks.
@@ -271,7 +305,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int red_col = reduce16_col_of_lane(lane);
     const uint32_t tfull_a = smem_u32(tfull_bar);
     const int j_first = g.alt_tiles ? 0 : set * 64;
-    const int j_step = g.alt_tiles ? 64 : 64 * kSets;
+    const int j_step = g.alt_tiles ? 64 : 64 * kEpiSets;
     const int col_base = grp * group_rows;
     // valid accumulator columns of this group (the last chunk of a 64-aligned split may be partly padding)
     const int gcols = min(chunks * g.chunk_n, ((g.N + 15) & ~15) - col_base);
@@ -565,6 +599,7 @@ struct SimtArgs {
   int rows_per_img, ld_row_bias, act;
   double* stat_sum; double* stat_sqs;
   int shuffle_r, shuffle_h, shuffle_w, shuffle_cs;
+  const float* a_scale; const float* a_shift; int a_act;
 };
 
 __global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const SimtArgs g) {
@@ -583,7 +618,14 @@ __global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const SimtArgs g) {
     {
       float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
       const int m = m0 + lr, n = n0 + lr, k = k0 + lk;
-      if (m < g.M && k < g.K) a = *reinterpret_cast<const float4*>(g.A + static_cast<size_t>(m) * g.lda + k);
+      if (m < g.M && k < g.K) {
+        a = *reinterpret_cast<const float4*>(g.A + static_cast<size_t>(m) * g.lda + k);
+        if (g.a_scale) {       // A-operand transform: BatchNorm affine + activation of the producing layer
+          const float4 sc = *reinterpret_cast<const float4*>(g.a_scale + k), sh = *reinterpret_cast<const float4*>(g.a_shift + k);
+          a.x = apply_act(fmaf(a.x, sc.x, sh.x), g.a_act); a.y = apply_act(fmaf(a.y, sc.y, sh.y), g.a_act);
+          a.z = apply_act(fmaf(a.z, sc.z, sh.z), g.a_act); a.w = apply_act(fmaf(a.w, sc.w, sh.w), g.a_act);
+        }
+      }
       if (n < g.N && k < g.K) b = *reinterpret_cast<const float4*>(g.Bt + static_cast<size_t>(n) * g.ldb + k);
       sA[lk + 0][lr] = a.x; sA[lk + 1][lr] = a.y; sA[lk + 2][lr] = a.z; sA[lk + 3][lr] = a.w;
       sB[lk + 0][lr] = b.x; sB[lk + 1][lr] = b.y; sB[lk + 2][lr] = b.z; sB[lk + 3][lr] = b.w;
@@ -739,10 +781,11 @@ int make_tmap_nhwc_sw128(CUtensorMap* map, int dtype, const void* ptr, int B, in
 
 // Tiling plan of the tensor-core kernel (pure host arithmetic; exported as dlb_pw_gemm_plan for the CPU tests).
 // Returns the number of epilogue warp sets (4 or 2), or 0 if no pipeline fits.
-static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, GemmArgs* gp, size_t* tail_out) {
+static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform, GemmArgs* gp, size_t* tail_out) {
   GemmArgs& g = *gp;
   // 16-bit row-major outputs take the 4-set (16 epilogue warps) staged instance; fp32 / phase-shift stores the 2-set one
   const int sets = (out_dtype != DLB_F32 && shuffle_r == 0) ? 4 : 2;
+  const int esets = sets - (xform ? 1 : 0);      // warp sets that drain accumulators (the last one transforms A tiles)
   const int npad = (N + 15) / 16 * 16;
   g.k_elems_per_block = 64; g.umma_k = 16;
   g.num_k_blocks = (K + 63) / 64;
@@ -773,13 +816,14 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, GemmArgs* 
     if (g.n_groups == 1) {
       // per-tile critical path in 64-column block units: all sets on one group vs one set per accumulator stage
       int alt_stages = 512 / g.acc_cols;
-      if (alt_stages > sets) alt_stages = sets;
+      if (alt_stages > esets) alt_stages = esets;
       const int blocks = (g.acc_cols + 63) / 64;
-      const int cost_split = (blocks + sets - 1) / sets * 64;
+      const int cost_split = (blocks + esets - 1) / esets * 64;
       if (alt_stages >= 2 && g.acc_cols < cost_split * alt_stages) { g.alt_tiles = 1; g.acc_stages = alt_stages; }
     }
-    const size_t tail = static_cast<size_t>(4 * sets) * kStageTileBytes + (2 * kMaxStages + 2 * kMaxAccStages + 2) * 8 + 16 +
-                        4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16;
+    const size_t tail = static_cast<size_t>(4 * sets) * kStageTileBytes + (3 * kMaxStages + 2 * kMaxAccStages + 2) * 8 + 16 +
+                        4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 +
+                        (xform ? 2 * static_cast<size_t>(g.num_k_blocks) * 64 * 4 : 0);
     *tail_out = tail;
     // Weight residency: a CTA serves one column group for the whole kernel, so its weight slice (k-blocks x acc_cols
     // x 128 B) can be fetched once instead of once per M tile (ncu, round 2: the epilogue warps wait on the
@@ -869,8 +913,10 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
 
+  const int xform = p->a_scale != nullptr;
+  g.a_scale = p->a_scale; g.a_shift = p->a_shift; g.a_act = p->a_act;
   size_t tail = 0;
-  const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, &g, &tail);
+  const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, xform, &g, &tail);
   DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
   g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 0, 0);
 
@@ -894,11 +940,28 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   const int grid = split_ctas(&g, p->N);
 
   const bool lean = !p->col_scale && !p->col_shift && !p->row_bias;
+  if (xform) {
+    // the training-forward project conv: raw depthwise output in, raw project output + statistics out
+    DLB_REQUIRE(p->a_shift != nullptr, "pw_gemm: a_scale without a_shift");
+    DLB_REQUIRE(sets == 4 && lean && g.tma_store && p->dtype == p->out_dtype,
+                "pw_gemm: the A-operand transform needs a 16-bit row-major output of the input dtype, no output "
+                "affine / bias / residual, and a 16-byte aligned C");
+#define LAUNCHX(OT)                                                                                                       \
+  do {                                                                                                                    \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, 4, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem_bytes));                                                                      \
+    launch_k(pw_gemm_tc_kernel<OT, 4, true, true, true>, grid, 64 + 128 * 4, smem_bytes, st, ta, tb, tc, g);                    \
+  } while (0)
+    if (p->out_dtype == DLB_F16) LAUNCHX(__half); else LAUNCHX(__nv_bfloat16);
+#undef LAUNCHX
+    g_launches++;
+    return check_launch("pw_gemm_tc_kernel");
+  }
 #define LAUNCH(OT, SETS, LEAN, TMA)                                                                                   \
   do {                                                                                                                \
-    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem_bytes));                                                                  \
-    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, tc, g);                 \
+    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA, false>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, tc, g);                 \
   } while (0)
 #define LAUNCH2(OT, SETS, TMA) do { if (lean) LAUNCH(OT, SETS, true, TMA); else LAUNCH(OT, SETS, false, TMA); } while (0)
 #define LAUNCH3(OT) do { if (sets == 4) { if (g.tma_store) LAUNCH2(OT, 4, true); else LAUNCH2(OT, 4, false); } else LAUNCH2(OT, 2, false); } while (0)
@@ -924,6 +987,10 @@ static int launch_simt(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.stat_sum = p->stat_sum; g.stat_sqs = p->stat_sqs;
   g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
+  g.a_scale = p->a_scale; g.a_shift = p->a_shift; g.a_act = p->a_act;
+  DLB_REQUIRE(!p->a_scale || (p->a_shift && (reinterpret_cast<uintptr_t>(p->a_scale) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(p->a_shift) & 15) == 0),
+              "pw_gemm(f32): a_scale / a_shift must both be given and 16-byte aligned");
   const int ncols = p->n_store > p->N ? p->n_store : p->N;
   dim3 grid((p->M + 63) / 64, (ncols + 63) / 64);
   launch_k(pw_gemm_simt_kernel, grid, 256, 0, st, g);
@@ -937,7 +1004,7 @@ extern "C" int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_
   using namespace dlb;
   GemmArgs g{};
   size_t tail = 0;
-  const int sets = plan_tc(N, K, M, out_dtype, shuffle_r, &g, &tail);
+  const int sets = plan_tc(N, K, M, out_dtype, shuffle_r & 0xffff, (shuffle_r >> 16) & 1, &g, &tail);
   if (sets == 0) return DLB_ERR_INVALID;
   plan[0] = sets; plan[1] = g.chunk_n; plan[2] = g.n_chunks; plan[3] = g.chunks_per_group; plan[4] = g.n_groups;
   plan[5] = g.acc_cols; plan[6] = g.acc_stages; plan[7] = g.alt_tiles; plan[8] = g.num_stages;

@@ -37,8 +37,14 @@ struct WgArgs {
   uint32_t stage_bytes, a_bytes;
   uint32_t idesc;
   float* dW;                   // [K, N] fp32, accumulated with vector reductions (red.global.add.v4.f32)
+  const float* a_scale;        // A-operand transform: A := act(A * a_scale[k] + a_shift[k]) on the landed tile (or NULL)
+  const float* a_shift;
+  int a_act;
 };
 
+// kXform: the (otherwise idle until the end) epilogue warps apply BatchNorm-affine + activation to every landed A tile
+// in place -- the weight gradient of the project conv reads the RAW depthwise output (see xform_row_sw128).
+template <typename T, bool kXform>
 __global__ void __launch_bounds__(kWgThreads, 1)
 pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                    const WgArgs g) {
@@ -49,13 +55,17 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kWgMaxStages;
   uint64_t* done_bar = empty_bar + kWgMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* xf_bar = done_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_bar + kWgMaxStages);
+  float* s_asc = reinterpret_cast<float*>(tmem_slot + 4);       // [128] scales, [128] shifts of this CTA's K tile
+  float* s_ash = s_asc + 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(done_bar, 1);
+    if (kXform) for (int i = 0; i < g.num_stages; ++i) mbar_init(&xf_bar[i], 4);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -76,6 +86,14 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int m_end = min(g.M, m_begin + g.rows_per_split);
   const int R = g.rows_per_stage;
   const int iters = m_end > m_begin ? (m_end - m_begin + R - 1) / R : 0;
+  if (kXform) {
+    if (threadIdx.x < 128) {
+      const int k = k0 + threadIdx.x;
+      s_asc[threadIdx.x] = k < g.K ? g.a_scale[k] : 0.f;       // channels past K are TMA zero fill and stay zero
+      s_ash[threadIdx.x] = k < g.K ? g.a_shift[k] : 0.f;
+    }
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -96,7 +114,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(kXform ? &xf_bar[stage] : &full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
         const uint32_t sy = sa + g.a_bytes;
@@ -115,6 +133,24 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       umma_commit(done_bar);
     }
   } else {
+    if constexpr (kXform) {
+      // the two landed [R x 64 channel] boxes: a thread owns rows r and r + R/2 of one box and half (R = 64) or all
+      // (R = 32) of their 16-byte chunks
+      const int t = threadIdx.x - 64;
+      const int box = t >> 6, tr = t & 63;
+      const uint32_t asc = smem_u32(s_asc), ash = smem_u32(s_ash);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
+        if (R == 64) xform_rows2<T, 4>(sa + box * R * 128, tr & 31, 32, (tr >> 5) * 4, asc + box * 256, ash + box * 256, g.a_act);
+        else if (tr < 16 || (tr >= 32 && tr < 48)) xform_rows2<T, 4>(sa + box * R * 128, tr & 15, 16, (tr >> 5) * 4, asc + box * 256, ash + box * 256, g.a_act);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[stage]);
+        if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
     const int quad = warp & 3;
     const int k = k0 + quad * 32 + lane;
     float* dst_row = g.dW + static_cast<size_t>(k) * g.N;
@@ -156,7 +192,8 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // exact fp32 SIMT path: blocks (k tile, n tile, split), fp32 atomics into dW
 __global__ void __launch_bounds__(256) pw_wgrad_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                             const float* __restrict__ dY, int ldy, float* __restrict__ dW,
-                                                            int ldw, int rows_per_split) {
+                                                            int ldw, int rows_per_split, const float* __restrict__ a_scale,
+                                                            const float* __restrict__ a_shift, int a_act) {
   pdl_prologue();
   constexpr int T = 64, TR = 16;
   __shared__ float sA[TR][T + 4];
@@ -174,6 +211,12 @@ __global__ void __launch_bounds__(256) pw_wgrad_simt_kernel(int M, int N, int K,
       const float* bp = dY + static_cast<size_t>(m) * ldy + n0 + lc;
       if (k0 + lc + 3 < K) a = *reinterpret_cast<const float4*>(ap);
       else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + lc + i < K) t[i] = ap[i]; a = make_float4(t[0], t[1], t[2], t[3]); }
+      if (a_scale) {       // A-operand transform (BatchNorm affine + activation of the producing layer)
+        float t[4] = {a.x, a.y, a.z, a.w};
+        for (int i = 0; i < 4; ++i)
+          t[i] = k0 + lc + i < K ? apply_act(fmaf(t[i], a_scale[k0 + lc + i], a_shift[k0 + lc + i]), a_act) : 0.f;
+        a = make_float4(t[0], t[1], t[2], t[3]);
+      }
       if (n0 + lc + 3 < N) b = *reinterpret_cast<const float4*>(bp);
       else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (n0 + lc + i < N) t[i] = bp[i]; b = make_float4(t[0], t[1], t[2], t[3]); }
     }
@@ -252,7 +295,7 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
     splits = (p->M + rps - 1) / rps;
     dim3 grid(kt, nt, splits);
     launch_k(pw_wgrad_simt_kernel, grid, 256, 0, st, p->M, p->N, p->K, (const float*)p->A, p->lda, (const float*)p->dY,
-                                               p->ldy, p->dW, p->ldw, rps);
+                                               p->ldy, p->dW, p->ldw, rps, p->a_scale, p->a_shift, p->a_act);
     g_launches++;
     return check_launch("pw_wgrad_simt_kernel");
   }
@@ -285,6 +328,8 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   splits = (p->M + rps - 1) / rps;
   g.splits = splits; g.rows_per_split = rps;
   g.dW = p->dW;
+  g.a_scale = p->a_scale; g.a_shift = p->a_shift; g.a_act = p->a_act;
+  DLB_REQUIRE(!p->a_scale || p->a_shift, "pw_wgrad: a_scale without a_shift");
   if (p->beta == 0.f) DLB_CUDA(cudaMemsetAsync(p->dW, 0, sizeof(float) * p->K * p->N, st));
   g.a_bytes = 2 * R * 128;
   g.stage_bytes = g.a_bytes + g.n_boxes * R * 128;
@@ -297,9 +342,15 @@ extern "C" int dlb_pw_wgrad(const dlb_pw_wgrad_params* p, void* stream) {
   if (rc) return rc;
   rc = make_tmap_2d(&ty, p->dtype, p->dY, p->M, p->N, p->ldy, R, 64);
   if (rc) return rc;
-  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + (2 * kWgMaxStages + 1) * 8 + 16;
-  DLB_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  launch_k(pw_wgrad_tc_kernel, tiles * splits, kWgThreads, smem_bytes, st, ta, ty, g);
+  const size_t smem_bytes = 1024 + static_cast<size_t>(g.num_stages) * g.stage_bytes + (3 * kWgMaxStages + 2) * 8 + 16 + 256 * 4;
+#define LAUNCH(T, X)                                                                                                   \
+  do {                                                                                                                 \
+    DLB_CUDA(cudaFuncSetAttribute(pw_wgrad_tc_kernel<T, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+    launch_k(pw_wgrad_tc_kernel<T, X>, tiles * splits, kWgThreads, smem_bytes, st, ta, ty, g);                          \
+  } while (0)
+  if (p->dtype == DLB_BF16) { if (p->a_scale) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+  else { if (p->a_scale) LAUNCH(__half, true); else LAUNCH(__half, false); }
+#undef LAUNCH
   g_launches++;
   return check_launch("pw_wgrad_tc_kernel");
 }

@@ -11,8 +11,8 @@ Numerics (Keras 2.2.4 semantics):
   * parameters, BN statistics, gradients of parameters and Adam state are fp32.
 
 Data flow of one inverted-residual block in training (deeplabv3p.py:167-206), raw = pre-BN conv output:
-    x_in --pw_gemm(+stats)--> y_e --dw_conv(prologue BN_e+ReLU6, +stats)--> y_d --bn_act_apply--> a_d
-         --pw_gemm(+stats)--> y_p --bn_act_apply(+x_in)--> x_out
+    x_in --pw_gemm(+stats)--> y_e --dw_conv(prologue BN_e+ReLU6, +stats)--> y_d
+         --pw_gemm(A-tile transform BN_d+ReLU6, +stats)--> y_p --bn_act_apply(+x_in)--> x_out
 """
 from __future__ import annotations
 
@@ -111,6 +111,10 @@ class Engine:
         self.grad_hook = None                  # called with the flat grad buffer before the optimizer step
         self._weights_dirty = True
         self._any_frozen = False
+        # depthwise_BN + relu6 applied to the A tiles inside the project GEMM / its weight gradient (no a_d tensor).
+        # DLB_FUSE_DW_BN=0 restores the materialised activation (A/B measurements only).
+        import os
+        self.fuse_dw_bn = os.environ.get("DLB_FUSE_DW_BN", "1") != "0"
 
     @property
     def loss_scale(self) -> float:
@@ -356,7 +360,8 @@ class Engine:
                 if b["bid"]:
                     ws[f"y_e{i}"] = E(B, g["h"], g["w"], b["mid"])
                 ws[f"y_d{i}"] = E(B, g["ho"], g["wo"], b["mid"])
-                ws[f"a_d{i}"] = E(B, g["ho"], g["wo"], b["mid"])
+                if not self.fuse_dw_bn:
+                    ws[f"a_d{i}"] = E(B, g["ho"], g["wo"], b["mid"])
                 ws[f"y_p{i}"] = E(B, g["ho"], g["wo"], b["cout"])
                 ws[f"x{i + 1}"] = E(B, g["ho"], g["wo"], b["cout"])
             ws["y_a0"] = E(B, fh, fw, 256)
@@ -555,10 +560,16 @@ class Engine:
                 ops.dw_conv_fwd(xin, b["dw"].params[0].data, ws[f"y_d{i}"], stride=b["stride"], dilation=b["rate"],
                                 pad_top=g["pt"], pad_left=g["pl"], stat_sum=dbn.sum, stat_sqs=dbn.sqs)
             self._finalize(dbn, Mout)
-            ops.bn_act_apply(ws[f"y_d{i}"], ws[f"a_d{i}"], scale=dbn.scale, shift=dbn.shift, act=ACT_RELU6)
+            # depthwise_BN + relu6 are applied to the A tiles inside the project GEMM: the normalised activation is
+            # never written (one read + one write of the 6C-wide tensor less per block, and nothing to save for backward)
             pbn = b["project_bn"]
-            ops.pw_gemm(ws[f"a_d{i}"], self.wcopies[b["project"].name]["nk"], ws[f"y_p{i}"], stat_sum=pbn.sum,
-                        stat_sqs=pbn.sqs)
+            if self.fuse_dw_bn:
+                ops.pw_gemm(ws[f"y_d{i}"], self.wcopies[b["project"].name]["nk"], ws[f"y_p{i}"], stat_sum=pbn.sum,
+                            stat_sqs=pbn.sqs, a_scale=dbn.scale, a_shift=dbn.shift, a_act=ACT_RELU6)
+            else:
+                ops.bn_act_apply(ws[f"y_d{i}"], ws[f"a_d{i}"], scale=dbn.scale, shift=dbn.shift, act=ACT_RELU6)
+                ops.pw_gemm(ws[f"a_d{i}"], self.wcopies[b["project"].name]["nk"], ws[f"y_p{i}"], stat_sum=pbn.sum,
+                            stat_sqs=pbn.sqs)
             self._finalize(pbn, Mout)
             ops.bn_act_apply(ws[f"y_p{i}"], ws[f"x{i + 1}"], scale=pbn.scale, shift=pbn.shift, act=ACT_NONE,
                              res=xin if b["skip"] else None)
@@ -680,7 +691,11 @@ class Engine:
                        act=ACT_NONE, red=pbn.red, dgamma=pbn.gamma.grad, dbeta=pbn.beta.grad)
             pj = b["project"]
             if pj.trainable:
-                ops.pw_wgrad(ws[f"a_d{i}"], dy_p, pj.params[0].grad.view(b["mid"], b["cout"]), beta=1.0)
+                if self.fuse_dw_bn:
+                    ops.pw_wgrad(ws[f"y_d{i}"], dy_p, pj.params[0].grad.view(b["mid"], b["cout"]), beta=1.0,
+                                 a_scale=dbn.scale, a_shift=dbn.shift, a_act=ACT_RELU6)
+                else:
+                    ops.pw_wgrad(ws[f"a_d{i}"], dy_p, pj.params[0].grad.view(b["mid"], b["cout"]), beta=1.0)
             if first > self._order(b["dw_bn"].layer.name):
                 return
             da_d = nview(gw[0], B, g["ho"], g["wo"], b["mid"])

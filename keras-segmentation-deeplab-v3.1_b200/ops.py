@@ -34,8 +34,9 @@ def _mat(t: torch.Tensor) -> Tuple[int, int, int]:
 
 def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional[int] = None, N: Optional[int] = None,
             n_store: Optional[int] = None, col_scale=None, col_shift=None, row_bias=None, rows_per_img: int = 1,
-            act: int = ACT_NONE, residual=None, stat_sum=None, stat_sqs=None, shuffle: Optional[Tuple[int, int, int]] = None):
-    """out[M, :n_store] = epilogue(A[M, K] @ Bt[N, K]^T); see dlb_pw_gemm."""
+            act: int = ACT_NONE, residual=None, stat_sum=None, stat_sqs=None, shuffle: Optional[Tuple[int, int, int]] = None,
+            a_scale=None, a_shift=None, a_act: int = ACT_NONE):
+    """out[M, :n_store] = epilogue(A'[M, K] @ Bt[N, K]^T), A' = a_act(A * a_scale + a_shift) if given; see dlb_pw_gemm."""
     L.require_cuda(A, Bt, out)
     M, Ka, lda = _mat(A)
     Nb, Kb, ldb = _mat(Bt)
@@ -61,6 +62,7 @@ def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional
     if residual is not None:
         p.R, p.ldr = residual.data_ptr(), _mat(residual)[2]
     p.stat_sum, p.stat_sqs = L.ptr(stat_sum), L.ptr(stat_sqs)
+    p.a_scale, p.a_shift, p.a_act = L.ptr(a_scale), L.ptr(a_shift), a_act
     L.check(L.lib().dlb_pw_gemm(C.byref(p), L.stream_ptr()), "pw_gemm")
     return out
 
@@ -70,8 +72,9 @@ def pw_wgrad_workspace_bytes(M: int, N: int, K: int) -> int:
 
 
 def pw_wgrad(A: torch.Tensor, dY: torch.Tensor, dW: torch.Tensor, *, K: Optional[int] = None, N: Optional[int] = None,
-             dbias=None, beta: float = 0.0, workspace: Optional[torch.Tensor] = None):
-    """dW[K, N] = A[M, K]^T @ dY[M, N]; see dlb_pw_wgrad."""
+             dbias=None, beta: float = 0.0, workspace: Optional[torch.Tensor] = None, a_scale=None, a_shift=None,
+             a_act: int = ACT_NONE):
+    """dW[K, N] = A'[M, K]^T @ dY[M, N], A' = a_act(A * a_scale + a_shift) if given; see dlb_pw_wgrad."""
     L.require_cuda(A, dY, dW)
     M, Ka, lda = _mat(A)
     _, Nb, ldy = _mat(dY)
@@ -84,6 +87,7 @@ def pw_wgrad(A: torch.Tensor, dY: torch.Tensor, dW: torch.Tensor, *, K: Optional
     p.beta = beta
     if workspace is not None:
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    p.a_scale, p.a_shift, p.a_act = L.ptr(a_scale), L.ptr(a_shift), a_act
     L.check(L.lib().dlb_pw_wgrad(C.byref(p), L.stream_ptr()), "pw_wgrad")
     return dW
 

@@ -443,3 +443,41 @@ def test_label_weights_bit_exact_vs_oracle(ldtype):
         yr, swr = R.generator_labels_and_weights(labs[b], n_classes)
         assert np.array_equal(y[b].cpu().numpy(), yr.astype(np.float32))
         assert np.array_equal(sw[b].cpu().numpy(), swr)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A-operand transform: the project conv (forward GEMM and weight gradient) consumes the RAW depthwise output and
+# applies depthwise_BN + relu6 to the landed tiles (deeplabv3p.py:189-196)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K,N", [(4096 + 37, 96, 24), (16384, 576, 96), (8192, 960, 160), (8192, 960, 320), (1024, 32, 16),
+                                   (2048, 144, 32)])
+def test_pw_gemm_and_wgrad_a_operand_transform(dt, M, K, N):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    raw = (torch.randn(M, K, device="cuda", generator=g) * 2 + 0.5).to(dt)
+    sc = torch.rand(K, device="cuda", generator=g) + 0.5
+    sh = torch.randn(K, device="cuda", generator=g)
+    Bt = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(dt)
+    a_ref = (raw.float() * sc + sh).clamp(0, 6)
+    a_rnd = a_ref.to(dt).float()                       # what the tensor cores see (tile rounded back to the storage type)
+    # forward GEMM + statistics of the (rounded) output
+    out = torch.empty(M, N, device="cuda", dtype=dt)
+    ssum = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ssqs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.pw_gemm(raw, Bt, out, stat_sum=ssum, stat_sqs=ssqs, a_scale=sc, a_shift=sh, a_act=ops.ACT_RELU6)
+    ref = a_rnd @ Bt.float().t()
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.5e-2, torch.float32: 1e-5}[dt]
+    assert rel_err(out, ref) < tol
+    o = out.double()
+    assert rel_err(ssum, o.sum(0)) < 1e-3 and rel_err(ssqs, (o * o).sum(0)) < 1e-3
+    # weight gradient dW[K, N] = A'^T dY
+    dY = (torch.randn(M, N, device="cuda", generator=g) / 8).to(dt)
+    dW = torch.zeros(K, N, device="cuda")
+    ops.pw_wgrad(raw, dY, dW, beta=0.0, a_scale=sc, a_shift=sh, a_act=ops.ACT_RELU6)
+    dW_ref = a_rnd.double().t() @ dY.double()
+    assert rel_err(dW, dW_ref) < {torch.float16: 1e-3, torch.bfloat16: 1e-3, torch.float32: 1e-4}[dt]
+    # and without the transform the same kernels still see A as is
+    dW2 = torch.zeros(K, N, device="cuda")
+    ops.pw_wgrad(raw, dY, dW2, beta=0.0)
+    assert rel_err(dW2, raw.double().t() @ dY.double()) < 1e-3
