@@ -352,11 +352,23 @@ typedef struct {
   int H, W, M, iters;
   float sxy_gauss, compat_gauss;             /* addPairwiseGaussian(sxy=3, compat=3)   utils.py:82 */
   float sxy_bilat, srgb_bilat, compat_bilat; /* addPairwiseBilateral(80, 13, compat=10) utils.py:85 */
+  int unary_layout;   /* 0: `unary` = energies, label-major [M, N] (pydensecrf setUnaryEnergy);
+                         1: `unary` = class probabilities, pixel-major [N, M] -- the network's softmax output as it
+                            lies in device memory; -U = log p (soft unaries, no argmax -> unary_from_labels round trip) */
 } dlb_crf_config;
 int64_t dlb_crf_workspace_bytes(const dlb_crf_config* cfg);
 int dlb_crf_inference(const dlb_crf_config* cfg, const float* unary, const uint8_t* image, float* Q,
                       uint8_t* map_out /* [N] argmax or NULL */, void* workspace, int64_t workspace_bytes,
                       void* stream);
+/* The same for a batch of independent images in ONE set of launches (batch = grid.y of every kernel):
+ *   unary [B, M, N], image [B, H, W, 3], Q [B, M, N], map_out [B, N] or NULL.
+ * The Gaussian lattice depends on (H, W, sxy) only and is built once for the whole batch; bilateral lattices are per
+ * image.  Per iteration: 2 splats (CSR gathers; lattice vertices are numbered in raster order of their first pixel so
+ * the gathers are cache-coherent), 3 + 6 blur passes, and ONE slice kernel that gathers both lattices, adds the Potts
+ * messages to -U and normalises (softmax) -- 12 launches per iteration for the whole batch. */
+int64_t dlb_crf_workspace_bytes_batched(const dlb_crf_config* cfg, int batch);
+int dlb_crf_inference_batched(const dlb_crf_config* cfg, int batch, const float* unary, const uint8_t* image, float* Q,
+                              uint8_t* map_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ class SepconvFusedParams(C.Structure):
 class CrfConfig(C.Structure):
     _fields_ = [
         ("H", i32), ("W", i32), ("M", i32), ("iters", i32), ("sxy_gauss", f32), ("compat_gauss", f32),
-        ("sxy_bilat", f32), ("srgb_bilat", f32), ("compat_bilat", f32),
+        ("sxy_bilat", f32), ("srgb_bilat", f32), ("compat_bilat", f32), ("unary_layout", i32),
     ]
 
 
@@ -115,7 +115,7 @@ EXPORTS = [
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
     "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan", "dlb_label_weights",
-    "dlb_grad_finite_check",
+    "dlb_grad_finite_check", "dlb_crf_workspace_bytes_batched", "dlb_crf_inference_batched",
 ]
 
 _lib = None
@@ -163,6 +163,9 @@ def lib() -> C.CDLL:
         L.dlb_sepconv_fused_fwd.argtypes = [vp, vp]
         L.dlb_crf_workspace_bytes.argtypes = [vp]
         L.dlb_crf_inference.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
+        L.dlb_crf_workspace_bytes_batched.restype = i64
+        L.dlb_crf_workspace_bytes_batched.argtypes = [vp, i32]
+        L.dlb_crf_inference_batched.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp]
         for name in ("dlb_pw_gemm", "dlb_pw_wgrad", "dlb_dw_conv_fwd", "dlb_dw_conv_bwd", "dlb_stem_conv_fwd",
                      "dlb_bn_act_apply", "dlb_bn_bwd_reduce", "dlb_bn_bwd_apply", "dlb_resize_softmax_ce"):
             getattr(L, name).argtypes = [vp, vp]

@@ -97,31 +97,48 @@ _crf_ws = {}
 
 
 def dense_crf(unary, image, iters=5, sxy_gauss=3.0, compat_gauss=3.0, sxy_bilat=80.0, srgb_bilat=13.0,
-              compat_bilat=10.0, return_map=False):
+              compat_bilat=10.0, return_map=False, probs=None):
     """Batched dense-CRF mean field on the GPU.
-    unary [B, M, H*W] (or [M, H*W]) float32 energies, image [B, H, W, 3] (or [H, W, 3]) uint8 -> Q [B, M, H*W]."""
-    un = torch.as_tensor(unary, dtype=torch.float32)
+    unary [B, M, H*W] (or [M, H*W]) float32 energies, image [B, H, W, 3] (or [H, W, 3]) uint8 -> Q [B, M, H*W].
+    Alternatively `probs` [B, H*W, M] (or [H*W, M]): class probabilities pixel-major, exactly what `model.predict` /
+    the engine's softmax leaves in device memory -- soft unaries -log p without leaving the GPU."""
+    if probs is not None:
+        un = torch.as_tensor(probs, dtype=torch.float32)
+        single = un.dim() == 2
+    else:
+        un = torch.as_tensor(unary, dtype=torch.float32)
+        single = un.dim() == 2
     im = torch.as_tensor(image, dtype=torch.uint8)
-    single = un.dim() == 2
     if single:
         un, im = un[None], im[None]
     un, im = un.cuda().contiguous(), im.cuda().contiguous()
-    B, M, N = un.shape
+    if probs is not None:
+        B, N, M = un.shape
+    else:
+        B, M, N = un.shape
     H, W = im.shape[1], im.shape[2]
     assert N == H * W
-    cfg = L.CrfConfig(H, W, M, iters, sxy_gauss, compat_gauss, sxy_bilat, srgb_bilat, compat_bilat)
-    nbytes = int(L.lib().dlb_crf_workspace_bytes(C.byref(cfg)))
+    cfg = L.CrfConfig(H, W, M, iters, sxy_gauss, compat_gauss, sxy_bilat, srgb_bilat, compat_bilat,
+                      1 if probs is not None else 0)
+    # the whole batch goes through ONE set of launches (batch = grid.y); very large batches are chunked so that the
+    # worst-case lattice workspace (~2.4 KB per pixel and image at 21 labels) stays below ~24 GB
+    per_img = int(L.lib().dlb_crf_workspace_bytes_batched(C.byref(cfg), 1))
+    chunk = max(1, min(B, int((24 << 30) // max(per_img, 1))))
+    nbytes = int(L.lib().dlb_crf_workspace_bytes_batched(C.byref(cfg), chunk))
     key = (H, W, M)
     ws = _crf_ws.get(key)
     if ws is None or ws.numel() < nbytes:
+        ws = None
+        _crf_ws.pop(key, None)
         ws = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
         _crf_ws[key] = ws
     Q = torch.empty(B, M, N, device="cuda")
     mp = torch.empty(B, N, device="cuda", dtype=torch.uint8) if return_map else None
-    for b in range(B):
-        L.check(L.lib().dlb_crf_inference(C.byref(cfg), un[b].data_ptr(), im[b].data_ptr(), Q[b].data_ptr(),
-                                          mp[b].data_ptr() if return_map else None, ws.data_ptr(), nbytes,
-                                          L.stream_ptr()), "crf_inference")
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        L.check(L.lib().dlb_crf_inference_batched(C.byref(cfg), nb, un[b0:b0 + nb].data_ptr(), im[b0:b0 + nb].data_ptr(),
+                                                  Q[b0:b0 + nb].data_ptr(), mp[b0:b0 + nb].data_ptr() if return_map else None,
+                                                  ws.data_ptr(), ws.numel(), L.stream_ptr()), "crf_inference")
     if return_map:
         return (Q[0], mp[0]) if single else (Q, mp)
     return Q[0] if single else Q

@@ -61,3 +61,23 @@ def test_do_crf_matches_reference_semantics():
         a = do_crf(img, mask, zero_unsure=zu)
         b = O.do_crf(img, mask, zero_unsure=zu)
         assert a.shape == (H, W) and (a == b).mean() > 0.999
+
+
+def test_crf_from_device_probabilities_and_batch_of_eight():
+    """soft unaries straight from pixel-major class probabilities on the device (-U = log p), no
+    argmax -> unary_from_labels round trip; and the batched launch path (8 images, shared Gaussian lattice, per-image
+    bilateral lattices) equals eight single-image runs of the oracle."""
+    from deeplab_b200.utils import dense_crf
+    from oracle import crf as O
+    H, W, M, B = 64, 80, 21, 8
+    rng = np.random.RandomState(3)
+    logits = rng.randn(B, H * W, M).astype(np.float32) * 2
+    probs = np.exp(logits - logits.max(-1, keepdims=True))
+    probs /= probs.sum(-1, keepdims=True)
+    imgs = np.stack([_image(H, W, 10 + b) for b in range(B)])
+    Q, mp = dense_crf(None, torch.from_numpy(imgs).cuda(), iters=5, return_map=True, probs=torch.from_numpy(probs).cuda())
+    assert Q.shape == (B, M, H * W) and mp.shape == (B, H * W)
+    for b in range(B):
+        ref = O.dense_crf(-np.log(probs[b].T), imgs[b], iters=5)
+        assert np.abs(Q[b].cpu().numpy() - ref).max() < 2e-3
+        assert (mp[b].cpu().numpy() == ref.argmax(0)).mean() > 0.999
