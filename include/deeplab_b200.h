@@ -89,7 +89,8 @@ int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
  *             CTAs serving column group 0..7}.  A CTA serves ONE column group for the whole kernel (its epilogue
  *             warps keep that group's BatchNorm statistics in registers); groups start on multiples of 64 columns so
  *             the staged 32 x 64 output tiles leave through bulk tensor stores.  Bit 16 of shuffle_r selects the plan
- *             of the A-operand-transform instance (one warp set rewrites A tiles).  0 or DLB_ERR_INVALID. */
+ *             of the A-operand-transform instance (one warp set rewrites A tiles), bit 17 the plan of the fp32-operand
+ *             (3xTF32) instance.  0 or DLB_ERR_INVALID. */
 int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_r, int* plan);
 
 /* Weight gradient of a 1x1 convolution: dW[K, N] (+)= A[M, K]^T * dY[M, N]  (fp32 out, ld = N).

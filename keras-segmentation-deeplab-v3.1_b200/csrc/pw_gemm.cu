@@ -62,6 +62,9 @@ struct GemmArgs {
   const float* a_scale;   // A-operand transform (kXform): A := act(A * a_scale[k] + a_shift[k]) applied to the landed tile
   const float* a_shift;
   int a_act;
+  int tf32x3;      // fp32 operands on the tensor cores: A and B tiles are split in shared memory into a tf32-exact high part
+                   // and the remainder, three kind::tf32 MMAs per k-step (hi*lo + lo*hi + hi*hi) ~ fp32 accuracy
+  uint32_t stg_bytes;     // epilogue staging tiles (0 for outputs that are stored straight from registers)
   int b_resident;  // the CTA's weight slice [acc_cols, K] stays in shared memory for the whole kernel (b_res_bytes), the
   uint32_t b_res_bytes;   // pipeline stages then carry the A tile only
   int tma_store;   // 16-bit row-major output without residual: staged 32x64 tiles leave through cp.async.bulk.tensor
@@ -141,7 +144,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // the TMA store is a function of the shared-memory address), then barriers and per-column tables
   uint8_t* s_bres = smem + static_cast<size_t>(g.num_stages) * g.stage_bytes;      // resident weights (may be empty)
   uint8_t* s_stage = s_bres + g.b_res_bytes;
-  uint8_t* tail = s_stage + static_cast<size_t>(4 * kSets) * kStageTileBytes;
+  uint8_t* tail = s_stage + g.stg_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -175,7 +178,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     s_sum[i] = 0.f;
     s_sqs[i] = 0.f;
   }
-  if (kXform)
+  if (kXform && sizeof(OutT) == 2)
     for (int i = threadIdx.x; i < g.num_k_blocks * 64; i += kThreads) {
       s_asc[i] = i < g.K ? g.a_scale[i] : 0.f;            // channels past K are TMA zero fill and must stay zero
       s_ash[i] = i < g.K ? g.a_shift[i] : 0.f;
@@ -211,7 +214,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kb = 0; kb < g.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
-          uint8_t* sb = sa + kABytes;
+          uint8_t* sb = sa + (g.tf32x3 ? 2 * kABytes : kABytes);
           mbar_expect_tx(&full_bar[stage], kABytes + (g.b_resident ? 0 : chunks * g.chunk_n * kSwzBytes));
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * g.k_elems_per_block, m0);
           if (!g.b_resident)
@@ -238,6 +241,21 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t sb = g.b_resident ? smem_u32(s_bres) + kb * g.acc_cols * kSwzBytes : sa + kABytes;
           const int k_left = g.K - kb * g.k_elems_per_block;
           const int ksteps = min(g.k_elems_per_block / g.umma_k, (k_left + g.umma_k - 1) / g.umma_k);
+          if constexpr (kXform && sizeof(OutT) == 4) {
+            // 3xTF32: stage = [A hi 16 KB][A lo 16 KB][B hi acc_cols x 128 B][B lo ...]; small terms first
+            const uint32_t sal = sa + kABytes, sbh = sa + 2 * kABytes, sbl = sbh + g.acc_cols * kSwzBytes;
+            for (int c = 0; c < chunks; ++c) {
+              const uint32_t d_tmem = tmem_base + as * g.acc_cols + c * g.chunk_n;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t bo = c * g.chunk_n * kSwzBytes + k * 32;
+                const uint64_t ah = make_sw128_desc(sa + k * 32, 16, 1024), al = make_sw128_desc(sal + k * 32, 16, 1024);
+                const uint64_t bh = make_sw128_desc(sbh + bo, 16, 1024), bl = make_sw128_desc(sbl + bo, 16, 1024);
+                umma_tf32(d_tmem, ah, bl, g.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_tf32(d_tmem, al, bh, g.idesc, 1u);
+                umma_tf32(d_tmem, ah, bh, g.idesc, 1u);
+              }
+            }
+          } else {
           for (int c = 0; c < chunks; ++c) {
             const uint32_t d_tmem = tmem_base + as * g.acc_cols + c * g.chunk_n;
             for (int k = 0; k < ksteps; ++k) {
@@ -246,6 +264,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const uint64_t bdesc = make_sw128_desc(sb + c * g.chunk_n * kSwzBytes + k * 32, 16, 1024);
               umma_f16(d_tmem, adesc, bdesc, g.idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
+          }
           }
           umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs retire
           if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
@@ -266,7 +285,31 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int kb = 0; kb < g.num_k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * g.stage_bytes);
-        xform_rows2<OutT, 4>(sa, r, 64, c0, asc + kb * 256, ash + kb * 256, g.a_act);
+        if constexpr (sizeof(OutT) == 4) {
+          // 3xTF32 operand split: x = hi + lo with hi = x with the 13 low mantissa bits cleared (exact in tf32, so the
+          // tensor core's own fp32 -> tf32 conversion cannot change it) and lo = x - hi (exact in fp32).  Rows of the
+          // A tile and of the weight tile are 128 B = 8 chunks; the 16-byte pieces keep their (swizzled) position.
+          const uint32_t sbh = sa + 2 * kABytes;
+          const int b_rows = chunks * g.chunk_n;
+          for (int row = t; row < kBlockM + b_rows; row += 128) {
+            const uint32_t hi = row < kBlockM ? sa + row * 128 : sbh + (row - kBlockM) * 128;
+            const uint32_t lo = row < kBlockM ? hi + kABytes : hi + g.acc_cols * kSwzBytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t off = static_cast<uint32_t>(i ^ (row & 7)) << 4;
+              uint4 u = lds128_u32(hi + off), l;
+              const uint4 h = make_uint4(u.x & 0xffffe000u, u.y & 0xffffe000u, u.z & 0xffffe000u, u.w & 0xffffe000u);
+              l.x = __float_as_uint(__uint_as_float(u.x) - __uint_as_float(h.x));
+              l.y = __float_as_uint(__uint_as_float(u.y) - __uint_as_float(h.y));
+              l.z = __float_as_uint(__uint_as_float(u.z) - __uint_as_float(h.z));
+              l.w = __float_as_uint(__uint_as_float(u.w) - __uint_as_float(h.w));
+              sts128_u32(hi + off, h);
+              sts128_u32(lo + off, l);
+            }
+          }
+        } else {
+          xform_rows2<OutT, 4>(sa, r, 64, c0, asc + kb * 256, ash + kb * 256, g.a_act);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&xf_bar[stage]);
@@ -781,14 +824,17 @@ int make_tmap_nhwc_sw128(CUtensorMap* map, int dtype, const void* ptr, int B, in
 
 // Tiling plan of the tensor-core kernel (pure host arithmetic; exported as dlb_pw_gemm_plan for the CPU tests).
 // Returns the number of epilogue warp sets (4 or 2), or 0 if no pipeline fits.
-static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform, GemmArgs* gp, size_t* tail_out) {
+static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform, int tf32, GemmArgs* gp, size_t* tail_out) {
   GemmArgs& g = *gp;
   // 16-bit row-major outputs take the 4-set (16 epilogue warps) staged instance; fp32 / phase-shift stores the 2-set one
-  const int sets = (out_dtype != DLB_F32 && shuffle_r == 0) ? 4 : 2;
-  const int esets = sets - (xform ? 1 : 0);      // warp sets that drain accumulators (the last one transforms A tiles)
+  // fp32 operands (3xTF32): 2 draining sets + the set that splits the landed tiles into hi / lo parts
+  const int sets = tf32 ? 3 : ((out_dtype != DLB_F32 && shuffle_r == 0) ? 4 : 2);
+  const int esets = sets - ((xform || tf32) ? 1 : 0);      // warp sets that drain accumulators (the last one transforms tiles)
   const int npad = (N + 15) / 16 * 16;
-  g.k_elems_per_block = 64; g.umma_k = 16;
-  g.num_k_blocks = (K + 63) / 64;
+  g.tf32x3 = tf32 ? 1 : 0;
+  g.k_elems_per_block = tf32 ? 32 : 64; g.umma_k = tf32 ? 8 : 16;
+  g.num_k_blocks = (K + g.k_elems_per_block - 1) / g.k_elems_per_block;
+  g.stg_bytes = (out_dtype != DLB_F32 && shuffle_r == 0) ? static_cast<uint32_t>(4 * sets) * kStageTileBytes : 0u;
   g.num_m_tiles = (M + kBlockM - 1) / kBlockM;
   static const int tune_cpg = [] { const char* e = getenv("DLB_GEMM_CPG"); return e ? atoi(e) : 0; }();   // tuning aid
   // Two chunks per accumulator group share one A fetch (matters when K is large); for small K prefer one chunk per
@@ -796,7 +842,7 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform,
   for (int pass = 0; pass < 2; ++pass) {
     g.n_chunks = (npad + 255) / 256;
     g.chunk_n = ((npad + g.n_chunks - 1) / g.n_chunks + 15) / 16 * 16;
-    int cpg = (pass == 0 && g.n_chunks >= 2 && K > 256 && 2 * g.chunk_n <= 512 && tune_cpg != 1) ? 2 : 1;
+    int cpg = (pass == 0 && !tf32 && g.n_chunks >= 2 && K > 256 && 2 * g.chunk_n <= 512 && tune_cpg != 1) ? 2 : 1;
     int n_groups = (g.n_chunks + cpg - 1) / cpg;
     if (n_groups > 1) {
       // several column groups (each served by its own CTAs): group boundaries on multiples of 64 columns, so every
@@ -821,7 +867,7 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform,
       const int cost_split = (blocks + esets - 1) / esets * 64;
       if (alt_stages >= 2 && g.acc_cols < cost_split * alt_stages) { g.alt_tiles = 1; g.acc_stages = alt_stages; }
     }
-    const size_t tail = static_cast<size_t>(4 * sets) * kStageTileBytes + (3 * kMaxStages + 2 * kMaxAccStages + 2) * 8 + 16 +
+    const size_t tail = g.stg_bytes + (3 * kMaxStages + 2 * kMaxAccStages + 2) * 8 + 16 +
                         4 * static_cast<size_t>(g.n_chunks * g.chunk_n) * 4 + 16 +
                         (xform ? 2 * static_cast<size_t>(g.num_k_blocks) * 64 * 4 : 0);
     *tail_out = tail;
@@ -834,6 +880,14 @@ static int plan_tc(int N, int K, int M, int out_dtype, int shuffle_r, int xform,
     const size_t bres = static_cast<size_t>(g.num_k_blocks) * g.acc_cols * kSwzBytes;
     g.b_resident = 0; g.b_res_bytes = 0;
     const size_t need_stages = K > 256 ? 5 : 3;
+    if (tf32) {
+      // stage = A hi + A lo + weight hi + weight lo; the MMA issue rate (3 per k-step) bounds this kernel, 2 stages do
+      g.stage_bytes = 2 * (kABytes + g.acc_cols * kSwzBytes);
+      if (static_cast<size_t>(kMaxSmem) < 1024 + tail + 2 * static_cast<size_t>(g.stage_bytes)) return 0;
+      g.num_stages = static_cast<int>((kMaxSmem - 1024 - tail) / g.stage_bytes);
+      if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+      return sets;
+    }
     if (bres_on && static_cast<size_t>(kMaxSmem) >= 1024 + tail + bres + need_stages * static_cast<size_t>(kABytes)) {
       g.b_resident = 1; g.b_res_bytes = static_cast<uint32_t>(bres);
       g.stage_bytes = kABytes;
@@ -913,17 +967,18 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.shuffle_r = p->shuffle_r; g.shuffle_h = p->shuffle_h; g.shuffle_w = p->shuffle_w;
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
 
-  const int xform = p->a_scale != nullptr;
+  const int tf32 = p->dtype == DLB_F32;
+  const int xform = !tf32 && p->a_scale != nullptr;
   g.a_scale = p->a_scale; g.a_shift = p->a_shift; g.a_act = p->a_act;
   size_t tail = 0;
-  const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, xform, &g, &tail);
+  const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, xform, tf32, &g, &tail);
   DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
-  g.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, g.chunk_n, 0, 0);
+  g.idesc = make_idesc(tf32 ? 2 : (p->dtype == DLB_BF16 ? 1 : 0), 128, g.chunk_n, 0, 0);
 
   CUtensorMap ta, tb, tc;
-  int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, kBlockM, 64);
+  int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, kBlockM, g.k_elems_per_block);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, 64);
+  rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, g.k_elems_per_block);
   if (rc) return rc;
   // output map for the bulk tensor store of staged 32-row x 64-column tiles (16-bit row-major outputs without residual)
   static const bool tma_store_on = [] { const char* e = getenv("DLB_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
@@ -940,6 +995,18 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   const int grid = split_ctas(&g, p->N);
 
   const bool lean = !p->col_scale && !p->col_shift && !p->row_bias;
+  if (tf32) {
+#define LAUNCHF(LEAN)                                                                                                       \
+  do {                                                                                                                      \
+    DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<float, 3, LEAN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem_bytes));                                                                        \
+    launch_k(pw_gemm_tc_kernel<float, 3, LEAN, false, true>, grid, 64 + 128 * 3, smem_bytes, st, ta, tb, tc, g);                  \
+  } while (0)
+    if (lean) LAUNCHF(true); else LAUNCHF(false);
+#undef LAUNCHF
+    g_launches++;
+    return check_launch("pw_gemm_tc_kernel(tf32x3)");
+  }
   if (xform) {
     // the training-forward project conv: raw depthwise output in, raw project output + statistics out
     DLB_REQUIRE(p->a_shift != nullptr, "pw_gemm: a_scale without a_shift");
@@ -1004,7 +1071,7 @@ extern "C" int dlb_pw_gemm_plan(int M, int N, int K, int out_dtype, int shuffle_
   using namespace dlb;
   GemmArgs g{};
   size_t tail = 0;
-  const int sets = plan_tc(N, K, M, out_dtype, shuffle_r & 0xffff, (shuffle_r >> 16) & 1, &g, &tail);
+  const int sets = plan_tc(N, K, M, out_dtype, shuffle_r & 0xffff, (shuffle_r >> 16) & 1, (shuffle_r >> 17) & 1, &g, &tail);
   if (sets == 0) return DLB_ERR_INVALID;
   plan[0] = sets; plan[1] = g.chunk_n; plan[2] = g.n_chunks; plan[3] = g.chunks_per_group; plan[4] = g.n_groups;
   plan[5] = g.acc_cols; plan[6] = g.acc_stages; plan[7] = g.alt_tiles; plan[8] = g.num_stages;
@@ -1028,7 +1095,17 @@ extern "C" int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream) {
     DLB_REQUIRE(p->R == nullptr, "pw_gemm: residual with shuffle store unsupported");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == DLB_F32) return launch_simt(p, st);
+  if (p->dtype == DLB_F32) {
+    // fp32 operands: 3xTF32 on the tensor cores (error ~1e-6 relative, the fp32 parity mode of BASELINE config 3) unless
+    // the shape is tiny / unaligned / carries an A-operand transform, or DLB_F32_SIMT=1 asks for the exact FMA kernel
+    static const bool force_simt = [] { const char* e = getenv("DLB_F32_SIMT"); return e && e[0] == '1'; }();
+    const bool tc_ok = !force_simt && p->out_dtype == DLB_F32 && p->M >= 64 && p->K % 4 == 0 && p->lda % 4 == 0 &&
+                       p->ldb % 4 == 0 && p->a_scale == nullptr && p->N <= 2048 &&
+                       (reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->Bt) & 15) == 0 &&
+                       p->n_store % 4 == 0 && (p->shuffle_r > 0 || p->ldc % 4 == 0) && (p->R == nullptr || p->ldr % 8 == 0);
+    if (!tc_ok) return launch_simt(p, st);
+    return launch_tc(p, st);
+  }
   const int es = 2;
   DLB_REQUIRE((p->lda * es) % 16 == 0 && (p->ldb * es) % 16 == 0, "pw_gemm: lda/ldb must be 16-byte multiples");
   DLB_REQUIRE((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->Bt) & 15) == 0,

@@ -113,6 +113,13 @@ def test_pw_gemm_plan_fits_every_layer_shape(lib):
                 assert acc_stages <= sets if alt else acc_stages <= 2
                 if alt:
                     assert n_groups == 1
+            # fp32 operands (3xTF32 instance, bit 17): 3 warp sets (2 drain + 1 splits the tiles), 32-element k-blocks,
+            # hi + lo copies of both operands per stage, at least two stages
+            plan = (C.c_int * 19)()
+            assert L.dlb_pw_gemm_plan(M, nn, kk, F32, 1 << 17, plan) == 0, (kk, nn)
+            sets, chunk_n, n_chunks, cpg, n_groups, acc_cols, acc_stages, alt, stages, smem = list(plan)[:10]
+            assert sets == 3 and cpg == 1 and acc_cols <= 256 and acc_cols * acc_stages <= 512
+            assert stages >= 2 and smem <= 227 * 1024 and 1 <= n_groups <= 8, (kk, nn, list(plan))
 
 
 def test_every_kernel_honours_the_dependent_launch_contract():
