@@ -81,6 +81,11 @@ typedef struct {
   const float* a_scale;     /* [K] or NULL */
   const float* a_shift;     /* [K] (required with a_scale) */
   int a_act;
+  /* fp32 operands run as 3xTF32 on the tensor cores (x = hi + lo, hi = x with the 13 low mantissa bits cleared; three
+   * tcgen05 kind::tf32 MMAs per k-step).  The kernel splits the landed tiles itself; for constant weights (inference)
+   * the caller may pass them pre-split: Bt = hi parts, Bt_lo = remainders (same shape / pitch), which removes two
+   * thirds of the in-kernel split work.  NULL = split in the kernel. */
+  const void* Bt_lo;
 } dlb_pw_gemm_params;
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
 /* Tiling plan dlb_pw_gemm would use for a 16-bit GEMM of this shape (host arithmetic only, no device needed):

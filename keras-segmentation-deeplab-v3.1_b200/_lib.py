@@ -28,7 +28,7 @@ class PwGemmParams(C.Structure):
         ("col_scale", vp), ("col_shift", vp), ("row_bias", vp), ("rows_per_img", i32), ("ld_row_bias", i32),
         ("act", i32), ("R", vp), ("ldr", i32), ("stat_sum", vp), ("stat_sqs", vp),
         ("shuffle_r", i32), ("shuffle_h", i32), ("shuffle_w", i32),
-        ("a_scale", vp), ("a_shift", vp), ("a_act", i32),
+        ("a_scale", vp), ("a_shift", vp), ("a_act", i32), ("Bt_lo", vp),
     ]
 
 

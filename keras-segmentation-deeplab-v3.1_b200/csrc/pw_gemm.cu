@@ -62,6 +62,7 @@ struct GemmArgs {
   const float* a_scale;   // A-operand transform (kXform): A := act(A * a_scale[k] + a_shift[k]) applied to the landed tile
   const float* a_shift;
   int a_act;
+  int b_lo_given;  // tf32x3: the caller supplies the weights already split (Bt = hi part, Bt_lo = remainder)
   int tf32x3;      // fp32 operands on the tensor cores: A and B tiles are split in shared memory into a tf32-exact high part
                    // and the remainder, three kind::tf32 MMAs per k-step (hi*lo + lo*hi + hi*hi) ~ fp32 accuracy
   uint32_t stg_bytes;     // epilogue staging tiles (0 for outputs that are stored straight from registers)
@@ -126,7 +127,8 @@ template <> __device__ __forceinline__ float2 word_to_float2<float>(uint32_t w) 
 template <typename OutT, int kSets, bool kLean, bool kTma, bool kXform>
 __global__ void __launch_bounds__(64 + 128 * kSets, 1)
 pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_c, const GemmArgs g) {
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_bl,
+                  const GemmArgs g) {
   constexpr int kThreads = 64 + 128 * kSets;
   constexpr int kEpiSets = kXform ? kSets - 1 : kSets;
   constexpr int kEpiThreads = 128 * kEpiSets;
@@ -164,6 +166,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (kTma) tma_prefetch_desc(&tmap_c);
+    if (g.b_lo_given) tma_prefetch_desc(&tmap_bl);
     for (int i = 0; i < g.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kMaxAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], g.alt_tiles ? 4 : 4 * kEpiSets); }
     mbar_init(bres_bar, 1);
@@ -215,12 +218,17 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * g.stage_bytes;
           uint8_t* sb = sa + (g.tf32x3 ? 2 * kABytes : kABytes);
-          mbar_expect_tx(&full_bar[stage], kABytes + (g.b_resident ? 0 : chunks * g.chunk_n * kSwzBytes));
+          const uint32_t b_bytes = g.b_resident ? 0 : chunks * g.chunk_n * kSwzBytes;
+          mbar_expect_tx(&full_bar[stage], kABytes + (g.b_lo_given ? 2 * b_bytes : b_bytes));
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * g.k_elems_per_block, m0);
           if (!g.b_resident)
-            for (int c = 0; c < chunks; ++c)
+            for (int c = 0; c < chunks; ++c) {
               tma_load_2d(sb + c * g.chunk_n * kSwzBytes, &tmap_b, &full_bar[stage], kb * g.k_elems_per_block,
                           (grp * g.chunks_per_group + c) * g.chunk_n);
+              if (g.b_lo_given)     // pre-split weights: the remainder goes straight into the "B lo" half of the stage
+                tma_load_2d(sb + (g.acc_cols + c * g.chunk_n) * kSwzBytes, &tmap_bl, &full_bar[stage],
+                            kb * g.k_elems_per_block, (grp * g.chunks_per_group + c) * g.chunk_n);
+            }
           if (++stage == g.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -290,7 +298,7 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // tensor core's own fp32 -> tf32 conversion cannot change it) and lo = x - hi (exact in fp32).  Rows of the
           // A tile and of the weight tile are 128 B = 8 chunks; the 16-byte pieces keep their (swizzled) position.
           const uint32_t sbh = sa + 2 * kABytes;
-          const int b_rows = chunks * g.chunk_n;
+          const int b_rows = g.b_lo_given ? 0 : chunks * g.chunk_n;
           for (int row = t; row < kBlockM + b_rows; row += 128) {
             const uint32_t hi = row < kBlockM ? sa + row * 128 : sbh + (row - kBlockM) * 128;
             const uint32_t lo = row < kBlockM ? hi + kABytes : hi + g.acc_cols * kSwzBytes;
@@ -975,11 +983,19 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
   g.idesc = make_idesc(tf32 ? 2 : (p->dtype == DLB_BF16 ? 1 : 0), 128, g.chunk_n, 0, 0);
 
-  CUtensorMap ta, tb, tc;
+  CUtensorMap ta, tb, tc, tbl;
   int rc = make_tmap_2d(&ta, p->dtype, p->A, p->M, p->K, p->lda, kBlockM, g.k_elems_per_block);
   if (rc) return rc;
   rc = make_tmap_2d(&tb, p->dtype, p->Bt, p->N, p->K, p->ldb, g.chunk_n, g.k_elems_per_block);
   if (rc) return rc;
+  tbl = tb;
+  g.b_lo_given = 0;
+  if (tf32 && p->Bt_lo) {
+    DLB_REQUIRE((reinterpret_cast<uintptr_t>(p->Bt_lo) & 15) == 0, "pw_gemm: Bt_lo must be 16-byte aligned");
+    rc = make_tmap_2d(&tbl, p->dtype, p->Bt_lo, p->N, p->K, p->ldb, g.chunk_n, g.k_elems_per_block);
+    if (rc) return rc;
+    g.b_lo_given = 1;
+  }
   // output map for the bulk tensor store of staged 32-row x 64-column tiles (16-bit row-major outputs without residual)
   static const bool tma_store_on = [] { const char* e = getenv("DLB_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
   g.tma_store = 0;
@@ -1000,7 +1016,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   do {                                                                                                                      \
     DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<float, 3, LEAN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem_bytes));                                                                        \
-    launch_k(pw_gemm_tc_kernel<float, 3, LEAN, false, true>, grid, 64 + 128 * 3, smem_bytes, st, ta, tb, tc, g);                  \
+    launch_k(pw_gemm_tc_kernel<float, 3, LEAN, false, true>, grid, 64 + 128 * 3, smem_bytes, st, ta, tb, tc, tbl, g);                  \
   } while (0)
     if (lean) LAUNCHF(true); else LAUNCHF(false);
 #undef LAUNCHF
@@ -1017,7 +1033,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   do {                                                                                                                    \
     DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, 4, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem_bytes));                                                                      \
-    launch_k(pw_gemm_tc_kernel<OT, 4, true, true, true>, grid, 64 + 128 * 4, smem_bytes, st, ta, tb, tc, g);                    \
+    launch_k(pw_gemm_tc_kernel<OT, 4, true, true, true>, grid, 64 + 128 * 4, smem_bytes, st, ta, tb, tc, tbl, g);                    \
   } while (0)
     if (p->out_dtype == DLB_F16) LAUNCHX(__half); else LAUNCHX(__nv_bfloat16);
 #undef LAUNCHX
@@ -1028,7 +1044,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   do {                                                                                                                \
     DLB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem_bytes));                                                                  \
-    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA, false>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, tc, g);                 \
+    launch_k(pw_gemm_tc_kernel<OT, SETS, LEAN, TMA, false>, grid, 64 + 128 * SETS, smem_bytes, st, ta, tb, tc, tbl, g);                 \
   } while (0)
 #define LAUNCH2(OT, SETS, TMA) do { if (lean) LAUNCH(OT, SETS, true, TMA); else LAUNCH(OT, SETS, false, TMA); } while (0)
 #define LAUNCH3(OT) do { if (sets == 4) { if (g.tma_store) LAUNCH2(OT, 4, true); else LAUNCH2(OT, 4, false); } else LAUNCH2(OT, 2, false); } while (0)

@@ -417,7 +417,18 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     # inference forward (BatchNorm folded into the producing kernel's epilogue)
     # ------------------------------------------------------------------------------------------------
+    def _wi(self, name, cols=None):
+        """inference-time [N, K] weight operand of a 1x1 conv: the 16-bit copy, or in fp32 mode the pre-split (hi, lo)
+        pair of the 3xTF32 GEMM (weights are constant between optimizer steps; re-split in _fold_all)."""
+        if self.dtype == torch.float32:
+            hi, lo = self._wsplit[name]
+            return (hi, lo) if cols is None else (hi[:, cols], lo[:, cols])
+        w = self.wcopies[name]["nk"]
+        return w if cols is None else w[:, cols]
+
     def _fold_all(self, ws):
+        if self.dtype == torch.float32:
+            self._wsplit = {name: ops.f32_split(d["nk"]) for name, d in self.wcopies.items()}
         o = 0
         for b in self.bns:
             sc, sh = ws["fold"][2 * o:2 * o + b.C], ws["fold"][2 * o + b.C:2 * o + 2 * b.C]
@@ -454,7 +465,7 @@ class Engine:
             if b["bid"]:
                 a_e = view(T[free[0]], B, g["h"], g["w"], b["mid"])
                 bn = b["expand_bn"]
-                ops.pw_gemm(xin, self.wcopies[b["expand"].name]["nk"], a_e, col_scale=bn.fscale, col_shift=bn.fshift,
+                ops.pw_gemm(xin, self._wi(b["expand"].name), a_e, col_scale=bn.fscale, col_shift=bn.fshift,
                             act=ACT_RELU6)
             else:
                 a_e = xin
@@ -464,7 +475,7 @@ class Engine:
                             pad_left=g["pl"], out_scale=bn.fscale, out_shift=bn.fshift, out_act=ACT_RELU6)
             xo = view(T[free[2]], B, g["ho"], g["wo"], b["cout"])
             bn = b["project_bn"]
-            ops.pw_gemm(a_d, self.wcopies[b["project"].name]["nk"], xo, col_scale=bn.fscale, col_shift=bn.fshift,
+            ops.pw_gemm(a_d, self._wi(b["project"].name), xo, col_scale=bn.fscale, col_shift=bn.fshift,
                         residual=xin if b["skip"] else None)
             x, cur = xo, free[2]
         self._aspp_head_infer(ws, x, B)
@@ -515,19 +526,19 @@ class Engine:
         wcp = self.wcopies["concat_projection"]
         ops.pw_gemm(ws["b4"], wcp["nk32"], ws["rowbias"], K=256, col_scale=bn.fscale)
         bn0 = self.aspp0_bn
-        ops.pw_gemm(x16, self.wcopies["aspp0"]["nk"], ws["a_a0"], col_scale=bn0.fscale, col_shift=bn0.fshift,
+        ops.pw_gemm(x16, self._wi("aspp0"), ws["a_a0"], col_scale=bn0.fscale, col_shift=bn0.fshift,
                     act=ACT_RELU)
-        ops.pw_gemm(ws["a_a0"], wcp["nk"][:, 256:], ws["feat"], col_scale=bn.fscale, col_shift=bn.fshift,
-                    row_bias=ws["rowbias"], rows_per_img=fh * fw, act=ACT_RELU)
-        self._head_fwd(ws, ws["feat"])
+        ops.pw_gemm(ws["a_a0"], self._wi("concat_projection", slice(256, None)), ws["feat"], col_scale=bn.fscale,
+                    col_shift=bn.fshift, row_bias=ws["rowbias"], rows_per_img=fh * fw, act=ACT_RELU)
+        self._head_fwd(ws, ws["feat"], infer=True)
 
-    def _head_fwd(self, ws, feat):
-        hw = self.wcopies[self.head_conv.name]
+    def _head_fwd(self, ws, feat, infer=False):
+        w = self._wi(self.head_conv.name) if infer else self.wcopies[self.head_conv.name]["nk"]
         bias = self.head_conv.params[1].data
         if self.head == "subpixel":
-            ops.pw_gemm(feat, hw["nk"], ws["logits"], col_shift=bias, shuffle=(self.scale, self.fh, self.fw))
+            ops.pw_gemm(feat, w, ws["logits"], col_shift=bias, shuffle=(self.scale, self.fh, self.fw))
         else:
-            ops.pw_gemm(feat, hw["nk"], ws["logits"], col_shift=bias, n_store=self.ldl)
+            ops.pw_gemm(feat, w, ws["logits"], col_shift=bias, n_store=self.ldl)
 
     # ------------------------------------------------------------------------------------------------
     # training forward / backward

@@ -36,7 +36,11 @@ def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional
             n_store: Optional[int] = None, col_scale=None, col_shift=None, row_bias=None, rows_per_img: int = 1,
             act: int = ACT_NONE, residual=None, stat_sum=None, stat_sqs=None, shuffle: Optional[Tuple[int, int, int]] = None,
             a_scale=None, a_shift=None, a_act: int = ACT_NONE):
-    """out[M, :n_store] = epilogue(A'[M, K] @ Bt[N, K]^T), A' = a_act(A * a_scale + a_shift) if given; see dlb_pw_gemm."""
+    """out[M, :n_store] = epilogue(A'[M, K] @ Bt[N, K]^T), A' = a_act(A * a_scale + a_shift) if given; see dlb_pw_gemm.
+    fp32 inference weights may be passed pre-split as a tuple (hi, lo) from `f32_split` (3xTF32, see dlb_pw_gemm_params)."""
+    Bt_lo = None
+    if isinstance(Bt, (tuple, list)):
+        Bt, Bt_lo = Bt
     L.require_cuda(A, Bt, out)
     M, Ka, lda = _mat(A)
     Nb, Kb, ldb = _mat(Bt)
@@ -63,8 +67,16 @@ def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional
         p.R, p.ldr = residual.data_ptr(), _mat(residual)[2]
     p.stat_sum, p.stat_sqs = L.ptr(stat_sum), L.ptr(stat_sqs)
     p.a_scale, p.a_shift, p.a_act = L.ptr(a_scale), L.ptr(a_shift), a_act
+    p.Bt_lo = L.ptr(Bt_lo)
     L.check(L.lib().dlb_pw_gemm(C.byref(p), L.stream_ptr()), "pw_gemm")
     return out
+
+
+def f32_split(w: torch.Tensor):
+    """fp32 tensor -> (hi, lo) with hi = w with the 13 low mantissa bits cleared (exactly representable in tf32) and
+    lo = w - hi (exact).  Host-side preparation of constant inference weights for the 3xTF32 GEMM."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, (w - hi).contiguous()
 
 
 def pw_wgrad_workspace_bytes(M: int, N: int, K: int) -> int:

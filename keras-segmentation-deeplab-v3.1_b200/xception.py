@@ -151,7 +151,7 @@ class XceptionEngine(Engine):
                         out_act=ACT_RELU if depth_activation else ACT_NONE)
         cout = sep["pw"].cout
         z = out if out is not None else self._buf(tag + "/pw", B, Ho, Wo, cout)
-        ops.pw_gemm(y, self.wcopies[sep["pw"].name]["nk"], z, N=cout, n_store=cout, col_scale=pwbn.fscale,
+        ops.pw_gemm(y, self._wi(sep["pw"].name), z, N=cout, n_store=cout, col_scale=pwbn.fscale,
                     col_shift=pwbn.fshift, act=ACT_RELU if depth_activation else ACT_NONE, residual=residual)
         return z
 
@@ -176,7 +176,7 @@ class XceptionEngine(Engine):
                 xin = ops.subsample(x, self._buf(tag + "/sub", B, (H + s - 1) // s, (W + s - 1) // s, C), s)
             bn = blk["shortcut_bn"]
             shortcut = self._buf(tag + "/short", xin.shape[0], xin.shape[1], xin.shape[2], blk["cout"])
-            ops.pw_gemm(xin, self.wcopies[blk["shortcut"].name]["nk"], shortcut, col_scale=bn.fscale, col_shift=bn.fshift)
+            ops.pw_gemm(xin, self._wi(blk["shortcut"].name), shortcut, col_scale=bn.fscale, col_shift=bn.fshift)
         elif blk["skip"] == "sum":
             shortcut = x
         r, skip_t = x, None
@@ -230,11 +230,11 @@ class XceptionEngine(Engine):
             # (dlb_sepconv_fused_fwd; deeplabv3p.py:385-399)
             pw_bns = [bn0] + [s_["pw_bn"] for s_ in self.aspp]
             ops.sepconv_fused_fwd(x, [0] + list(self.atrous),
-                                  [self.wcopies["aspp0"]["nk"]] + [self.wcopies[s_["pw"].name]["nk"] for s_ in self.aspp],
+                                  [self._wi("aspp0")] + [self.wcopies[s_["pw"].name]["nk"] for s_ in self.aspp],
                                   self._dw_pack("aspp", self.aspp), [b_.fscale for b_ in pw_bns],
                                   [b_.fshift for b_ in pw_bns], [cat[..., 256 * i:256 * (i + 1)] for i in range(4)])
         else:
-            ops.pw_gemm(x, self.wcopies["aspp0"]["nk"], cat[..., 0:256], N=256, n_store=256, col_scale=bn0.fscale,
+            ops.pw_gemm(x, self._wi("aspp0"), cat[..., 0:256], N=256, n_store=256, col_scale=bn0.fscale,
                         col_shift=bn0.fshift, act=ACT_RELU)
         if fused and fw <= 128:
             pass
@@ -245,20 +245,20 @@ class XceptionEngine(Engine):
                              [s_["dw_bn"].fscale for s_ in self.aspp], [s_["dw_bn"].fshift for s_ in self.aspp], dws)
             for i, sep in enumerate(self.aspp):
                 pwbn = sep["pw_bn"]
-                ops.pw_gemm(dws[i], self.wcopies[sep["pw"].name]["nk"], cat[..., 256 * (i + 1):256 * (i + 2)], N=256,
+                ops.pw_gemm(dws[i], self._wi(sep["pw"].name), cat[..., 256 * (i + 1):256 * (i + 2)], N=256,
                             n_store=256, col_scale=pwbn.fscale, col_shift=pwbn.fshift, act=ACT_RELU)
         else:
             for i, sep in enumerate(self.aspp):
                 self._sepconv(f"aspp{i + 1}", x, sep, 1, self.atrous[i], True, out=cat[..., 256 * (i + 1):256 * (i + 2)])
         feat = self._buf("aspp_out", B, fh, fw, 256)
-        ops.pw_gemm(cat, wcp["nk"][:, 256:], feat, col_scale=cbn.fscale, col_shift=cbn.fshift, row_bias=rowbias,
+        ops.pw_gemm(cat, self._wi("concat_projection", slice(256, None)), feat, col_scale=cbn.fscale, col_shift=cbn.fshift, row_bias=rowbias,
                     rows_per_img=fh * fw, act=ACT_RELU)
         # ---- decoder (deeplabv3p.py:414-429)
         dh, dw_ = H // 4, W // 4
         dcat = self._buf("dec_cat", B, dh, dw_, 304)
         ops.resize_bilinear(feat, dcat, 256)
         fbn = self.feature_projection0_bn
-        ops.pw_gemm(skip1, self.wcopies["feature_projection0"]["nk"], dcat[..., 256:304], N=48, n_store=48,
+        ops.pw_gemm(skip1, self._wi("feature_projection0"), dcat[..., 256:304], N=48, n_store=48,
                     col_scale=fbn.fscale, col_shift=fbn.fshift, act=ACT_RELU)
         if fused and dw_ <= 128:
             # decoder_conv0/1 (deeplabv3p.py:426-429): depthwise 3x3 + BN + ReLU + 1x1 + BN + ReLU, one kernel each
@@ -273,7 +273,7 @@ class XceptionEngine(Engine):
             d = self._sepconv("decoder_conv1", d, self.decoder[1], 1, 1, True)
         # ---- head
         hw = self.wcopies[self.head_conv.name]
-        ops.pw_gemm(d, hw["nk"], ws["logits"], col_shift=self.head_conv.params[1].data, n_store=self.ldl)
+        ops.pw_gemm(d, self._wi(self.head_conv.name), ws["logits"], col_shift=self.head_conv.params[1].data, n_store=self.ldl)
         ops.resize_softmax_fwd(ws["logits"], self.n_out, H, W, ws["probs"] if want_probs else None,
                                ws["argmax"] if want_argmax or not want_probs else None)
         return ws["probs"] if want_probs else ws["argmax"]
