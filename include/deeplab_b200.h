@@ -195,9 +195,12 @@ int dlb_aspp_dw3_fwd(int B, int H, int W, int C, int dtype, const void* x, const
  * Replaces the spatial ASPP branches aspp0 (rate 0 = plain 1x1, no depthwise stage) and aspp1..3 = SepConv_BN(x, 256,
  * rate=atrous_rates[i], depth_activation=True, epsilon=1e-5) (deeplabv3p.py:385-399, SepConv_BN :47-84; stride 1,
  * TF 'same' zero padding) and, with one branch, decoder_conv0/1 (:426-429), BatchNorms folded (inference).
- * x: [B,H,W,C] NHWC f16/bf16, W <= 128, C % 8 == 0.  w_pw[i]: [N, C] (C contiguous), N in {64,128,192,256}.
+ * x: [B,H,W,C] NHWC f16/bf16, W <= 128, C % 8 == 0.  w_pw[i]: [N, C] (C contiguous), N a multiple of 8, 8..256.
  * out[i]: rows of pitch ldc (a channel slice of the concat buffer).  dw_pack: dlb_sepconv_pack_dw() output for the
- * branches with rate > 0, in branch order. */
+ * branches with rate > 0, in branch order.
+ * With res[i] != NULL the kernel is also the inference form of the second half of _inverted_res_block
+ * (deeplabv3p.py:186-206): out = res + BN(project(relu6(BN(depthwise(x))))) with dw_act = RELU6, pw_act = NONE -- the
+ * 6C-wide expanded activation is then read once and its depthwise result never exists in memory. */
 typedef struct {
   int B, H, W, C, N;
   int dtype;
@@ -211,6 +214,8 @@ typedef struct {
   void* out[4];
   int ldc;
   int dw_act, pw_act;         /* dlb_act after the depthwise BN / pointwise BN */
+  const void* res[4];         /* optional residual [B,H,W,N] rows of pitch ldr, added after pw_act (NULL = none) */
+  int ldr;
 } dlb_sepconv_fused_params;
 int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* stream);
 /* Packs depthwise kernels w_dw[i] [3,3,C] fp32 + folded BN scale/shift[i] [C] into the per-64-channel-chunk blocks the

@@ -94,7 +94,7 @@ class SepconvFusedParams(C.Structure):
     _fields_ = [
         ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("N", i32), ("dtype", i32), ("n_branches", i32),
         ("rates", i32 * 4), ("x", vp), ("w_pw", vp * 4), ("dw_pack", vp), ("pw_scale", vp * 4), ("pw_shift", vp * 4),
-        ("out", vp * 4), ("ldc", i32), ("dw_act", i32), ("pw_act", i32),
+        ("out", vp * 4), ("ldc", i32), ("dw_act", i32), ("pw_act", i32), ("res", vp * 4), ("ldr", i32),
     ]
 
 

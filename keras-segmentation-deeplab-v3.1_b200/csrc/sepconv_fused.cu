@@ -70,7 +70,9 @@ struct FusedArgs {
   const float* pw_scale[kFMaxBr];
   const float* pw_shift[kFMaxBr];
   void* out[kFMaxBr];
-  int ldc, dw_act, pw_act;
+  const void* res[kFMaxBr];       // optional residual added after the pointwise BN / activation (MobileNetV2 skip)
+  int ldc, ldr, dw_act, pw_act;
+  int n_valid;                    // real output channels (N is padded to a multiple of 64: zero-filled weight rows)
   uint32_t idesc;
   unsigned int* ticket;           // zeroed by the host before every launch
 };
@@ -155,8 +157,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   for (int i = threadIdx.x; i < a.n_br * 512; i += kFThreads) {
     const int br = i >> 9, j = i & 511;
     float v;
-    if (j < 256) v = (j < a.N && a.pw_scale[br]) ? a.pw_scale[br][j] : 1.f;
-    else v = (j - 256 < a.N && a.pw_shift[br]) ? a.pw_shift[br][j - 256] : 0.f;
+    if (j < 256) v = (j < a.n_valid && a.pw_scale[br]) ? a.pw_scale[br][j] : 1.f;
+    else v = (j - 256 < a.n_valid && a.pw_shift[br]) ? a.pw_shift[br][j - 256] : 0.f;
     s_pw[i] = v;
   }
   tc_fence_before();
@@ -253,6 +255,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       const float* sc = s_pw + g.br * 512;
       const float* sh = sc + 256;
       T* out = reinterpret_cast<T*>(a.out[g.br]);
+      const T* res = reinterpret_cast<const T*>(a.res[g.br]);
       mbar_wait(&t_full[as], (n >> 1) & 1);
       tc_fence_after();
       for (int j64 = 0; j64 < a.N; j64 += 64) {
@@ -283,8 +286,16 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int i = 0; i < 8; ++i) {
           const int row = i * 4 + (lane >> 3);
           const int p = quad * 32 + row;
-          if (p < rows_valid) {
-            const uint4 pk = stg[row * 8 + (cchunk ^ (row & 7))];
+          if (p < rows_valid && j64 + cchunk * 8 < a.n_valid) {
+            uint4 pk = stg[row * 8 + (cchunk ^ (row & 7))];
+            if (res) {
+              float o[8], rr[8];
+              Vec8<T>::ld(reinterpret_cast<const T*>(&pk), o);
+              Vec8<T>::ld(res + (m0 + p) * a.ldr + j64 + cchunk * 8, rr);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] += rr[q];
+              Vec8<T>::st(reinterpret_cast<T*>(&pk), o);
+            }
             *reinterpret_cast<uint4*>(out + (m0 + p) * a.ldc + j64 + cchunk * 8) = pk;
           }
         }
@@ -444,19 +455,22 @@ extern "C" int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* st
   DLB_REQUIRE(p->n_branches >= 1 && p->n_branches <= kFMaxBr, "sepconv_fused_fwd: 1..4 branches");
   DLB_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0 && p->W <= 128, "sepconv_fused_fwd: W must be <= 128 (got %d)", p->W);
   DLB_REQUIRE(p->C % 8 == 0 && p->C >= 16, "sepconv_fused_fwd: C must be a multiple of 8");
-  DLB_REQUIRE(p->N % 64 == 0 && p->N >= 64 && p->N <= 256, "sepconv_fused_fwd: N must be 64, 128, 192 or 256");
+  DLB_REQUIRE(p->N % 8 == 0 && p->N >= 8 && p->N <= 256, "sepconv_fused_fwd: N must be a multiple of 8, 8..256 (got %d)", p->N);
   DLB_REQUIRE(p->ldc % 8 == 0 && p->ldc >= p->N, "sepconv_fused_fwd: ldc must be a multiple of 8 and >= N");
   DLB_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0, "sepconv_fused_fwd: x must be 16-byte aligned");
   FusedArgs a{};
-  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = p->N;
+  // accumulator / weight-tile width: N rounded up to a 64-column epilogue block; the weight rows past N are zero-filled
+  // by the tensor map (out-of-bounds box rows), the store masks them
+  const int n_pad = (p->N + 63) / 64 * 64;
+  a.B = p->B; a.H = p->H; a.W = p->W; a.C = p->C; a.N = n_pad; a.n_valid = p->N;
   a.TH = 128 / p->W; if (a.TH > p->H) a.TH = p->H;
   a.tiles_y = (p->H + a.TH - 1) / a.TH;
   a.n_br = p->n_branches;
   a.n_items = p->B * a.tiles_y * a.n_br;
   a.nk = (p->C + 63) / 64;
   a.pack = static_cast<const uint8_t*>(p->dw_pack);
-  a.ldc = p->ldc; a.dw_act = p->dw_act; a.pw_act = p->pw_act;
-  a.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, p->N, 0, 0);
+  a.ldc = p->ldc; a.ldr = p->ldr; a.dw_act = p->dw_act; a.pw_act = p->pw_act;
+  a.idesc = make_idesc(p->dtype == DLB_BF16 ? 1 : 0, 128, n_pad, 0, 0);
   WMaps wm;
   std::memset(&wm, 0, sizeof(wm));
   int n_dw = 0;
@@ -469,7 +483,10 @@ extern "C" int dlb_sepconv_fused_fwd(const dlb_sepconv_fused_params* p, void* st
     a.pack_idx[i] = p->rates[i] > 0 ? n_dw++ : 0;
     a.pw_scale[i] = p->pw_scale[i]; a.pw_shift[i] = p->pw_shift[i];
     a.out[i] = p->out[i];
-    int rc = make_tmap_2d(&wm.m[i], p->dtype, p->w_pw[i], p->N, p->C, p->C, p->N, 64);
+    a.res[i] = p->res[i];
+    DLB_REQUIRE(p->res[i] == nullptr || (p->ldr % 8 == 0 && p->ldr >= p->N && (reinterpret_cast<uintptr_t>(p->res[i]) & 15) == 0),
+                "sepconv_fused_fwd: branch %d: residual needs ldr %% 8 == 0, ldr >= N and 16-byte alignment", i);
+    int rc = make_tmap_2d(&wm.m[i], p->dtype, p->w_pw[i], p->N, p->C, p->C, n_pad, 64);
     if (rc) return rc;
   }
   DLB_REQUIRE(n_dw == 0 || p->dw_pack, "sepconv_fused_fwd: dw_pack missing");

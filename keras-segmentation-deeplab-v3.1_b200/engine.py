@@ -115,6 +115,9 @@ class Engine:
         # DLB_FUSE_DW_BN=0 restores the materialised activation (A/B measurements only).
         import os
         self.fuse_dw_bn = os.environ.get("DLB_FUSE_DW_BN", "1") != "0"
+        # inference: depthwise -> project of an inverted-residual block in one kernel (DLB_FUSE_MBCONV=0: separate)
+        self.fuse_dw_project = os.environ.get("DLB_FUSE_MBCONV", "1") != "0"
+        self._mb_packs = {}
 
     @property
     def loss_scale(self) -> float:
@@ -427,6 +430,7 @@ class Engine:
         return w if cols is None else w[:, cols]
 
     def _fold_all(self, ws):
+        self._mb_packs = {}           # packed depthwise taps + folded BN of the fused depthwise -> project kernel
         if self.dtype == torch.float32:
             self._wsplit = {name: ops.f32_split(d["nk"]) for name, d in self.wcopies.items()}
         o = 0
@@ -469,14 +473,25 @@ class Engine:
                             act=ACT_RELU6)
             else:
                 a_e = xin
-            a_d = view(T[free[1]], B, g["ho"], g["wo"], b["mid"])
-            bn = b["dw_bn"]
-            ops.dw_conv_fwd(a_e, b["dw"].params[0].data, a_d, stride=b["stride"], dilation=b["rate"], pad_top=g["pt"],
-                            pad_left=g["pl"], out_scale=bn.fscale, out_shift=bn.fshift, out_act=ACT_RELU6)
             xo = view(T[free[2]], B, g["ho"], g["wo"], b["cout"])
-            bn = b["project_bn"]
-            ops.pw_gemm(a_d, self._wi(b["project"].name), xo, col_scale=bn.fscale, col_shift=bn.fshift,
-                        residual=xin if b["skip"] else None)
+            dbn, pbn = b["dw_bn"], b["project_bn"]
+            if self.fuse_dw_project and self.dtype != torch.float32 and b["stride"] == 1 and g["w"] <= 128 \
+                    and b["cout"] <= 256 and b["mid"] >= 16:
+                # depthwise + BN + relu6 -> project + BN (+ add) in one kernel: the expanded activation is read once,
+                # its depthwise result is produced in shared memory as the tensor-core A operand (sepconv_fused.cu)
+                pk = self._mb_packs.get(b["bid"])
+                if pk is None:
+                    pk = self._mb_packs[b["bid"]] = ops.sepconv_pack_dw([b["dw"].params[0].data], [dbn.fscale],
+                                                                        [dbn.fshift], self.dtype)
+                ops.sepconv_fused_fwd(a_e, [b["rate"]], [self.wcopies[b["project"].name]["nk"]], pk, [pbn.fscale],
+                                      [pbn.fshift], [xo], dw_act=ACT_RELU6, pw_act=ACT_NONE,
+                                      residuals=[xin if b["skip"] else None])
+            else:
+                a_d = view(T[free[1]], B, g["ho"], g["wo"], b["mid"])
+                ops.dw_conv_fwd(a_e, b["dw"].params[0].data, a_d, stride=b["stride"], dilation=b["rate"], pad_top=g["pt"],
+                                pad_left=g["pl"], out_scale=dbn.fscale, out_shift=dbn.fshift, out_act=ACT_RELU6)
+                ops.pw_gemm(a_d, self._wi(b["project"].name), xo, col_scale=pbn.fscale, col_shift=pbn.fshift,
+                            residual=xin if b["skip"] else None)
             x, cur = xo, free[2]
         self._aspp_head_infer(ws, x, B)
         C_ = self.n_out

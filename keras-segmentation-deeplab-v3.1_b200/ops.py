@@ -370,7 +370,7 @@ def sepconv_pack_dw(ws, scales, shifts, dtype: torch.dtype) -> torch.Tensor:
 
 
 def sepconv_fused_fwd(x: torch.Tensor, rates, w_pws, dw_pack, pw_scales, pw_shifts, outs, dw_act=L.ACT_RELU,
-                      pw_act=L.ACT_RELU):
+                      pw_act=L.ACT_RELU, residuals=None):
     """Fused [atrous depthwise 3x3 + BN + act] -> [1x1 + BN + act] branches sharing the input x (rate 0 = plain 1x1).
 
     x [B,H,W,C] f16/bf16; w_pws[i] [N,C]; outs[i]: [B,H,W,N] views (channel slices of a concat buffer are fine)."""
@@ -387,6 +387,9 @@ def sepconv_fused_fwd(x: torch.Tensor, rates, w_pws, dw_pack, pw_scales, pw_shif
         p.pw_scale[i] = L.ptr(pw_scales[i])
         p.pw_shift[i] = L.ptr(pw_shifts[i])
         p.out[i] = outs[i].data_ptr()
+        if residuals is not None and residuals[i] is not None:
+            p.res[i] = residuals[i].data_ptr()
+            p.ldr = residuals[i].stride(2)
     p.x = x.data_ptr()
     p.dw_pack = L.ptr(dw_pack)
     p.ldc = outs[0].stride(2)

@@ -481,3 +481,38 @@ def test_pw_gemm_and_wgrad_a_operand_transform(dt, M, K, N):
     dW2 = torch.zeros(K, N, device="cuda")
     ops.pw_wgrad(raw, dY, dW2, beta=0.0)
     assert rel_err(dW2, raw.double().t() @ dY.double()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# second half of _inverted_res_block in one kernel (inference): depthwise 3x3 (rate r) + BN + relu6 -> project 1x1 + BN
+# (+ add), deeplabv3p.py:186-206, for every stride-1 MobileNetV2 block shape at 64x64 / 128x128
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("HW,C,N,rate,skip", [(128, 144, 24, 1, True), (64, 192, 32, 1, True), (64, 192, 64, 1, False),
+                                               (64, 384, 64, 2, True), (64, 384, 96, 2, False), (64, 576, 96, 2, True),
+                                               (64, 576, 160, 2, False), (64, 960, 160, 4, True)])
+def test_fused_depthwise_project_matches_unfused(dt, HW, C, N, rate, skip):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(C + N + rate)
+    B = 2
+    x = (torch.rand(B, HW, HW, C, device="cuda", generator=g) * 6).to(dt)            # relu6 output of the expand conv
+    wd = torch.randn(3, 3, C, 1, device="cuda", generator=g) / 3
+    dsc = torch.rand(C, device="cuda", generator=g) + 0.5
+    dsh = torch.randn(C, device="cuda", generator=g) * 0.5
+    wp = (torch.randn(N, C, device="cuda", generator=g) / math.sqrt(C)).to(dt)
+    psc = torch.rand(N, device="cuda", generator=g) + 0.5
+    psh = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(B, HW, HW, N, device="cuda", generator=g).to(dt) if skip else None
+    out = torch.empty(B, HW, HW, N, device="cuda", dtype=dt)
+    pk = ops.sepconv_pack_dw([wd], [dsc], [dsh], dt)
+    ops.sepconv_fused_fwd(x, [rate], [wp], pk, [psc], [psh], [out], dw_act=ops.ACT_RELU6, pw_act=ops.ACT_NONE,
+                          residuals=[res])
+    # fp32 reference of the same chain on the stored (rounded) operands
+    xn = x.float().permute(0, 3, 1, 2)
+    y = F.conv2d(xn, wd.to(dt).float().reshape(3, 3, C).permute(2, 0, 1).unsqueeze(1), padding=rate, dilation=rate, groups=C)
+    a = (y * dsc.to(dt).float().view(1, C, 1, 1) + dsh.to(dt).float().view(1, C, 1, 1)).clamp(0, 6).permute(0, 2, 3, 1)
+    ref = (a.reshape(-1, C) @ wp.float().t()) * psc + psh
+    if skip:
+        ref = ref + res.float().reshape(-1, N)
+    tol = 1e-2 if dt == torch.float16 else 6e-2          # the depthwise stage accumulates its 9 taps in 16 bit
+    assert rel_err(out.reshape(-1, N), ref) < tol
