@@ -352,6 +352,26 @@ int dlb_label_weights(int B, int64_t npix, int n_classes, int label_type, const 
                       unsigned long long* counts, float* y, float* sw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * SegmentationGenerator.__getitem__'s augmentations on the device (utils.py:319-365), bit-exact with OpenCV's uint8
+ * paths: GaussianBlur((k,k), 0) for k in {3,5,7} -> flips -> gamma LUT -> warpAffine (INTER_LINEAR for image AND label,
+ * constant border 0) -> "labels the decoded image did not contain become void" -> float32 image + label map (feed
+ * label_out to dlb_label_weights for Y / SW).  The random decisions stay with the caller (the reference draws them from
+ * Python's `random`); they arrive as one dlb_aug_params per image in DEVICE memory.
+ *   img [B,H,W,3] uint8 (cv2 BGR), label [B,H,W] uint8, luts [B,256] uint8 or NULL (identity),
+ *   tmp_img [B,H,W,3] / tmp_label [B,H,W] uint8 scratch, present [B,8] uint32 scratch,
+ *   X [B,H,W,3] float32 out, label_out [B,H,W] uint8 out (values 0..n_classes).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int hflip, vflip;          /* cv2.flip(.., 1) / cv2.flip(.., 0) */
+  int blur_ksize;            /* 0 = none, else 3 / 5 / 7 */
+  int warp;                  /* 0 = none */
+  double minv[6];            /* INVERSE of the 2x3 affine matrix passed to cv2.warpAffine (cv2.invertAffineTransform) */
+} dlb_aug_params;
+int dlb_augment_batch(int B, int H, int W, int n_classes, const uint8_t* img, const uint8_t* label,
+                      const dlb_aug_params* params_dev, const uint8_t* luts, uint8_t* tmp_img, uint8_t* tmp_label,
+                      unsigned int* present, float* X, uint8_t* label_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Dense CRF (utils.py:74-91 -> pydensecrf DenseCRF2D.inference): permutohedral lattice mean field.
  *   unary   : [M, N] fp32 energies (N = H*W pixels, label-major as pydensecrf)
  *   image   : [H, W, 3] uint8

@@ -98,6 +98,10 @@ class SepconvFusedParams(C.Structure):
     ]
 
 
+class AugParams(C.Structure):
+    _fields_ = [("hflip", i32), ("vflip", i32), ("blur_ksize", i32), ("warp", i32), ("minv", f64 * 6)]
+
+
 class CrfConfig(C.Structure):
     _fields_ = [
         ("H", i32), ("W", i32), ("M", i32), ("iters", i32), ("sxy_gauss", f32), ("compat_gauss", f32),
@@ -115,7 +119,7 @@ EXPORTS = [
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
     "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan", "dlb_label_weights",
-    "dlb_grad_finite_check", "dlb_crf_workspace_bytes_batched", "dlb_crf_inference_batched",
+    "dlb_grad_finite_check", "dlb_crf_workspace_bytes_batched", "dlb_crf_inference_batched", "dlb_augment_batch",
 ]
 
 _lib = None
@@ -163,6 +167,7 @@ def lib() -> C.CDLL:
         L.dlb_sepconv_fused_fwd.argtypes = [vp, vp]
         L.dlb_crf_workspace_bytes.argtypes = [vp]
         L.dlb_crf_inference.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
+        L.dlb_augment_batch.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.dlb_crf_workspace_bytes_batched.restype = i64
         L.dlb_crf_workspace_bytes_batched.argtypes = [vp, i32]
         L.dlb_crf_inference_batched.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp]

@@ -4,7 +4,8 @@
   sparse_crossentropy_ignoring_last_label, sparse_accuracy_ignoring_last_label, Jaccard   utils.py:127-157
   do_crf                                                                      utils.py:74-91
   get_VOC2012_classes                                                         utils.py:99-124
-Out of scope: SegmentationGenerator (cv2 / VOC data pipeline), plot_confusion_matrix.
+SegmentationGenerator's per-image augmentations + label / weight contract run on the device (augment_batch);
+its file handling (glob / cv2.imread / resize of VOC files) and plot_confusion_matrix stay out of scope.
 
 The loss / metric callables are accepted by `model.compile(...)` for API compatibility; the training step always
 uses the fused CUDA implementation of exactly these functions (dlb_resize_softmax_ce / dlb_confusion).  Calling
@@ -254,6 +255,94 @@ def generator_labels_and_weights(labels, n_classes):
     sw = torch.empty_like(y)
     ops.label_weights(t, int(n_classes), y, sw)
     return y.unsqueeze(-1), sw
+
+
+class AugmentParams:
+    """The random decisions SegmentationGenerator.__getitem__ takes for ONE image (reference utils.py:319-357)."""
+
+    def __init__(self, blur_ksize=0, hflip=False, vflip=False, gamma=None, angle=0.0, scale=1.0, warp=False):
+        self.blur_ksize, self.hflip, self.vflip = int(blur_ksize), bool(hflip), bool(vflip)
+        self.gamma, self.angle, self.scale, self.warp = gamma, float(angle), float(scale), bool(warp)
+
+
+def draw_augment_params(rng, blur=0, horizontal_flip=True, vertical_flip=0, brightness=0.1, rotation=5.0, zoom=0.1):
+    """Draws from `rng` (Python's `random` module or a random.Random) in exactly the order of the reference's
+    __getitem__ (utils.py:323-352), so the same seed gives the same augmentation stream."""
+    p = AugmentParams()
+    if blur and rng.randint(0, 1):
+        p.blur_ksize = int(blur)
+    if horizontal_flip and rng.randint(0, 1):
+        p.hflip = True
+    if vertical_flip and rng.randint(0, 1):
+        p.vflip = True
+    if brightness:
+        factor = 1.0 + rng.gauss(mu=0.0, sigma=brightness)
+        if rng.randint(0, 1):
+            factor = 1.0 / factor
+        p.gamma = factor
+    p.angle = rng.gauss(mu=0.0, sigma=rotation) if rotation else 0.0
+    p.scale = rng.gauss(mu=1.0, sigma=zoom) if zoom else 1.0
+    p.warp = bool(rotation or zoom)
+    return p
+
+
+def rotation_matrix_2d(center, angle, scale):
+    """cv2.getRotationMatrix2D restated (float64): [[a, b, (1-a)cx - b cy], [-b, a, b cx + (1-a)cy]]."""
+    a_ = np.float64(angle) * (np.pi / 180.0)          # (OpenCV folds CV_PI / 180 first)
+    alpha, beta = np.cos(a_) * scale, np.sin(a_) * scale
+    cx, cy = np.float64(center[0]), np.float64(center[1])
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy], [-beta, alpha, beta * cx + (1 - alpha) * cy]], np.float64)
+
+
+def invert_affine(M):
+    """cv2.invertAffineTransform restated (float64)."""
+    M = np.asarray(M, np.float64)
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22, A12, A21 = M[1, 1] * D, M[0, 0] * D, -M[0, 1] * D, -M[1, 0] * D
+    b1 = -A11 * M[0, 2] - A12 * M[1, 2]
+    b2 = -A21 * M[0, 2] - A22 * M[1, 2]
+    return np.array([[A11, A12, b1], [A21, A22, b2]], np.float64)
+
+
+def gamma_lut(factor):
+    """the brightness table of utils.py:344 (float64 power, truncated to uint8)."""
+    return np.array([((i / 255.0) ** factor) * 255 for i in np.arange(0, 256)]).astype(np.uint8)
+
+
+def augment_batch(images, labels, params, n_classes=21):
+    """SegmentationGenerator.__getitem__ from the decoded (already resized) arrays on, on the device:
+    images [B,H,W,3] uint8 BGR, labels [B,H,W] uint8, params: list of AugmentParams ->
+    (X [B,H,W,3] float32, Y [B,H*W,1] float32, {'pred_mask': SW [B,H*W] float32}) CUDA tensors -- what fit_generator
+    takes.  Bit-exact with the cv2 calls of the reference (tests/test_augment.py)."""
+    img = torch.as_tensor(images, dtype=torch.uint8).cuda().contiguous()
+    lab = torch.as_tensor(labels, dtype=torch.uint8).cuda().contiguous()
+    B, H, W = lab.shape
+    arr = (L.AugParams * B)()
+    luts = np.tile(np.arange(256, dtype=np.uint8), (B, 1))
+    any_lut = False
+    for b, p in enumerate(params):
+        arr[b].hflip, arr[b].vflip, arr[b].blur_ksize, arr[b].warp = int(p.hflip), int(p.vflip), int(p.blur_ksize), int(p.warp)
+        if p.blur_ksize not in (0, 3, 5, 7):
+            raise ValueError("blur kernel size must be 0, 3, 5 or 7")
+        if p.warp:
+            minv = invert_affine(rotation_matrix_2d((W // 2, H // 2), p.angle, p.scale))
+            for i in range(6):
+                arr[b].minv[i] = float(minv.flat[i])
+        if p.gamma is not None:
+            luts[b] = gamma_lut(p.gamma)
+            any_lut = True
+    prm = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+    lut_t = torch.from_numpy(luts).cuda() if any_lut else None
+    tmp_img, tmp_lab = torch.empty_like(img), torch.empty_like(lab)
+    present = torch.empty(B, 8, device="cuda", dtype=torch.int32)
+    X = torch.empty(B, H, W, 3, device="cuda", dtype=torch.float32)
+    lab_out = torch.empty_like(lab)
+    L.check(L.lib().dlb_augment_batch(B, H, W, int(n_classes), img.data_ptr(), lab.data_ptr(), prm.data_ptr(), L.ptr(lut_t),
+                                      tmp_img.data_ptr(), tmp_lab.data_ptr(), present.data_ptr(), X.data_ptr(),
+                                      lab_out.data_ptr(), L.stream_ptr()), "augment_batch")
+    Y, SW = generator_labels_and_weights(lab_out, n_classes)
+    return X, Y, {"pred_mask": SW}
 
 
 def calculate_iou(model, nb_classes=21, data=None, batch_size=16):
