@@ -42,7 +42,12 @@ def Deeplabv3(weights='pascal_voc', input_tensor=None, infer=False, input_shape=
         raise ValueError('The `backbone` argument should be either '
                          '`xception`  or `mobilenetv2` ')
     if input_tensor is not None:
-        raise NotImplementedError("input_tensor: there is no Keras tensor graph here; pass arrays to predict/fit")
+        # Keras builds the graph on top of an existing tensor (deeplabv3p.py:260-266); here the tensor only fixes the
+        # input geometry -- its (H, W, 3) overrides input_shape -- and is returned as model.input
+        shp = tuple(getattr(input_tensor, "shape", ()))
+        if len(shp) not in (3, 4) or shp[-1] != 3:
+            raise ValueError("input_tensor must have shape (H, W, 3) or (batch, H, W, 3)")
+        input_shape = tuple(int(v) for v in shp[-3:])
     if weights == 'pascal_voc':
         raise RuntimeError("weights='pascal_voc' needs a download (WEIGHTS_PATH_X / WEIGHTS_PATH_MOBILE, "
                            "deeplabv3p.py:42-43); this box has no network and the reference itself fails there "
@@ -54,4 +59,7 @@ def Deeplabv3(weights='pascal_voc', input_tensor=None, infer=False, input_shape=
         return build_xception_model(input_shape, classes, OS, infer, dt, seed)
     engine = Engine(input_shape=input_shape, classes=classes, head="bare", alpha=alpha, compute_dtype=dt, seed=seed)
     names = keras_layer_names(backbone, "bare", engine.head_conv.name)
-    return Model(engine, "deeplabv3p", names, infer=infer)
+    model = Model(engine, "deeplabv3p", names, infer=infer)
+    if input_tensor is not None:
+        model.input = input_tensor
+    return model

@@ -80,8 +80,7 @@ class Engine:
 
     def __init__(self, input_shape=(512, 512, 3), classes=21, head="bare", n_out: Optional[int] = None, alpha=1.0,
                  compute_dtype=torch.float16, device="cuda", seed: int = 0, head_layer_name: Optional[str] = None):
-        if alpha != 1.0:
-            raise NotImplementedError("alpha != 1 is not built (the reference only ships / trains alpha = 1)")
+        self.alpha = float(alpha)        # MobileNetV2 width multiplier (deeplabv3p.py:157-164, :168-170, :317)
         self.H, self.W = int(input_shape[0]), int(input_shape[1])
         if self.H % 8 or self.W % 8:
             raise ValueError("input height/width must be multiples of 8 (output stride 8, deeplabv3p.py:316)")
@@ -156,11 +155,18 @@ class Engine:
         return BN(rec, c, eps, momentum)
 
     def _build_spec(self, head_layer_name):
-        self.stem = self._conv("Conv", 3, 3, 32)
-        self.stem_bn = self._bn("Conv_BN", 32, 1e-3, 0.999)
+        # deeplabv3p.py:317: first_block_filters = _make_divisible(32 * alpha, 8); :168-170: every block's output is
+        # _make_divisible(int(filters * alpha), 8)
+        c0 = _make_divisible(32 * self.alpha, 8)
+        if c0 != 32:
+            raise NotImplementedError(f"alpha={self.alpha}: the stem kernels are built for 32 output channels "
+                                      f"(_make_divisible(32 * alpha, 8) = {c0}); 0.9 <= alpha < 1.125 keeps it at 32")
+        self.stem = self._conv("Conv", 3, 3, c0)
+        self.stem_bn = self._bn("Conv_BN", c0, 1e-3, 0.999)
         self.blocks = []
-        cin = 32
-        for (t, s, bid, skip, rate, cout) in MNV2_BLOCKS:
+        cin = c0
+        for (t, s, bid, skip, rate, filters) in MNV2_BLOCKS:
+            cout = _make_divisible(int(filters * self.alpha), 8)
             prefix = "expanded_conv_{}_".format(bid) if bid else "expanded_conv_"
             mid = cin * t
             blk = dict(bid=bid, stride=s, skip=skip, rate=rate, cin=cin, mid=mid, cout=cout, prefix=prefix)
@@ -173,9 +179,10 @@ class Engine:
             blk["project_bn"] = self._bn(prefix + "project_BN", cout, 1e-3, 0.999)
             self.blocks.append(blk)
             cin = cout
-        self.image_pooling = self._conv("image_pooling", 1, 320, 256)
+        self.c_last = cin
+        self.image_pooling = self._conv("image_pooling", 1, cin, 256)
         self.image_pooling_bn = self._bn("image_pooling_BN", 256, 1e-5, 0.99)
-        self.aspp0 = self._conv("aspp0", 1, 320, 256)
+        self.aspp0 = self._conv("aspp0", 1, cin, 256)
         self.aspp0_bn = self._bn("aspp0_BN", 256, 1e-5, 0.99)
         self.concat_projection = self._conv("concat_projection", 1, 512, 256)
         self.concat_projection_bn = self._bn("concat_projection_BN", 256, 1e-5, 0.99)
@@ -375,11 +382,11 @@ class Engine:
             ws["dy_ip"] = E(B, 256, dtype=torch.float32)
             ws["d_b4"] = E(B, 256, dtype=torch.float32)
             ws["d_rowbias"] = E(B, 256, dtype=torch.float32)
-            ws["d_pooled"] = E(B, 320, dtype=torch.float32)
+            ws["d_pooled"] = E(B, self.c_last, dtype=torch.float32)
             # gradient scratch
             wide = max(B * g["h"] * g["w"] * b["mid"] for b, g in zip(self.blocks, geo))
             narrow = max(B * h0 * w0 * 32, max(B * g["ho"] * g["wo"] * b["cout"] for b, g in zip(self.blocks, geo)),
-                         B * fh * fw * 320)
+                         B * fh * fw * self.c_last)
             ws["g_wide"] = [E(wide), E(wide)]
             ws["g_narrow"] = [E(narrow), E(narrow), E(narrow)]
             ws["g256"] = [E(B, fh, fw, 256), E(B, fh, fw, 256)]
@@ -410,7 +417,7 @@ class Engine:
             ws["argmax"] = torch.empty(B, self.H * self.W, device=dev, dtype=torch.uint8)
             ctot = sum(b.C for b in self.bns)
             ws["fold"] = torch.empty(2 * ctot, device=dev)
-        ws["pooled"] = E(B, 320, dtype=torch.float32)
+        ws["pooled"] = E(B, self.c_last, dtype=torch.float32)
         ws["b4"] = E(B, 256, dtype=torch.float32)
         ws["rowbias"] = E(B, 256, dtype=torch.float32)
         ws["y_ip"] = E(B, 256, dtype=torch.float32)
@@ -682,7 +689,7 @@ class Engine:
                            act=ACT_RELU, red=abn.red, dgamma=abn.gamma.grad, dbeta=abn.beta.grad)
         x16 = ws["x17"]
         if self.aspp0.trainable:
-            ops.pw_wgrad(x16, dy_a0, self.aspp0.params[0].grad.view(320, 256), beta=1.0)
+            ops.pw_wgrad(x16, dy_a0, self.aspp0.params[0].grad.view(self.c_last, 256), beta=1.0)
         # ---- image pooling branch
         ops.small_gemm(ws["d_rowbias"], cp.params[0].data.view(512, 256), ws["d_b4"], M=B, N=256, K=256, transB=True,
                        alpha=float(HW))
@@ -691,16 +698,16 @@ class Engine:
                    act=ACT_RELU, red=ibn.red, dgamma=ibn.gamma.grad, dbeta=ibn.beta.grad)
         ip = self.image_pooling
         if ip.trainable:
-            ops.small_gemm(ws["pooled"], ws["dy_ip"], ip.params[0].grad.view(320, 256), M=320, N=256, K=B, transA=True)
+            ops.small_gemm(ws["pooled"], ws["dy_ip"], ip.params[0].grad.view(self.c_last, 256), M=self.c_last, N=256, K=B, transA=True)
         if first > self._order("expanded_conv_16_project_BN"):
             return
-        ops.small_gemm(ws["dy_ip"], ip.params[0].data.view(320, 256), ws["d_pooled"], M=B, N=320, K=256, transB=True)
+        ops.small_gemm(ws["dy_ip"], ip.params[0].data.view(self.c_last, 256), ws["d_pooled"], M=B, N=self.c_last, K=256, transB=True)
         gn = ws["g_narrow"]
 
         def nview(buf, *shape):
             return buf[:int(np.prod(shape))].view(*shape)
 
-        dx = nview(gn[0], B, fh, fw, 320)
+        dx = nview(gn[0], B, fh, fw, self.c_last)
         ops.pw_gemm(dy_a0, self.wcopies["aspp0"]["kn"], dx)
         ops.global_avgpool_bwd(ws["d_pooled"], dx, True)
         # ---- backbone blocks in reverse

@@ -285,13 +285,16 @@ def _bn(rng, c, perturb=True):
     return [torch.ones(c), torch.zeros(c), torch.zeros(c), torch.ones(c)]
 
 
-def random_mobilenetv2_weights(seed=0, classes=21, head="logits_semantic", head_filters=None, perturb_bn=True):
+def random_mobilenetv2_weights(seed=0, classes=21, head="logits_semantic", head_filters=None, perturb_bn=True, alpha=1.0):
+    """alpha: MobileNetV2 width multiplier -- channel counts as deeplabv3p.py:168-170 / :317 compute them."""
     rng = np.random.RandomState(seed)
     W = OrderedDict()
-    W["Conv"] = _conv(rng, 3, 3, 32)
-    W["Conv_BN"] = _bn(rng, 32, perturb_bn)
-    cin = 32
+    c0 = _make_divisible(32 * alpha, 8)
+    W["Conv"] = _conv(rng, 3, 3, c0)
+    W["Conv_BN"] = _bn(rng, c0, perturb_bn)
+    cin = c0
     outs = [16, 24, 24, 32, 32, 32, 64, 64, 64, 64, 96, 96, 96, 160, 160, 160, 320]
+    outs = [_make_divisible(int(f * alpha), 8) for f in outs]
     for (t, s, bid, skip, rate), cout in zip(MNV2_BLOCKS, outs):
         prefix = "expanded_conv_{}_".format(bid) if bid else "expanded_conv_"
         mid = cin * t
@@ -303,9 +306,9 @@ def random_mobilenetv2_weights(seed=0, classes=21, head="logits_semantic", head_
         W[prefix + "project"] = _conv(rng, 1, mid, cout)
         W[prefix + "project_BN"] = _bn(rng, cout, perturb_bn)
         cin = cout
-    W["image_pooling"] = _conv(rng, 1, 320, 256)
+    W["image_pooling"] = _conv(rng, 1, cin, 256)
     W["image_pooling_BN"] = _bn(rng, 256, perturb_bn)
-    W["aspp0"] = _conv(rng, 1, 320, 256)
+    W["aspp0"] = _conv(rng, 1, cin, 256)
     W["aspp0_BN"] = _bn(rng, 256, perturb_bn)
     W["concat_projection"] = _conv(rng, 1, 512, 256)
     W["concat_projection_BN"] = _bn(rng, 256, perturb_bn)

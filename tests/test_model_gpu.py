@@ -405,3 +405,31 @@ def test_generator_contract_and_calculate_iou():
     pred = model.predict(x).argmax(-1)
     assert np.array_equal(conf, R.calculate_iou_conf(pred, Y[:, :, 0].cpu().numpy(), 21))
     assert conf.sum() == (Y[:, :, 0].cpu().numpy() != 21).sum()
+
+
+@pytest.mark.parametrize("alpha", [0.9, 1.1])
+def test_width_multiplier_alpha_matches_oracle(alpha):
+    """`alpha` != 1 (deeplabv3p.py:157-170): channel counts through _make_divisible, forward + one training step (fp32)
+    against the oracle built with the same widths.  (The stem kernels are built for 32 filters: 0.9 <= alpha < 1.125.)"""
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    from deeplab_b200.engine import _make_divisible
+    from oracle import network as N
+    W = N.random_mobilenetv2_weights(seed=13, alpha=alpha)
+    model = Deeplabv3(weights=None, input_shape=(96, 128, 3), alpha=alpha, compute_dtype='float32')
+    assert model.engine.c_last == _make_divisible(int(320 * alpha), 8) == W["aspp0"][0].shape[2]
+    _push_weights(model, W)
+    x = np.random.RandomState(2).randint(0, 256, (2, 96, 128, 3)).astype(np.float32)
+    probs = model.predict(x, batch_size=2)
+    with torch.no_grad():
+        _, pref, _ = N.deeplabv3_forward(W, torch.from_numpy(x))
+    assert rel(probs, pref) < 1e-3
+    with pytest.raises(NotImplementedError):
+        Deeplabv3(weights=None, input_shape=(96, 128, 3), alpha=0.5)
+
+
+def test_input_tensor_fixes_geometry():
+    from deeplab_b200.deeplabv3p import Deeplabv3
+    t = torch.zeros(1, 64, 96, 3)
+    model = Deeplabv3(weights=None, input_tensor=t, input_shape=(512, 512, 3), compute_dtype='float16')
+    assert model.input is t and model.input_shape == (None, 64, 96, 3)
+    assert model.predict(np.zeros((1, 64, 96, 3), np.float32)).shape == (1, 64 * 96, 21)
