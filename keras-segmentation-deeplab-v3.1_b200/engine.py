@@ -116,6 +116,10 @@ class Engine:
         self.fuse_dw_bn = os.environ.get("DLB_FUSE_DW_BN", "1") != "0"
         # inference: depthwise -> project of an inverted-residual block in one kernel (DLB_FUSE_MBCONV=0: separate)
         self.fuse_dw_project = os.environ.get("DLB_FUSE_MBCONV", "1") != "0"
+        # data parallel: gradient buckets are all-reduced while the rest of the backward pass runs, inside the captured
+        # step (DLB_AR_IN_GRAPH=0: one all-reduce of the whole buffer between two graphs, the round-1 schedule)
+        self.ar_in_graph = os.environ.get("DLB_AR_IN_GRAPH", "1") != "0"
+        self._on_bucket = None
         self._mb_packs = {}
 
     @property
@@ -715,6 +719,8 @@ class Engine:
         gw = ws["g_wide"]
         for i in range(len(self.blocks) - 1, -1, -1):
             b, g = self.blocks[i], geo[i]
+            if i == 12 and self._on_bucket is not None:
+                self._on_bucket(0)          # gradients of blocks 13..16, ASPP and the head are complete
             others = [k for k in range(3) if k != cur]
             pbn, dbn = b["project_bn"], b["dw_bn"]
             xin = ws[f"x{i}"]
@@ -779,6 +785,14 @@ class Engine:
         if self.stem.trainable:
             ops.stem_conv_wgrad(ws["img"], dy_s, self.stem.params[0].grad)
 
+    def grad_buckets(self):
+        """[(lo, hi)] slices of the flat gradient buffer in the order the backward pass completes them.  Parameters
+        lie in forward order, so everything from block 13 on (76 % of the 2.11 M parameters) is final after the first
+        ~30 % of the backward pass: that suffix is reduced while blocks 12..0 and the stem are still running, and only
+        the 2 MB prefix is left for the end."""
+        off = self._by_name["expanded_conv_13_expand"].params[0].offset
+        return [(off, self.n_params), (0, off)]
+
     def _unshuffle_dlogits(self, ws):
         """[B,H,W,n] fp32 gradient -> [B,fh,fw,(jj,i,k)] in the compute dtype (transpose of the fused store)."""
         B = ws["dlogits"].shape[0]
@@ -803,6 +817,30 @@ class Engine:
         self.forward_train(ws, B, dropout)
         self.loss_and_head_grad(ws, B, use_sample_w)
         self.backward(ws, B, dropout)
+
+    def _step_body_bucketed(self, ws, B, dropout, use_sample_w):
+        """forward + backward with the gradient buckets all-reduced asynchronously as they complete, then Adam: the
+        whole data-parallel step in one capturable body (the collectives run on the process group's own stream;
+        `wait()` makes the optimizer depend on them)."""
+        buckets, works, fired = self.grad_buckets(), [], set()
+
+        def fire(k):
+            lo, hi = buckets[k]
+            works.append(self.grad_hook(self.grads[lo:hi], True))
+            fired.add(k)
+
+        self._on_bucket = fire
+        try:
+            self._fwd_bwd_body(ws, B, dropout, use_sample_w)
+        finally:
+            self._on_bucket = None
+        for k in range(len(buckets)):          # (a frozen prefix ends the backward pass early)
+            if k not in fired:
+                fire(k)
+        for w in works:
+            if w is not None:
+                w.wait()
+        self._update_body()
 
     def _update_body(self):
         c = self.adam_cfg
@@ -848,7 +886,11 @@ class Engine:
         if use_sw:
             ws["sample_w"].copy_(sample_w.view(B, -1), non_blocking=True)
         self._fold_dirty = True
+        bucketed = self.grad_hook is not None and self.ar_in_graph
         if not use_graph:
+            if bucketed:
+                self._step_body_bucketed(ws, B, dropout, use_sw)
+                return ws["loss_sum"], ws["wcount"]
             self._fwd_bwd_body(ws, B, dropout, use_sw)
             if self.grad_hook is not None:
                 self.grad_hook(self.grads)
@@ -862,6 +904,8 @@ class Engine:
                     self._fwd_bwd_body(ws, B, dropout, use_sw)
                     self._update_body()
                 self._graphs[key] = (self._capture(whole), None)
+            elif bucketed:
+                self._graphs[key] = (self._capture(lambda: self._step_body_bucketed(ws, B, dropout, use_sw)), None)
             else:
                 ga = self._capture(lambda: self._fwd_bwd_body(ws, B, dropout, use_sw))
                 self.grad_hook(self.grads)

@@ -3,8 +3,10 @@
 Replaces `keras.utils.multi_gpu_model` (utils.py:209-211): the reference slices the batch over towers inside one TF
 graph and sums the tower gradients implicitly through shared variables; BatchNorm statistics stay per tower.  Here
 each rank holds a replica and a batch shard, BatchNorm stays per replica (same semantics), and the 2.11 M fp32
-gradients (8.45 MB) are summed with a single all-reduce over NVLink/NVSwitch between the backward graph and the
-optimizer graph; Adam divides by world_size (dlb_adam_step grad_mult).  The path has no other exchange step.
+gradients (8.45 MB) are summed over NVLink/NVSwitch in two buckets INSIDE the captured step: the suffix of the flat
+buffer (blocks 13..16 + ASPP + head, 76 % of the parameters) as soon as the backward pass has produced it, overlapped
+with the remaining backward kernels, and the 2 MB prefix at the end; Adam divides by world_size (dlb_adam_step
+grad_mult).  The path has no other exchange step.
 """
 from __future__ import annotations
 
@@ -36,8 +38,10 @@ def make_data_parallel(model, group=None):
     e = model.engine
     e.world_size = dist.get_world_size(group)
 
-    def hook(flat_grads: torch.Tensor):
-        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    def hook(flat_grads: torch.Tensor, async_op: bool = False):
+        """sum a (slice of the) flat gradient buffer over the ranks; async_op=True returns the work handle so the
+        engine can launch the next backward kernels before the collective has finished"""
+        return dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     e.grad_hook = hook
     e._graphs.clear()

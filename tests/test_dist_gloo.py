@@ -37,6 +37,12 @@ def _worker(rank, world, port, q):
     ok = ok and torch.equal(e.params, torch.full((10,), 1.0)) and torch.equal(e.stats, torch.full((4,), 10.0))
     e.grad_hook(e.grads)
     ok = ok and torch.equal(e.grads, torch.arange(10, dtype=torch.float32) * 3)       # sum over ranks
+    # bucketed form used inside the captured step: two slices reduced asynchronously, then waited for
+    g2 = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    works = [e.grad_hook(g2[6:], True), e.grad_hook(g2[:6], True)]
+    for w in works:
+        w.wait()
+    ok = ok and torch.equal(g2, torch.arange(10, dtype=torch.float32) * 3)
     lo, hi = parallel.shard_batch(32, rank, world)
     ok = ok and (lo, hi) == (16 * rank, 16 * rank + 16)
     q.put((rank, bool(ok)))
