@@ -45,8 +45,13 @@ def main():
         ssum = torch.zeros(N, device="cuda", dtype=torch.float64) if stats else None
         ssqs = torch.zeros(N, device="cuda", dtype=torch.float64) if stats else None
 
+        xf = "--xform" in sys.argv
+        asc = torch.rand(K, device="cuda", generator=g) + 0.5 if xf else None
+        ash = torch.randn(K, device="cuda", generator=g) if xf else None
+
         def fn():
-            ops.pw_gemm(A, Bt, out, residual=R, stat_sum=ssum, stat_sqs=ssqs)
+            ops.pw_gemm(A, Bt, out, residual=R, stat_sum=ssum, stat_sqs=ssqs, a_scale=asc, a_shift=ash,
+                        a_act=ops.ACT_RELU6 if xf else ops.ACT_NONE)
 
         fn()
         torch.cuda.synchronize()

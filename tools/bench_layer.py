@@ -57,7 +57,9 @@ def main():
                                                 in_shift=shift, in_act=ACT_RELU6, stat_sum=ssum, stat_sqs=ssqs), 2 * n * es),
         "dw_conv_bwd": (lambda: ops.dw_conv_bwd(x, da, wdw, dx=dx, dw=ddw, stride=1, dilation=4, pad_top=4, pad_left=4,
                                                 in_scale=scale, in_shift=shift, in_act=ACT_RELU6), 4 * n * es),
-        "pw_wgrad": (lambda: ops.pw_wgrad(x.view(-1, C), dyn.view(-1, Cn), dW), (n + dyn.numel()) * es + dW.numel() * 4),
+        # the project conv's weight gradient as the training step runs it: A-operand transform (depthwise_BN + relu6) on
+        "pw_wgrad": (lambda: ops.pw_wgrad(x.view(-1, C), dyn.view(-1, Cn), dW, a_scale=scale, a_shift=shift, a_act=ACT_RELU6),
+                     (n + dyn.numel()) * es + dW.numel() * 4),
     }
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, (fn, byt) in cases.items():
