@@ -304,6 +304,10 @@ int dlb_resize_softmax_ce(const dlb_softmax_ce_params* p, void* stream);
 int dlb_ce_grad_scale(int64_t n, const float* sample_w, float* grad_scale_dev, double* wcount, float loss_scale,
                       const float* loss_scale_state, void* stream);
 
+/* Backward of the phase-shift store fused into dlb_pw_gemm (whose columns are ordered (jj, i, k)):
+ *   dst[n, a, b, (jj*r + i)*Cs + k] = dlogits[n, a*r + jj, b*r + i, k], fp32 -> dst_dtype.  dlogits [B, h*r, w*r, Cs]. */
+int dlb_subpixel_grad_gather(int B, int h, int w, int Cs, int r, const float* dlogits, int dst_dtype, void* dst,
+                             void* stream);
 /* Standalone Subpixel phase shift (subpixel.py:77-88): out[n, a*r+j, b*r+i, k] = in[n, a, b, k*r*r + i*r + j] */
 int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, const void* in, void* out, int inverse,
                     void* stream);

@@ -119,7 +119,7 @@ EXPORTS = [
     "dlb_cast_weight", "dlb_cast_weights_batched", "dlb_cast", "dlb_fill_zero", "dlb_confusion", "dlb_crf_workspace_bytes",
     "dlb_crf_inference", "dlb_conv3x3_fwd", "dlb_subsample", "dlb_resize_bilinear", "dlb_aspp_dw3_fwd",
     "dlb_sepconv_fused_fwd", "dlb_sepconv_pack_bytes", "dlb_sepconv_pack_dw", "dlb_pw_gemm_plan", "dlb_label_weights",
-    "dlb_grad_finite_check", "dlb_crf_workspace_bytes_batched", "dlb_crf_inference_batched", "dlb_augment_batch",
+    "dlb_grad_finite_check", "dlb_crf_workspace_bytes_batched", "dlb_crf_inference_batched", "dlb_augment_batch", "dlb_subpixel_grad_gather",
 ]
 
 _lib = None
@@ -167,6 +167,7 @@ def lib() -> C.CDLL:
         L.dlb_sepconv_fused_fwd.argtypes = [vp, vp]
         L.dlb_crf_workspace_bytes.argtypes = [vp]
         L.dlb_crf_inference.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
+        L.dlb_subpixel_grad_gather.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp, vp]
         L.dlb_augment_batch.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.dlb_crf_workspace_bytes_batched.restype = i64
         L.dlb_crf_workspace_bytes_batched.argtypes = [vp, i32]

@@ -478,6 +478,7 @@ struct StreamArgs {
   const float* scale; const float* shift; const float* mean; const float* rstd;
   int act, frozen;
   double* red; float* dgamma; float* dbeta;
+  float drop_rate; uint64_t seed; const long long* seed_dev;      // Dropout after the activation (deeplabv3p.py:410)
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -486,7 +487,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
                : "memory");
 }
 
-template <typename T, int kMode>
+// kDrop: the Dropout instance (one layer of the graph) -- a template parameter so that the hash and its registers
+// stay out of the other ~120 launches per step (as a run-time flag it cost them 4 % each)
+template <typename T, int kMode, bool kDrop>
 __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArgs a) {
   extern __shared__ __align__(128) uint8_t s_raw[];
   using P = typename BP2<T>::t;
@@ -554,6 +557,11 @@ __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArg
     }
   }
   const P zero2 = BP2<T>::bcast(0.f), six2 = BP2<T>::bcast(6.f);
+  // inverted dropout: the keep mask is a counter-based hash of (seed, device iteration counter, element index), so the
+  // forward pass, both backward passes and a replayed CUDA graph regenerate the same mask without storing it
+  constexpr bool drop = kDrop;
+  const float keep_inv = drop ? 1.f / (1.f - a.drop_rate) : 1.f;
+  const uint64_t dseed = a.seed + (a.seed_dev ? static_cast<uint64_t>(*a.seed_dev) * 0x632BE59BD9B4E019ull : 0ull);
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   T* out = reinterpret_cast<T*>(a.out);
   const uint32_t t_off = static_cast<uint32_t>((r_in * a.C + c0) * sizeof(T));      // this thread inside one pass
@@ -591,6 +599,11 @@ __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArg
               const float2 f = BP2<T>::unpack(xv[u].h[k]);
               o[2 * k] = apply_act(fmaf(f.x, sc[2 * k], sh[2 * k]), a.act);
               o[2 * k + 1] = apply_act(fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]), a.act);
+              if (drop) {
+                const uint64_t e = static_cast<uint64_t>(r * a.C + c0 + 2 * k);
+                o[2 * k] = hash_uniform(dseed, e) >= a.drop_rate ? o[2 * k] * keep_inv : 0.f;
+                o[2 * k + 1] = hash_uniform(dseed, e + 1) >= a.drop_rate ? o[2 * k + 1] * keep_inv : 0.f;
+              }
               if (a.n_in > 1) {
                 const float2 g = BP2<T>::unpack(gv[u].h[k]);
                 o[2 * k] += g.x; o[2 * k + 1] += g.y;
@@ -607,6 +620,12 @@ __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArg
                 P m = __hgt2(z, zero2);
                 if (a.act == DLB_ACT_RELU6) m = __hmul2(m, __hlt2(z, six2));
                 dz = __hmul2(dz, m);
+              }
+              if (drop) {
+                const uint64_t e = static_cast<uint64_t>(r * a.C + c0 + 2 * k);
+                const float2 d = BP2<T>::unpack(dz);
+                dz = BP2<T>::pack(hash_uniform(dseed, e) >= a.drop_rate ? d.x * keep_inv : 0.f,
+                                  hash_uniform(dseed, e + 1) >= a.drop_rate ? d.y * keep_inv : 0.f);
               }
               const P xh2 = __hmul2(__hsub2(xv[u].h[k], mu2[k]), rs2[k]);
               if (kMode == 1) {
@@ -670,11 +689,21 @@ static int launch_bn_stream(StreamArgs a, int dtype, cudaStream_t st) {
   const long long n_blk = (a.M + a.rows_per_stage - 1) / a.rows_per_stage;
   const int grid = static_cast<int>(n_blk < num_sms() ? n_blk : num_sms());
   if (dtype == DLB_F16) {
-    DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__half, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_k(bn_stream_kernel<__half, kMode>, grid, kSThreads, smem, st, a);
+    if (a.drop_rate > 0.f) {
+      DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__half, kMode, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_k(bn_stream_kernel<__half, kMode, true>, grid, kSThreads, smem, st, a);
+    } else {
+      DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__half, kMode, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_k(bn_stream_kernel<__half, kMode, false>, grid, kSThreads, smem, st, a);
+    }
   } else {
-    DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__nv_bfloat16, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_k(bn_stream_kernel<__nv_bfloat16, kMode>, grid, kSThreads, smem, st, a);
+    if (a.drop_rate > 0.f) {
+      DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__nv_bfloat16, kMode, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_k(bn_stream_kernel<__nv_bfloat16, kMode, true>, grid, kSThreads, smem, st, a);
+    } else {
+      DLB_CUDA(cudaFuncSetAttribute(bn_stream_kernel<__nv_bfloat16, kMode, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_k(bn_stream_kernel<__nv_bfloat16, kMode, false>, grid, kSThreads, smem, st, a);
+    }
   }
   g_launches++;
   return check_launch("bn_stream_kernel");
@@ -719,10 +748,11 @@ extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed,
               reinterpret_cast<const long long*>(p->drop_seed_dev)};
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
-  if (p->drop_rate <= 0.f && g_bn_stream) {
+  if (g_bn_stream) {
     StreamArgs sa{};
     sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->res; sa.out = p->y; sa.n_in = p->res ? 2 : 1;
     sa.scale = p->scale; sa.shift = p->shift; sa.act = p->act;
+    sa.drop_rate = p->drop_rate; sa.seed = p->drop_seed; sa.seed_dev = reinterpret_cast<const long long*>(p->drop_seed_dev);
     const int rc = launch_bn_stream<0>(sa, p->dtype, st0);
     if (rc <= 0) return rc;
   }
@@ -753,10 +783,11 @@ extern "C" int dlb_bn_bwd_reduce(const dlb_bn_bwd_params* p, void* stream) {
   BwdArgs a{};
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
-  if (p->drop_rate <= 0.f && g_bn_stream) {
+  if (g_bn_stream) {
     StreamArgs sa{};
     sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->da; sa.out = nullptr; sa.n_in = 2;
     sa.scale = p->scale; sa.shift = p->shift; sa.mean = p->mean; sa.rstd = p->rstd; sa.act = p->act; sa.red = p->red;
+    sa.drop_rate = p->drop_rate; sa.seed = p->drop_seed; sa.seed_dev = reinterpret_cast<const long long*>(p->drop_seed_dev);
     rc = launch_bn_stream<1>(sa, p->dtype, static_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;
   }
@@ -781,11 +812,12 @@ extern "C" int dlb_bn_bwd_apply(const dlb_bn_bwd_params* p, void* stream) {
   int rc = fill_bwd(p, &a);
   if (rc) return rc;
   DLB_REQUIRE(p->dx, "bn_bwd_apply: dx is null");
-  if (p->drop_rate <= 0.f && g_bn_stream) {
+  if (g_bn_stream) {
     StreamArgs sa{};
     sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->da; sa.out = p->dx; sa.n_in = 2;
     sa.scale = p->scale; sa.shift = p->shift; sa.mean = p->mean; sa.rstd = p->rstd; sa.act = p->act; sa.red = p->red;
     sa.frozen = p->frozen_stats; sa.dgamma = p->dgamma; sa.dbeta = p->dbeta;
+    sa.drop_rate = p->drop_rate; sa.seed = p->drop_seed; sa.seed_dev = reinterpret_cast<const long long*>(p->drop_seed_dev);
     rc = launch_bn_stream<2>(sa, p->dtype, static_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;
   }

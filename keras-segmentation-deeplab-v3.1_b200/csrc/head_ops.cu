@@ -302,6 +302,27 @@ __global__ void phase_shift_kernel(long long total, int h, int w, int Cs, int r,
   }
 }
 
+// backward of the FUSED Subpixel store of dlb_pw_gemm: the GEMM's columns are ordered (jj, i, k), so
+//   dst[n, a, b, (jj*r + i)*Cs + k] = src[n, a*r + jj, b*r + i, k]      (fp32 gradient -> storage dtype)
+// reads and writes are both contiguous runs of r*Cs elements.
+template <typename T>
+__global__ void __launch_bounds__(256) subpixel_grad_gather_kernel(long long total, int h, int w, int Cs, int r,
+                                                                   const float* __restrict__ src, T* __restrict__ dst) {
+  pdl_prologue();
+  const int run = r * Cs;
+  for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < total;
+       o += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(o % run);          // (i, k)
+    long long t = o / run;
+    const int jj = static_cast<int>(t % r); t /= r;
+    const int b = static_cast<int>(t % w); t /= w;
+    const int a = static_cast<int>(t % h);
+    const long long n = t / h;
+    const long long s = ((n * h * r + static_cast<long long>(a) * r + jj) * (static_cast<long long>(w) * r) + static_cast<long long>(b) * r) * Cs + e;
+    Act<T>::st(&dst[o], src[s]);
+  }
+}
+
 __global__ void __launch_bounds__(256) confusion_kernel(long long npix, int C, const float* labels,
                                                         const uint8_t* argmax, unsigned long long* conf) {
   pdl_prologue();
@@ -506,6 +527,21 @@ extern "C" int dlb_phase_shift(int B, int h, int w, int Cs, int r, int dtype, co
   else launch_k(phase_shift_kernel<uint16_t>, grid, 256, 0, st, total, h, w, Cs, r, (const uint16_t*)in, (uint16_t*)out, inverse);
   g_launches++;
   return check_launch("phase_shift_kernel");
+}
+
+extern "C" int dlb_subpixel_grad_gather(int B, int h, int w, int Cs, int r, const float* dlogits, int dst_dtype, void* dst,
+                                        void* stream) {
+  DLB_REQUIRE(dlogits && dst && B > 0 && h > 0 && w > 0 && Cs > 0 && r >= 1, "subpixel_grad_gather: bad arguments");
+  const long long total = static_cast<long long>(B) * h * w * r * r * Cs;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst_dtype == DLB_F16) launch_k(subpixel_grad_gather_kernel<__half>, grid, 256, 0, st, total, h, w, Cs, r, dlogits, (__half*)dst);
+  else if (dst_dtype == DLB_BF16) launch_k(subpixel_grad_gather_kernel<__nv_bfloat16>, grid, 256, 0, st, total, h, w, Cs, r, dlogits, (__nv_bfloat16*)dst);
+  else launch_k(subpixel_grad_gather_kernel<float>, grid, 256, 0, st, total, h, w, Cs, r, dlogits, (float*)dst);
+  g_launches++;
+  return check_launch("subpixel_grad_gather_kernel");
 }
 
 extern "C" int dlb_confusion(int B, int64_t npix, int C, const float* labels, const uint8_t* argmax,

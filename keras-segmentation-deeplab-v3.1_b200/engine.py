@@ -795,10 +795,7 @@ class Engine:
 
     def _unshuffle_dlogits(self, ws):
         """[B,H,W,n] fp32 gradient -> [B,fh,fw,(jj,i,k)] in the compute dtype (transpose of the fused store)."""
-        B = ws["dlogits"].shape[0]
-        r, n = self.scale, self.n_out
-        d = ws["dlogits"].view(B, self.fh, r, self.fw, r * n)       # [b, a, jj, bb, (i,k)]
-        ws["dlogits_lo"].view(B, self.fh, self.fw, r, r * n).copy_(d.permute(0, 1, 3, 2, 4))
+        ops.subpixel_grad_gather(ws["dlogits"], ws["dlogits_lo"], self.fh, self.fw, self.scale)
 
     def _order(self, layer_name: str) -> int:
         return self._order_map[layer_name]

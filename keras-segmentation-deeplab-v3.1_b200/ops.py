@@ -263,6 +263,14 @@ def phase_shift(x: torch.Tensor, out: torch.Tensor, r: int, inverse: bool = Fals
     return out
 
 
+def subpixel_grad_gather(dlogits: torch.Tensor, dst: torch.Tensor, h: int, w: int, r: int):
+    """[B, h*r, w*r, Cs] fp32 gradient -> [B, h, w, (jj, i, k)] in dst's dtype (inverse of the fused Subpixel store)."""
+    B, Cs = dlogits.shape[0], dlogits.shape[-1]
+    L.check(L.lib().dlb_subpixel_grad_gather(B, h, w, Cs, r, dlogits.data_ptr(), L.dt(dst), dst.data_ptr(), L.stream_ptr()),
+            "subpixel_grad_gather")
+    return dst
+
+
 def adam_step(param, grad, m, v, step_dev, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, decay=0.0, grad_mult=1.0,
               train_mask=None, loss_scale_state=None):
     L.check(L.lib().dlb_adam_step(param.numel(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),

@@ -516,3 +516,41 @@ def test_fused_depthwise_project_matches_unfused(dt, HW, C, N, rate, skip):
         ref = ref + res.float().reshape(-1, N)
     tol = 1e-2 if dt == torch.float16 else 6e-2          # the depthwise stage accumulates its 9 taps in 16 bit
     assert rel_err(out.reshape(-1, N), ref) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_dropout_in_streaming_bn_kernels_matches_fp32_mask(dt):
+    """Dropout(0.1) behind concat_projection_BN (deeplabv3p.py:410) runs in the bulk-copy streaming BatchNorm kernels for
+    16-bit storage (round 1 fell back to the register-staged kernels there: 134 us instead of 33).  The keep mask is a
+    hash of (seed, element), so the 16-bit streaming kernels and the fp32 kernels must drop exactly the same elements,
+    forward and backward, and scale the kept ones by 1 / (1 - p)."""
+    ops = _ops()
+    M, C = 16 * 64 * 64 // 4, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x32 = torch.randn(M, C, device="cuda", generator=g)
+    x = x32.to(dt)
+    sc = torch.rand(C, device="cuda", generator=g) + 0.5
+    sh = torch.randn(C, device="cuda", generator=g) * 0.2
+    seed_dev = torch.tensor([5], device="cuda", dtype=torch.int64)
+    y32, y = torch.empty_like(x32), torch.empty_like(x)
+    ops.bn_act_apply(x.float(), y32, scale=sc, shift=sh, act=1, drop_rate=0.1, drop_seed=99, drop_seed_dev=seed_dev)
+    ops.bn_act_apply(x, y, scale=sc, shift=sh, act=1, drop_rate=0.1, drop_seed=99, drop_seed_dev=seed_dev)
+    assert rel_err(y, y32) < (2e-3 if dt == torch.float16 else 1.5e-2)
+    pos = y32 > 1e-2
+    assert torch.equal((y != 0)[pos], torch.ones_like(pos)[pos])                  # kept elements are kept
+    z = (x.float() * sc + sh)
+    dropped32 = (y32 == 0) & (z > 1e-2)
+    assert torch.equal((y == 0)[dropped32], torch.ones_like(pos)[dropped32])      # dropped elements are dropped
+    assert abs(dropped32.float().sum().item() / (z > 1e-2).float().sum().item() - 0.1) < 0.01
+    # backward: same mask, gradient scaled by 1 / (1 - p); statistics frozen so dx = scale * mask * da
+    da32 = torch.randn(M, C, device="cuda", generator=g)
+    da = da32.to(dt)
+    mean, rstd = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    dx32, dx = torch.empty_like(x32), torch.empty_like(x)
+    for (xx, dd, oo) in ((x.float(), da.float(), dx32), (x, da, dx)):
+        red = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+        ops.bn_bwd(xx, dd, oo, scale=sc, shift=sh, mean=mean, rstd=rstd, act=1, red=red, drop_rate=0.1, drop_seed=99,
+                   drop_seed_dev=seed_dev, frozen=True)
+    clear = z.abs() > 1e-2                                                        # away from the ReLU kink
+    assert rel_err(dx[clear], dx32[clear]) < (3e-3 if dt == torch.float16 else 2e-2)
+    assert torch.equal((dx != 0)[clear & (da != 0)], (dx32 != 0)[clear & (da != 0)])
