@@ -472,3 +472,48 @@ def test_bucketed_allreduce_schedule_single_gpu():
     # (same data, same start: the first loss is identical; later ones differ by the float-atomic summation order that
     # Adam's sign-like first steps amplify, see test_graph_replay_equals_eager_and_mious_match)
     assert abs(losses[0][0] - losses[1][0]) <= 1e-5 * abs(losses[0][0]) and np.allclose(losses[0], losses[1], rtol=6e-2), losses
+
+
+def test_test_on_batch_and_validation_match_oracle(tmp_path):
+    """Keras `test_on_batch` / `evaluate_generator` / `fit_generator(validation_data=...)`: inference-phase forward
+    (moving statistics, no dropout) + the fused loss / argmax / confusion kernels vs the oracle's loss
+    (utils.py:127-130 with temporal weights), Jaccard (:139-157) and accuracy (:132-138)."""
+    from deeplab_b200.model import Adam, ModelCheckpoint
+    from deeplab_b200.utils import SegModel
+    from oracle import network as N
+    from oracle import ref_ops as R
+    B, H, Wd = 3, 64, 96
+    x, y, sw = _synthetic_batch(B, H, Wd, seed=17)
+    W = N.random_mobilenetv2_weights(seed=9, head="conv_upsample")
+    model = SegModel(image_size=(H, Wd), compute_dtype='float32').create_seg_model("original", n=21)
+    _push_weights(model, W)
+    model.compile(optimizer=Adam(lr=7e-4, epsilon=1e-8, decay=1e-6), sample_weight_mode="temporal")
+    with torch.no_grad():
+        _, pref, _ = N.deeplabv3_forward(W, torch.from_numpy(x))
+    ty, tsw = torch.from_numpy(y), torch.from_numpy(sw)
+    loss_ref = R.keras_weighted_loss(ty, pref, tsw).item()
+    jac_ref, acc_ref = R.jaccard(ty, pref).item(), R.sparse_accuracy_ignoring_last_label(ty, pref).item()
+    got = model.test_on_batch(x, y, {"pred_mask": sw})
+    assert abs(got[0] - loss_ref) <= 1e-4 * abs(loss_ref), (got, loss_ref)
+    assert abs(got[1] - jac_ref) <= 1e-6 and abs(got[2] - acc_ref) <= 1e-6, (got, jac_ref, acc_ref)
+    # no sample weights: plain mean over all pixels (void pixels contribute 0)
+    got2 = model.test_on_batch(x, y)
+    assert abs(got2[0] - R.keras_weighted_loss(ty, pref).item()) <= 1e-4 * abs(got2[0])
+
+    class Seq:
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            return x, y, {"pred_mask": sw}
+
+    ev = model.evaluate_generator(Seq())
+    assert abs(ev[0] - loss_ref) <= 1e-4 * abs(loss_ref)
+    ck = str(tmp_path / "best.h5")
+    hist = model.fit_generator(Seq(), steps_per_epoch=2, epochs=2, verbose=0, validation_data=Seq(), validation_steps=1,
+                               callbacks=[ModelCheckpoint(ck, monitor="val_Jaccard", save_best_only=True, save_weights_only=True)])
+    assert set(hist.history) >= {"loss", "Jaccard", "val_loss", "val_Jaccard"} and len(hist.history["val_loss"]) == 2
+    assert all(np.isfinite(v) for v in hist.history["val_loss"]) and os.path.exists(ck)
+    m2 = SegModel(image_size=(H, Wd), compute_dtype='float32').create_seg_model("original", n=21)
+    m2.load_weights(ck)                                    # the checkpoint written by the callback loads back
+    assert np.array_equal(m2.get_layer("aspp0").get_weights()[0].shape, (1, 1, 320, 256))
