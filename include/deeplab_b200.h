@@ -41,6 +41,23 @@ int64_t dlb_launch_count(void);
 int dlb_device_ok(void);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm finalisation done by the CONSUMER of the statistics instead of a kernel of its own
+ * (dlb_bn_finalize below was 54 single-wave launches per training step in round 1).  A kernel that is handed a
+ * dlb_bn_fin computes scale / shift for the channels it needs from the fp64 sums in its prologue -- the arithmetic of
+ * dlb_bn_finalize -- and one of its CTAs also writes scale / shift / mean / rstd (the backward pass reads them) and
+ * updates the moving statistics.  sum / sqs are NOT cleared (every CTA reads them): zero the accumulators once per
+ * step before the forward pass.  moving_* / mean / rstd may be NULL.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const double* sum; const double* sqs;     /* [C] fp64 sums of x and x*x over `count` elements */
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  double count;
+  float* moving_mean; float* moving_var;
+  float* scale; float* shift; float* mean; float* rstd;
+} dlb_bn_fin;
+
+/* ---------------------------------------------------------------------------------------------------
  * Pointwise (1x1) convolution = GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA).
  * Replaces every Conv2D(.., (1,1)) of the graph: deeplabv3p.py:78-82, :175-177, :194-196, :385, :406,
  * :420, :438; utils.py:189; subpixel.py:90-91 (the conv half of Subpixel).
@@ -86,6 +103,9 @@ typedef struct {
    * the caller may pass them pre-split: Bt = hi parts, Bt_lo = remainders (same shape / pitch), which removes two
    * thirds of the in-kernel split work.  NULL = split in the kernel. */
   const void* Bt_lo;
+  /* A-operand transform whose scale / shift the kernel derives from the producing layer's batch statistics (instead
+   * of a_scale / a_shift; a_act still applies).  16-bit tensor-core path only, else DLB_ERR_INVALID. */
+  const dlb_bn_fin* a_fin;
 } dlb_pw_gemm_params;
 int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream);
 /* Tiling plan dlb_pw_gemm would use for a 16-bit GEMM of this shape (host arithmetic only, no device needed):
@@ -138,6 +158,7 @@ typedef struct {
   /* optional inference epilogue y = act(y*out_scale + out_shift) (folded BN) */
   const float* out_scale; const float* out_shift; int out_act;
   double* stat_sum; double* stat_sqs;
+  const dlb_bn_fin* in_fin;       /* optional: in_scale / in_shift from the batch statistics (dlb_bn_fin above) */
 } dlb_dw_conv_params;
 int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream);
 
@@ -243,6 +264,7 @@ typedef struct {
   const float* scale; const float* shift; int act;
   float drop_rate; uint64_t drop_seed;      /* Dropout(0.1), deeplabv3p.py:410; 0 = off */
   const int64_t* drop_seed_dev;             /* optional device counter added to drop_seed (graph replay) */
+  const dlb_bn_fin* fin;                    /* optional: scale / shift from the batch statistics (dlb_bn_fin above) */
 } dlb_bn_apply_params;
 int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream);
 /* Backward through  a = dropout(act(z)), z = x*scale + shift  where scale/shift come from batch statistics.

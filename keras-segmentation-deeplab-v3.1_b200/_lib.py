@@ -21,6 +21,14 @@ TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
 vp, i32, i64, f32, f64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 
 
+class BnFin(C.Structure):
+    """dlb_bn_fin: consumer-side BatchNorm finalisation (include/deeplab_b200.h)."""
+    _fields_ = [
+        ("sum", vp), ("sqs", vp), ("gamma", vp), ("beta", vp), ("eps", f32), ("momentum", f32), ("count", C.c_double),
+        ("moving_mean", vp), ("moving_var", vp), ("scale", vp), ("shift", vp), ("mean", vp), ("rstd", vp),
+    ]
+
+
 class PwGemmParams(C.Structure):
     _fields_ = [
         ("M", i32), ("N", i32), ("K", i32), ("dtype", i32), ("out_dtype", i32),
@@ -28,7 +36,7 @@ class PwGemmParams(C.Structure):
         ("col_scale", vp), ("col_shift", vp), ("row_bias", vp), ("rows_per_img", i32), ("ld_row_bias", i32),
         ("act", i32), ("R", vp), ("ldr", i32), ("stat_sum", vp), ("stat_sqs", vp),
         ("shuffle_r", i32), ("shuffle_h", i32), ("shuffle_w", i32),
-        ("a_scale", vp), ("a_shift", vp), ("a_act", i32), ("Bt_lo", vp),
+        ("a_scale", vp), ("a_shift", vp), ("a_act", i32), ("Bt_lo", vp), ("a_fin", C.POINTER(BnFin)),
     ]
 
 
@@ -46,6 +54,7 @@ class DwConvParams(C.Structure):
         ("stride", i32), ("dilation", i32), ("pad_top", i32), ("pad_left", i32), ("dtype", i32),
         ("x", vp), ("y", vp), ("w", vp), ("in_scale", vp), ("in_shift", vp), ("in_act", i32),
         ("out_scale", vp), ("out_shift", vp), ("out_act", i32), ("stat_sum", vp), ("stat_sqs", vp),
+        ("in_fin", C.POINTER(BnFin)),
     ]
 
 
@@ -70,6 +79,7 @@ class BnApplyParams(C.Structure):
     _fields_ = [
         ("M", i64), ("C", i32), ("dtype", i32), ("x", vp), ("y", vp), ("res", vp),
         ("scale", vp), ("shift", vp), ("act", i32), ("drop_rate", f32), ("drop_seed", u64), ("drop_seed_dev", vp),
+        ("fin", C.POINTER(BnFin)),
     ]
 
 

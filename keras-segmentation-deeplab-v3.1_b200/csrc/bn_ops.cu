@@ -13,28 +13,12 @@ extern std::atomic<long long> g_launches;
 // DLB_BN_STREAM=0 selects the register-staged BatchNorm streaming kernels (A/B measurements)
 static const bool g_bn_stream = [] { const char* e = getenv("DLB_BN_STREAM"); return !(e && e[0] == '0'); }();
 
-__global__ void bn_finalize_kernel(int C, double count, double* sum, double* sqs, const float* gamma,
-                                   const float* beta, float eps, float momentum, float* moving_mean,
-                                   float* moving_var, float* scale, float* shift, float* mean_out, float* rstd_out,
-                                   int reset) {
+__global__ void bn_finalize_kernel(int C, const dlb_bn_fin f, double* sum, double* sqs, int reset) {
   pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = sum[c] / count;
-  double var = sqs[c] / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float sc = gamma[c] * rstd;
-  scale[c] = sc;
-  shift[c] = beta[c] - static_cast<float>(mean) * sc;
-  if (mean_out) mean_out[c] = static_cast<float>(mean);
-  if (rstd_out) rstd_out[c] = rstd;
-  if (moving_mean) {
-    // Keras 2.2.4 / TF backend: moving average is fed the Bessel-corrected variance
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    moving_mean[c] = moving_mean[c] * momentum + (1.f - momentum) * static_cast<float>(mean);
-    moving_var[c] = moving_var[c] * momentum + (1.f - momentum) * static_cast<float>(unbiased);
-  }
+  float sc, sh;
+  bn_fin_channel(f, c, true, sc, sh);
   if (reset) { sum[c] = 0.0; sqs[c] = 0.0; }
 }
 
@@ -479,6 +463,7 @@ struct StreamArgs {
   int act, frozen;
   double* red; float* dgamma; float* dbeta;
   float drop_rate; uint64_t seed; const long long* seed_dev;      // Dropout after the activation (deeplabv3p.py:410)
+  int has_fin; dlb_bn_fin fin;          // kMode 0: scale / shift are finalised here from the batch statistics
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -542,8 +527,13 @@ __global__ void __launch_bounds__(kSThreads, 1) bn_stream_kernel(const StreamArg
   const float invM = 1.f / static_cast<float>(a.M);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    sc[k] = a.scale ? a.scale[c0 + k] : 1.f;
-    sh[k] = a.scale ? a.shift[c0 + k] : 0.f;
+    if (kMode == 0 && a.has_fin) {
+      // consumer-side finalisation: every thread derives its 8 channels; the first row of CTA 0 publishes them
+      bn_fin_channel(a.fin, c0 + k, blockIdx.x == 0 && active && r_in == 0, sc[k], sh[k]);
+    } else {
+      sc[k] = a.scale ? a.scale[c0 + k] : 1.f;
+      sh[k] = a.scale ? a.shift[c0 + k] : 0.f;
+    }
     k1[k] = (kMode == 2 && !a.frozen) ? static_cast<float>(a.red[c0 + k]) * invM : 0.f;
     k2[k] = (kMode == 2 && !a.frozen) ? static_cast<float>(a.red[a.C + c0 + k]) * invM : 0.f;
   }
@@ -726,8 +716,8 @@ extern "C" int dlb_bn_finalize(int C, double count, double* sum, double* sqs, co
                                float* shift, float* mean, float* rstd, int reset, void* stream) {
   DLB_REQUIRE(C > 0 && sum && sqs && gamma && beta && scale && shift, "bn_finalize: null pointer");
   DLB_REQUIRE(count > 0, "bn_finalize: count must be positive");
-  launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
-      C, count, sum, sqs, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, mean, rstd, reset);
+  const dlb_bn_fin f{sum, sqs, gamma, beta, eps, momentum, count, moving_mean, moving_var, scale, shift, mean, rstd};
+  launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), C, f, sum, sqs, reset);
   g_launches++;
   return check_launch("bn_finalize_kernel");
 }
@@ -741,21 +731,44 @@ extern "C" int dlb_bn_fold(int C, const float* gamma, const float* beta, const f
   return check_launch("bn_fold_kernel");
 }
 
+int dlb::check_bn_fin(const dlb_bn_fin* f, const char* who) {
+  DLB_REQUIRE(f->sum && f->sqs && f->gamma && f->beta && f->scale && f->shift, "%s: dlb_bn_fin with a null pointer", who);
+  DLB_REQUIRE(f->count > 0, "%s: dlb_bn_fin.count must be positive", who);
+  DLB_REQUIRE((f->moving_mean == nullptr) == (f->moving_var == nullptr), "%s: dlb_bn_fin needs both moving statistics or none", who);
+  return DLB_OK;
+}
+
+int dlb::bn_fin_standalone(int C, const dlb_bn_fin* f, void* stream) {
+  return dlb_bn_finalize(C, f->count, const_cast<double*>(f->sum), const_cast<double*>(f->sqs), f->gamma, f->beta, f->eps,
+                         f->momentum, f->moving_mean, f->moving_var, f->scale, f->shift, f->mean, f->rstd, 0, stream);
+}
+
 extern "C" int dlb_bn_act_apply(const dlb_bn_apply_params* p, void* stream) {
   DLB_REQUIRE(p && p->x && p->y, "bn_act_apply: null pointer");
   DLB_REQUIRE(p->C % 8 == 0, "bn_act_apply: C must be a multiple of 8 (C=%d)", p->C);
   DLB_REQUIRE(p->C / 8 <= 256, "bn_act_apply: C <= 2048");
-  ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, p->scale, p->shift, p->act, p->drop_rate, p->drop_seed,
-              reinterpret_cast<const long long*>(p->drop_seed_dev)};
+  const float* scale = p->scale; const float* shift = p->shift;
+  if (p->fin) {
+    const int rc = check_bn_fin(p->fin, "bn_act_apply");
+    if (rc) return rc;
+    scale = p->fin->scale; shift = p->fin->shift;
+  }
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
   if (g_bn_stream) {
     StreamArgs sa{};
     sa.M = p->M; sa.C = p->C; sa.in0 = p->x; sa.in1 = p->res; sa.out = p->y; sa.n_in = p->res ? 2 : 1;
-    sa.scale = p->scale; sa.shift = p->shift; sa.act = p->act;
+    sa.scale = scale; sa.shift = shift; sa.act = p->act;
     sa.drop_rate = p->drop_rate; sa.seed = p->drop_seed; sa.seed_dev = reinterpret_cast<const long long*>(p->drop_seed_dev);
+    if (p->fin) { sa.has_fin = 1; sa.fin = *p->fin; }
     const int rc = launch_bn_stream<0>(sa, p->dtype, st0);
     if (rc <= 0) return rc;
   }
+  if (p->fin) {       // shapes the streaming kernel does not take: finalise with the stand-alone kernel first
+    const int rc = bn_fin_standalone(p->C, p->fin, stream);
+    if (rc) return rc;
+  }
+  ApplyArgs a{p->M * p->C / 8, p->C, p->x, p->y, p->res, scale, shift, p->act, p->drop_rate, p->drop_seed,
+              reinterpret_cast<const long long*>(p->drop_seed_dev)};
   const int rpb_ = 256 / (p->C / 8);
   long long blocks_ = (p->M + static_cast<long long>(rpb_) * 4 - 1) / (static_cast<long long>(rpb_) * 4);
   const long long cap_ = static_cast<long long>(num_sms()) * 8;

@@ -416,6 +416,36 @@ __device__ __forceinline__ void xform_rows2(uint32_t box_saddr, int r, int dr, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Training-mode BatchNorm finalisation of one channel from the fp64 sums (dlb_bn_fin, deeplab_b200.h): the one place
+// this arithmetic lives -- the stand-alone kernel and the consumer-side prologues (bn_stream, the A-operand transform
+// of pw_gemm, the depthwise prologue) all call it, so a layer's scale / shift do not depend on which kernel finalised it.
+// Keras 2.2.4 / TF backend: the moving average is fed the Bessel-corrected variance.
+// ---------------------------------------------------------------------------------------------
+// Every multiply-add is spelled as an explicit fma / mul intrinsic: left to the compiler, contraction differed between the
+// kernels this is inlined into and the results were one ulp apart.
+__device__ __forceinline__ void bn_fin_channel(const dlb_bn_fin& f, int c, bool publish, float& sc, float& sh) {
+  const double mean = f.sum[c] / f.count;
+  double var = __fma_rn(-mean, mean, f.sqs[c] / f.count);
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(f.eps)));
+  const float mean_f = static_cast<float>(mean);
+  sc = __fmul_rn(f.gamma[c], rstd);
+  sh = __fmaf_rn(-mean_f, sc, f.beta[c]);
+  if (publish) {
+    f.scale[c] = sc;
+    f.shift[c] = sh;
+    if (f.mean) f.mean[c] = mean_f;
+    if (f.rstd) f.rstd[c] = rstd;
+    if (f.moving_mean) {
+      const double unbiased = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
+      const float keep = 1.f - f.momentum;
+      f.moving_mean[c] = __fmaf_rn(f.moving_mean[c], f.momentum, __fmul_rn(keep, mean_f));
+      f.moving_var[c] = __fmaf_rn(f.moving_var[c], f.momentum, __fmul_rn(keep, static_cast<float>(unbiased)));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: every kernel of the library is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_prologue(), so the CTAs of kernel i+1 are
 // scheduled (and run their launch / index-math prologue) while kernel i drains; griddepcontrol.wait returns only
@@ -432,6 +462,10 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_wait();
 }
 bool pdl_enabled();
+// dlb_bn_fin given to a kernel's host entry: argument check, and the stand-alone finalize launch for the shapes whose
+// kernel variant has no consumer-side prologue (bn_ops.cu)
+int check_bn_fin(const dlb_bn_fin* f, const char* who);
+int bn_fin_standalone(int C, const dlb_bn_fin* f, void* stream);
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};

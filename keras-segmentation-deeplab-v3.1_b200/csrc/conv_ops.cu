@@ -242,6 +242,7 @@ struct DwTileArgs {
   int B, H, W, C, Ho, Wo, stride, dil, pad_t, pad_l;
   const void* x; void* y; const float* w;
   const float* in_scale; const float* in_shift; int in_act;
+  int has_fin; dlb_bn_fin fin;   // dw_fwd_tma_h_kernel: the prologue affine is finalised here from the batch statistics
   const float* out_scale; const float* out_shift; int out_act;
   double* stat_sum; double* stat_sqs;
   const void* dy; float* dw;     // backward-weight mode
@@ -728,7 +729,21 @@ __global__ void __launch_bounds__(256, 2) dw_fwd_tma_h_kernel(const __grid_const
           for (int i = 0; i < 4; ++i) w2[t][i] = P2<T>::pack(a.w[ts * a.C + cc + 2 * i], a.w[ts * a.C + cc + 2 * i + 1]);
         }
       }
-      if (pro && tid < 64) {
+      if (pro && a.has_fin) {
+        // consumer-side BatchNorm finalisation: 32 threads derive the chunk's 64 channels from the fp64 sums; the CTA
+        // of spatial group 0 publishes them (the backward pass reads scale / shift / mean / rstd)
+        if (tid < 32) {
+          typename P2<T>::t* af = reinterpret_cast<typename P2<T>::t*>(s_aff);
+          const int ch = c0 + 2 * tid;
+          float sc0 = 0.f, sh0 = 0.f, sc1 = 0.f, sh1 = 0.f;
+          if (ch + 1 < a.C) {
+            bn_fin_channel(a.fin, ch, grp == 0, sc0, sh0);
+            bn_fin_channel(a.fin, ch + 1, grp == 0, sc1, sh1);
+          }
+          af[tid] = P2<T>::pack(sc0, sc1);
+          af[32 + tid] = P2<T>::pack(sh0, sh1);
+        }
+      } else if (pro && tid < 64) {
         typename P2<T>::t* af = reinterpret_cast<typename P2<T>::t*>(s_aff);
         const int ch = c0 + 2 * (tid & 31);
         const float* src = tid < 32 ? a.in_scale : a.in_shift;
@@ -1586,10 +1601,25 @@ extern "C" int dlb_dw_conv_fwd(const dlb_dw_conv_params* p, void* stream) {
   a.out_scale = p->out_scale; a.out_shift = p->out_shift; a.out_act = p->out_act;
   a.stat_sum = p->stat_sum; a.stat_sqs = p->stat_sqs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!dw_tile_fits(p->stride, p->dilation, dtype_size(p->dtype))) {
-    if (p->dtype == DLB_F16) return launch_dw_gather_fwd<__half>(p, st);
-    if (p->dtype == DLB_BF16) return launch_dw_gather_fwd<__nv_bfloat16>(p, st);
-    return launch_dw_gather_fwd<float>(p, st);
+  const bool tiled = dw_tile_fits(p->stride, p->dilation, dtype_size(p->dtype));
+  dlb_dw_conv_params q = *p;
+  if (p->in_fin) {
+    DLB_REQUIRE(p->in_scale == nullptr, "dw_conv_fwd: give in_fin or in_scale / in_shift, not both");
+    const int rc = check_bn_fin(p->in_fin, "dw_conv_fwd");
+    if (rc) return rc;
+    a.in_scale = q.in_scale = p->in_fin->scale; a.in_shift = q.in_shift = p->in_fin->shift;
+    if (tiled && p->dtype != DLB_F32 && p->C % 2 == 0) {
+      a.has_fin = 1; a.fin = *p->in_fin;        // the TMA kernel finalises in its prologue
+    } else {
+      const int rf = bn_fin_standalone(p->C, p->in_fin, stream);   // gather / fp32 kernels read finished tables
+      if (rf) return rf;
+    }
+    q.in_fin = nullptr;
+  }
+  if (!tiled) {
+    if (p->dtype == DLB_F16) return launch_dw_gather_fwd<__half>(&q, st);
+    if (p->dtype == DLB_BF16) return launch_dw_gather_fwd<__nv_bfloat16>(&q, st);
+    return launch_dw_gather_fwd<float>(&q, st);
   }
   if (p->dtype == DLB_F16) return launch_dw_tiled<__half>(a, st);
   if (p->dtype == DLB_BF16) return launch_dw_tiled<__nv_bfloat16>(a, st);

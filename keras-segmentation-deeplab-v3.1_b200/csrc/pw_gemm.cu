@@ -62,6 +62,7 @@ struct GemmArgs {
   const float* a_scale;   // A-operand transform (kXform): A := act(A * a_scale[k] + a_shift[k]) applied to the landed tile
   const float* a_shift;
   int a_act;
+  int has_afin; dlb_bn_fin afin;   // kXform: a_scale / a_shift are finalised in the prologue from the batch statistics
   int b_lo_given;  // tf32x3: the caller supplies the weights already split (Bt = hi part, Bt_lo = remainder)
   int tf32x3;      // fp32 operands on the tensor cores: A and B tiles are split in shared memory into a tf32-exact high part
                    // and the remainder, three kind::tf32 MMAs per k-step (hi*lo + lo*hi + hi*hi) ~ fp32 accuracy
@@ -183,8 +184,13 @@ pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (kXform && sizeof(OutT) == 2)
     for (int i = threadIdx.x; i < g.num_k_blocks * 64; i += kThreads) {
-      s_asc[i] = i < g.K ? g.a_scale[i] : 0.f;            // channels past K are TMA zero fill and must stay zero
-      s_ash[i] = i < g.K ? g.a_shift[i] : 0.f;
+      float sc = 0.f, sh = 0.f;                            // channels past K are TMA zero fill and must stay zero
+      if (i < g.K) {
+        if (g.has_afin) bn_fin_channel(g.afin, i, blockIdx.x == 0, sc, sh);    // CTA 0 publishes for the backward pass
+        else { sc = g.a_scale[i]; sh = g.a_shift[i]; }
+      }
+      s_asc[i] = sc;
+      s_ash[i] = sh;
     }
   tc_fence_before();
   __syncthreads();
@@ -976,8 +982,9 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   g.shuffle_cs = p->shuffle_r > 0 ? p->N / (p->shuffle_r * p->shuffle_r) : 0;
 
   const int tf32 = p->dtype == DLB_F32;
-  const int xform = !tf32 && p->a_scale != nullptr;
+  const int xform = !tf32 && (p->a_scale != nullptr || p->a_fin != nullptr);
   g.a_scale = p->a_scale; g.a_shift = p->a_shift; g.a_act = p->a_act;
+  if (p->a_fin) { g.has_afin = 1; g.afin = *p->a_fin; }
   size_t tail = 0;
   const int sets = plan_tc(p->N, p->K, p->M, p->out_dtype, p->shuffle_r, xform, tf32, &g, &tail);
   DLB_REQUIRE(sets > 0, "pw_gemm: N=%d K=%d leaves no room for a 2-stage pipeline", p->N, p->K);
@@ -1025,7 +1032,7 @@ static int launch_tc(const dlb_pw_gemm_params* p, cudaStream_t st) {
   }
   if (xform) {
     // the training-forward project conv: raw depthwise output in, raw project output + statistics out
-    DLB_REQUIRE(p->a_shift != nullptr, "pw_gemm: a_scale without a_shift");
+    DLB_REQUIRE(p->a_fin != nullptr || p->a_shift != nullptr, "pw_gemm: a_scale without a_shift");
     DLB_REQUIRE(sets == 4 && lean && g.tma_store && p->dtype == p->out_dtype,
                 "pw_gemm: the A-operand transform needs a 16-bit row-major output of the input dtype, no output "
                 "affine / bias / residual, and a 16-byte aligned C");
@@ -1111,6 +1118,18 @@ extern "C" int dlb_pw_gemm(const dlb_pw_gemm_params* p, void* stream) {
     DLB_REQUIRE(p->R == nullptr, "pw_gemm: residual with shuffle store unsupported");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->a_fin) {
+    DLB_REQUIRE(p->a_scale == nullptr, "pw_gemm: give a_fin or a_scale / a_shift, not both");
+    const int rc = check_bn_fin(p->a_fin, "pw_gemm");
+    if (rc) return rc;
+    if (p->dtype == DLB_F32) {      // the fp32 kernels read finished tables: stand-alone finalize, then a_scale / a_shift
+      const int rf = bn_fin_standalone(p->K, p->a_fin, stream);
+      if (rf) return rf;
+      dlb_pw_gemm_params q = *p;
+      q.a_scale = p->a_fin->scale; q.a_shift = p->a_fin->shift; q.a_fin = nullptr;
+      return dlb_pw_gemm(&q, stream);
+    }
+  }
   if (p->dtype == DLB_F32) {
     // fp32 operands: 3xTF32 on the tensor cores (error ~1e-6 relative, the fp32 parity mode of BASELINE config 3) unless
     // the shape is tiny / unaligned / carries an A-operand transform, or DLB_F32_SIMT=1 asks for the exact FMA kernel

@@ -116,6 +116,9 @@ class Engine:
         self.fuse_dw_bn = os.environ.get("DLB_FUSE_DW_BN", "1") != "0"
         # inference: depthwise -> project of an inverted-residual block in one kernel (DLB_FUSE_MBCONV=0: separate)
         self.fuse_dw_project = os.environ.get("DLB_FUSE_MBCONV", "1") != "0"
+        # BatchNorm statistics are finalised in the prologue of the kernel that consumes them (dlb_bn_fin) instead of by
+        # 54 stand-alone launches per step; DLB_FUSE_BN_FIN=0 restores the stand-alone kernel
+        self.fuse_bn_fin = os.environ.get("DLB_FUSE_BN_FIN", "1") != "0"
         # data parallel: gradient buckets are all-reduced while the rest of the backward pass runs, inside the captured
         # step (DLB_AR_IN_GRAPH=0: one all-reduce of the whole buffer between two graphs, the round-1 schedule)
         self.ar_in_graph = os.environ.get("DLB_AR_IN_GRAPH", "1") != "0"
@@ -572,16 +575,29 @@ class Engine:
     def _finalize(self, bn: BN, count):
         upd = bn.layer.trainable
         ops.bn_finalize(count, bn.sum, bn.sqs, bn.gamma.data, bn.beta.data, bn.eps, bn.momentum,
-                        bn.mm.data if upd else None, bn.mv.data if upd else None, bn.scale, bn.shift, bn.mean, bn.rstd)
+                        bn.mm.data if upd else None, bn.mv.data if upd else None, bn.scale, bn.shift, bn.mean, bn.rstd,
+                        reset=False)
+
+    def _fin(self, bn: BN, count):
+        """scale / shift of `bn` for its consumer: a dlb_bn_fin (the consumer finalises in its prologue), or the finished
+        tables after a stand-alone finalize launch (DLB_FUSE_BN_FIN=0).  Returns (fin, scale, shift)."""
+        if self.fuse_bn_fin:
+            upd = bn.layer.trainable
+            return ops.bn_fin(count, bn.sum, bn.sqs, bn.gamma.data, bn.beta.data, bn.eps, bn.momentum,
+                              bn.mm.data if upd else None, bn.mv.data if upd else None, bn.scale, bn.shift, bn.mean,
+                              bn.rstd), None, None
+        self._finalize(bn, count)
+        return None, bn.scale, bn.shift
 
     def forward_train(self, ws, B, dropout: bool):
         geo = ws["geo"]
         img = ws["img"]
         h0, w0 = geo[0]["h"], geo[0]["w"]
         bn = self.stem_bn
+        ops.fill_zero(self.bn_sums)      # every BatchNorm's fp64 accumulators, once per step (consumers do not clear them)
         ops.stem_conv_fwd(img, self.stem.params[0].data, ws["y_stem"], stat_sum=bn.sum, stat_sqs=bn.sqs)
-        self._finalize(bn, B * h0 * w0)
-        ops.bn_act_apply(ws["y_stem"], ws["x0"], scale=bn.scale, shift=bn.shift, act=ACT_RELU6)
+        fin, sc, sh = self._fin(bn, B * h0 * w0)
+        ops.bn_act_apply(ws["y_stem"], ws["x0"], scale=sc, shift=sh, act=ACT_RELU6, fin=fin)
         for i, (b, g) in enumerate(zip(self.blocks, geo)):
             xin = ws[f"x{i}"]
             Min, Mout = B * g["h"] * g["w"], B * g["ho"] * g["wo"]
@@ -589,26 +605,26 @@ class Engine:
             if b["bid"]:
                 ebn = b["expand_bn"]
                 ops.pw_gemm(xin, self.wcopies[b["expand"].name]["nk"], ws[f"y_e{i}"], stat_sum=ebn.sum, stat_sqs=ebn.sqs)
-                self._finalize(ebn, Min)
+                fin, sc, sh = self._fin(ebn, Min)
                 ops.dw_conv_fwd(ws[f"y_e{i}"], b["dw"].params[0].data, ws[f"y_d{i}"], stride=b["stride"],
-                                dilation=b["rate"], pad_top=g["pt"], pad_left=g["pl"], in_scale=ebn.scale,
-                                in_shift=ebn.shift, in_act=ACT_RELU6, stat_sum=dbn.sum, stat_sqs=dbn.sqs)
+                                dilation=b["rate"], pad_top=g["pt"], pad_left=g["pl"], in_scale=sc, in_shift=sh,
+                                in_fin=fin, in_act=ACT_RELU6, stat_sum=dbn.sum, stat_sqs=dbn.sqs)
             else:
                 ops.dw_conv_fwd(xin, b["dw"].params[0].data, ws[f"y_d{i}"], stride=b["stride"], dilation=b["rate"],
                                 pad_top=g["pt"], pad_left=g["pl"], stat_sum=dbn.sum, stat_sqs=dbn.sqs)
-            self._finalize(dbn, Mout)
+            fin, sc, sh = self._fin(dbn, Mout)
             # depthwise_BN + relu6 are applied to the A tiles inside the project GEMM: the normalised activation is
             # never written (one read + one write of the 6C-wide tensor less per block, and nothing to save for backward)
             pbn = b["project_bn"]
             if self.fuse_dw_bn:
                 ops.pw_gemm(ws[f"y_d{i}"], self.wcopies[b["project"].name]["nk"], ws[f"y_p{i}"], stat_sum=pbn.sum,
-                            stat_sqs=pbn.sqs, a_scale=dbn.scale, a_shift=dbn.shift, a_act=ACT_RELU6)
+                            stat_sqs=pbn.sqs, a_scale=sc, a_shift=sh, a_fin=fin, a_act=ACT_RELU6)
             else:
-                ops.bn_act_apply(ws[f"y_d{i}"], ws[f"a_d{i}"], scale=dbn.scale, shift=dbn.shift, act=ACT_RELU6)
+                ops.bn_act_apply(ws[f"y_d{i}"], ws[f"a_d{i}"], scale=sc, shift=sh, fin=fin, act=ACT_RELU6)
                 ops.pw_gemm(ws[f"a_d{i}"], self.wcopies[b["project"].name]["nk"], ws[f"y_p{i}"], stat_sum=pbn.sum,
                             stat_sqs=pbn.sqs)
-            self._finalize(pbn, Mout)
-            ops.bn_act_apply(ws[f"y_p{i}"], ws[f"x{i + 1}"], scale=pbn.scale, shift=pbn.shift, act=ACT_NONE,
+            fin, sc, sh = self._fin(pbn, Mout)
+            ops.bn_act_apply(ws[f"y_p{i}"], ws[f"x{i + 1}"], scale=sc, shift=sh, fin=fin, act=ACT_NONE,
                              res=xin if b["skip"] else None)
         x16 = ws["x17"]
         fh, fw = self.fh, self.fw
@@ -617,21 +633,21 @@ class Engine:
         ops.global_avgpool_fwd(x16, ws["pooled"])
         ibn = self.image_pooling_bn
         ops.pw_gemm(ws["pooled"], self.wcopies["image_pooling"]["nk32"], ws["y_ip"], stat_sum=ibn.sum, stat_sqs=ibn.sqs)
-        self._finalize(ibn, B)
-        ops.bn_act_apply(ws["y_ip"], ws["b4"], scale=ibn.scale, shift=ibn.shift, act=ACT_RELU)
+        fin, sc, sh = self._fin(ibn, B)
+        ops.bn_act_apply(ws["y_ip"], ws["b4"], scale=sc, shift=sh, fin=fin, act=ACT_RELU)
         wcp = self.wcopies["concat_projection"]
         ops.pw_gemm(ws["b4"], wcp["nk32"], ws["rowbias"], K=256)
         abn = self.aspp0_bn
         ops.pw_gemm(x16, self.wcopies["aspp0"]["nk"], ws["y_a0"], stat_sum=abn.sum, stat_sqs=abn.sqs)
-        self._finalize(abn, M)
-        ops.bn_act_apply(ws["y_a0"], ws["a_a0"], scale=abn.scale, shift=abn.shift, act=ACT_RELU)
+        fin, sc, sh = self._fin(abn, M)
+        ops.bn_act_apply(ws["y_a0"], ws["a_a0"], scale=sc, shift=sh, fin=fin, act=ACT_RELU)
         cbn = self.concat_projection_bn
         ops.pw_gemm(ws["a_a0"], wcp["nk"][:, 256:], ws["y_cp"], row_bias=ws["rowbias"], rows_per_img=fh * fw,
                     stat_sum=cbn.sum, stat_sqs=cbn.sqs)
-        self._finalize(cbn, M)
+        fin, sc, sh = self._fin(cbn, M)
         # the dropout mask is a counter-based hash of (seed, optimizer iteration on the device, element index):
         # forward and backward regenerate the same mask, and a replayed CUDA graph still gets a fresh one per step
-        ops.bn_act_apply(ws["y_cp"], ws["feat"], scale=cbn.scale, shift=cbn.shift, act=ACT_RELU,
+        ops.bn_act_apply(ws["y_cp"], ws["feat"], scale=sc, shift=sh, fin=fin, act=ACT_RELU,
                          drop_rate=self.dropout_rate if dropout else 0.0, drop_seed=self.dropout_seed,
                          drop_seed_dev=self.adam_step)
         self._head_fwd(ws, ws["feat"])

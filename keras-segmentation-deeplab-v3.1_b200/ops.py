@@ -35,8 +35,9 @@ def _mat(t: torch.Tensor) -> Tuple[int, int, int]:
 def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional[int] = None, N: Optional[int] = None,
             n_store: Optional[int] = None, col_scale=None, col_shift=None, row_bias=None, rows_per_img: int = 1,
             act: int = ACT_NONE, residual=None, stat_sum=None, stat_sqs=None, shuffle: Optional[Tuple[int, int, int]] = None,
-            a_scale=None, a_shift=None, a_act: int = ACT_NONE):
+            a_scale=None, a_shift=None, a_act: int = ACT_NONE, a_fin=None):
     """out[M, :n_store] = epilogue(A'[M, K] @ Bt[N, K]^T), A' = a_act(A * a_scale + a_shift) if given; see dlb_pw_gemm.
+    a_fin (a `bn_fin(...)`) instead of a_scale / a_shift: the kernel finalises the producing BatchNorm itself.
     fp32 inference weights may be passed pre-split as a tuple (hi, lo) from `f32_split` (3xTF32, see dlb_pw_gemm_params)."""
     Bt_lo = None
     if isinstance(Bt, (tuple, list)):
@@ -68,6 +69,8 @@ def pw_gemm(A: torch.Tensor, Bt: torch.Tensor, out: torch.Tensor, *, K: Optional
     p.stat_sum, p.stat_sqs = L.ptr(stat_sum), L.ptr(stat_sqs)
     p.a_scale, p.a_shift, p.a_act = L.ptr(a_scale), L.ptr(a_shift), a_act
     p.Bt_lo = L.ptr(Bt_lo)
+    if a_fin is not None:
+        p.a_fin = C.pointer(a_fin)
     L.check(L.lib().dlb_pw_gemm(C.byref(p), L.stream_ptr()), "pw_gemm")
     return out
 
@@ -106,7 +109,7 @@ def pw_wgrad(A: torch.Tensor, dY: torch.Tensor, dW: torch.Tensor, *, K: Optional
 
 def dw_conv_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, stride: int, dilation: int, pad_top: int,
                 pad_left: int, in_scale=None, in_shift=None, in_act: int = ACT_NONE, out_scale=None, out_shift=None,
-                out_act: int = ACT_NONE, stat_sum=None, stat_sqs=None):
+                out_act: int = ACT_NONE, stat_sum=None, stat_sqs=None, in_fin=None):
     L.require_cuda(x, w, y)
     p = L.DwConvParams()
     p.B, p.H, p.W, p.C = x.shape
@@ -117,6 +120,8 @@ def dw_conv_fwd(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, stride: in
     p.in_scale, p.in_shift, p.in_act = L.ptr(in_scale), L.ptr(in_shift), in_act
     p.out_scale, p.out_shift, p.out_act = L.ptr(out_scale), L.ptr(out_shift), out_act
     p.stat_sum, p.stat_sqs = L.ptr(stat_sum), L.ptr(stat_sqs)
+    if in_fin is not None:
+        p.in_fin = C.pointer(in_fin)
     L.check(L.lib().dlb_dw_conv_fwd(C.byref(p), L.stream_ptr()), "dw_conv_fwd")
     return y
 
@@ -166,6 +171,19 @@ def bn_finalize(count: float, s: torch.Tensor, q: torch.Tensor, gamma, beta, eps
                                     L.stream_ptr()), "bn_finalize")
 
 
+def bn_fin(count: float, s: torch.Tensor, q: torch.Tensor, gamma, beta, eps: float, momentum: float, moving_mean,
+           moving_var, scale, shift, mean=None, rstd=None):
+    """dlb_bn_fin for the `fin=` / `a_fin=` / `in_fin=` arguments: the consuming kernel finalises the BatchNorm from the
+    fp64 sums in its prologue (same arithmetic as `bn_finalize`, which this replaces launch for launch).  The sums are
+    not cleared: zero them once per step."""
+    f = L.BnFin()
+    f.sum, f.sqs, f.gamma, f.beta = s.data_ptr(), q.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    f.eps, f.momentum, f.count = eps, momentum, float(count)
+    f.moving_mean, f.moving_var = L.ptr(moving_mean), L.ptr(moving_var)
+    f.scale, f.shift, f.mean, f.rstd = scale.data_ptr(), shift.data_ptr(), L.ptr(mean), L.ptr(rstd)
+    return f
+
+
 def bn_fold(gamma, beta, moving_mean, moving_var, eps: float, scale, shift):
     L.check(L.lib().dlb_bn_fold(gamma.numel(), gamma.data_ptr(), beta.data_ptr(), moving_mean.data_ptr(),
                                 moving_var.data_ptr(), eps, scale.data_ptr(), shift.data_ptr(), L.stream_ptr()),
@@ -173,7 +191,7 @@ def bn_fold(gamma, beta, moving_mean, moving_var, eps: float, scale, shift):
 
 
 def bn_act_apply(x: torch.Tensor, y: torch.Tensor, *, scale=None, shift=None, act: int = ACT_NONE, res=None,
-                 drop_rate: float = 0.0, drop_seed: int = 0, drop_seed_dev=None):
+                 drop_rate: float = 0.0, drop_seed: int = 0, drop_seed_dev=None, fin=None):
     L.require_cuda(x, y)
     p = L.BnApplyParams()
     p.C = x.shape[-1]
@@ -182,6 +200,8 @@ def bn_act_apply(x: torch.Tensor, y: torch.Tensor, *, scale=None, shift=None, ac
     p.x, p.y, p.res = x.data_ptr(), y.data_ptr(), L.ptr(res)
     p.scale, p.shift, p.act = L.ptr(scale), L.ptr(shift), act
     p.drop_rate, p.drop_seed, p.drop_seed_dev = drop_rate, drop_seed, L.ptr(drop_seed_dev)
+    if fin is not None:
+        p.fin = C.pointer(fin)
     L.check(L.lib().dlb_bn_act_apply(C.byref(p), L.stream_ptr()), "bn_act_apply")
     return y
 

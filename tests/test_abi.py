@@ -40,7 +40,8 @@ def test_struct_sizes_match_header(lib):
              "dlb_dw_conv_params": lib.DwConvParams, "dlb_dw_conv_bwd_params": lib.DwConvBwdParams,
              "dlb_stem_conv_params": lib.StemConvParams, "dlb_bn_apply_params": lib.BnApplyParams,
              "dlb_bn_bwd_params": lib.BnBwdParams, "dlb_softmax_ce_params": lib.SoftmaxCeParams,
-             "dlb_crf_config": lib.CrfConfig, "dlb_sepconv_fused_params": lib.SepconvFusedParams}
+             "dlb_crf_config": lib.CrfConfig, "dlb_sepconv_fused_params": lib.SepconvFusedParams,
+             "dlb_bn_fin": lib.BnFin, "dlb_aug_params": lib.AugParams}
     src = '#include <stdio.h>\n#include "deeplab_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

@@ -554,3 +554,108 @@ def test_dropout_in_streaming_bn_kernels_matches_fp32_mask(dt):
     clear = z.abs() > 1e-2                                                        # away from the ReLU kink
     assert rel_err(dx[clear], dx32[clear]) < (3e-3 if dt == torch.float16 else 2e-2)
     assert torch.equal((dx != 0)[clear & (da != 0)], (dx32 != 0)[clear & (da != 0)])
+
+
+def _bn_state(C, g):
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g)
+    mm, mv = torch.randn(C, device="cuda", generator=g), torch.rand(C, device="cuda", generator=g) + 0.5
+    return gamma, beta, mm, mv
+
+
+def _fin_pair(ops, x2d, gamma, beta, mm, mv, moving=True):
+    """(stand-alone finalize results, a dlb_bn_fin over cloned state + its output tensors) for the same statistics."""
+    C = x2d.shape[1]
+    xd = x2d.double()
+    ssum, ssqs = xd.sum(0), (xd * xd).sum(0)
+    ref = dict(mm=mm.clone(), mv=mv.clone(), **{k: torch.empty(C, device="cuda") for k in ("scale", "shift", "mean", "rstd")})
+    ops.bn_finalize(x2d.shape[0], ssum.clone(), ssqs.clone(), gamma, beta, 1e-3, 0.999, ref["mm"] if moving else None,
+                    ref["mv"] if moving else None, ref["scale"], ref["shift"], ref["mean"], ref["rstd"], reset=False)
+    out = dict(mm=mm.clone(), mv=mv.clone(), **{k: torch.full((C,), float("nan"), device="cuda") for k in ("scale", "shift", "mean", "rstd")})
+    fin = ops.bn_fin(x2d.shape[0], ssum, ssqs, gamma, beta, 1e-3, 0.999, out["mm"] if moving else None,
+                     out["mv"] if moving else None, out["scale"], out["shift"], out["mean"], out["rstd"])
+    return ref, out, fin, (ssum, ssqs)
+
+
+def _same_state(ref, out):
+    for k in ref:
+        assert torch.equal(ref[k], out[k]), k
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,C,res,moving", [(16384, 96, True, True), (4096 + 5, 32, False, True), (8192, 960, False, False),
+                                            (16, 256, False, True)])
+def test_bn_apply_consumer_side_finalize_is_bit_identical(dt, M, C, res, moving):
+    """dlb_bn_fin through bn_act_apply (streaming kernel and the fallback shapes): output, scale / shift / mean / rstd
+    and the moving statistics equal the stand-alone finalize + apply bit for bit; the sums are left untouched."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(C + M)
+    x = (torch.randn(M, C, device="cuda", generator=g) * 1.5 + 0.3).to(dt)
+    r = torch.randn(M, C, device="cuda", generator=g).to(dt) if res else None
+    gamma, beta, mm, mv = _bn_state(C, g)
+    ref, out, fin, (ssum, ssqs) = _fin_pair(ops, x, gamma, beta, mm, mv, moving)
+    s0 = ssum.clone()
+    y0, y1 = torch.empty_like(x), torch.empty_like(x)
+    ops.bn_act_apply(x, y0, scale=ref["scale"], shift=ref["shift"], act=2, res=r)
+    ops.bn_act_apply(x, y1, fin=fin, act=2, res=r)
+    assert torch.equal(y0, y1)
+    _same_state(ref, out)
+    assert torch.equal(ssum, s0)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,K,N", [(16384, 576, 96), (8192, 960, 160), (4096 + 37, 96, 24), (1024, 32, 16)])
+def test_pw_gemm_a_operand_consumer_side_finalize(dt, M, K, N):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(K + N)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 1.5 + 0.3).to(dt)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(dt)
+    gamma, beta, mm, mv = _bn_state(K, g)
+    ref, out, fin, _ = _fin_pair(ops, a, gamma, beta, mm, mv)
+    y0, y1 = torch.empty(M, N, device="cuda", dtype=dt), torch.empty(M, N, device="cuda", dtype=dt)
+    s0, q0, s1, q1 = (torch.zeros(N, device="cuda", dtype=torch.float64) for _ in range(4))
+    ops.pw_gemm(a, w, y0, stat_sum=s0, stat_sqs=q0, a_scale=ref["scale"], a_shift=ref["shift"], a_act=2)
+    ops.pw_gemm(a, w, y1, stat_sum=s1, stat_sqs=q1, a_fin=fin, a_act=2)
+    assert torch.equal(y0, y1)
+    _same_state(ref, out)
+    assert rel_err(s1, s0) < 1e-6 and rel_err(q1, q0) < 1e-6      # atomics: order differs run to run
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("H,C,stride,dil", [(64, 96, 1, 1), (64, 144, 2, 1), (32, 384, 1, 2), (32, 960, 1, 4), (16, 64, 1, 36)])
+def test_dw_conv_prologue_consumer_side_finalize(dt, H, C, stride, dil):
+    ops = _ops()
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(C + dil)
+    x = (torch.randn(B, H, H, C, device="cuda", generator=g) * 1.5 + 0.3).to(dt)
+    w = torch.randn(3, 3, C, 1, device="cuda", generator=g) * 0.3
+    gamma, beta, mm, mv = _bn_state(C, g)
+    ref, out, fin, _ = _fin_pair(ops, x.view(-1, C), gamma, beta, mm, mv)
+    Ho = (H + stride - 1) // stride
+    pad = max((Ho - 1) * stride + 2 * dil + 1 - H, 0) // 2
+    y0, y1 = (torch.empty(B, Ho, Ho, C, device="cuda", dtype=dt) for _ in range(2))
+    s0, q0, s1, q1 = (torch.zeros(C, device="cuda", dtype=torch.float64) for _ in range(4))
+    kw = dict(stride=stride, dilation=dil, pad_top=pad, pad_left=pad, in_act=2)
+    ops.dw_conv_fwd(x, w, y0, in_scale=ref["scale"], in_shift=ref["shift"], stat_sum=s0, stat_sqs=q0, **kw)
+    ops.dw_conv_fwd(x, w, y1, in_fin=fin, stat_sum=s1, stat_sqs=q1, **kw)
+    assert torch.equal(y0, y1)
+    _same_state(ref, out)
+    assert rel_err(s1, s0) < 1e-6 and rel_err(q1, q0) < 1e-6
+
+
+def test_consumer_side_finalize_argument_checks():
+    ops = _ops()
+    C = 64
+    x = torch.randn(2048, C, device="cuda").half()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    gamma, beta, mm, mv = _bn_state(C, g)
+    ref, out, fin, _ = _fin_pair(ops, x, gamma, beta, mm, mv)
+    y = torch.empty_like(x)
+    fin.count = 0.0
+    with pytest.raises(RuntimeError, match="count"):
+        ops.bn_act_apply(x, y, fin=fin, act=2)
+    fin.count = 2048.0
+    w = torch.randn(32, C, device="cuda").half()
+    with pytest.raises(RuntimeError, match="not both"):
+        ops.pw_gemm(x, w, torch.empty(2048, 32, device="cuda", dtype=torch.float16), a_fin=fin, a_scale=ref["scale"],
+                    a_shift=ref["shift"], a_act=2)
