@@ -666,7 +666,8 @@ static int launch_bn_stream(StreamArgs a, int dtype, cudaStream_t st) {
   a.cv = a.C / 8;
   a.rpb = kSConsumers / a.cv;
   const long long pass_bytes = static_cast<long long>(a.rpb) * a.C * 2;
-  a.U = static_cast<int>(24576 / pass_bytes);
+  static const long long stage_target = [] { const char* e = getenv("DLB_BN_STAGE_KB"); return (e ? atoll(e) : 32) * 1024; }();
+  a.U = static_cast<int>(stage_target / pass_bytes);
   if (a.U < 1) a.U = 1;
   a.rows_per_stage = a.rpb * a.U;
   a.slot_bytes = static_cast<uint32_t>((static_cast<long long>(a.rows_per_stage) * a.C * 2 + 127) / 128 * 128);
