@@ -104,8 +104,15 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
   constexpr int PX = TILE * S;                        // output pixels per tile side (64 or 32)
   constexpr int RG = 256 / PX;                        // thread = (pixel column, row group); a row group owns cell rows
   static_assert(TILE % RG == 0 && S <= 32 && (S & (S - 1)) == 0, "tile / thread mapping");
+  // gradient tiles are warp-private: shared-memory atomicAdd(float) is a compare-and-swap loop (37 % of this kernel's
+  // stall samples sat on it); a warp's leader lanes instead read-modify-write the warp's own tile, ordered by
+  // __syncwarp, and the eight tiles are summed once at the end
+  constexpr int CW = 32 / S;                          // low-res cells a warp spans
+  constexpr int GC = CW + 1;                          // corner columns of a warp's tile
+  constexpr int NIT = TILE / RG;                      // cell rows a warp visits; its tile holds their 2 corner rows each
+  constexpr int GSZ = 2 * NIT * GC * C;
   __shared__ float s_log[TP * TP * C];
-  __shared__ float s_grad[TP * TP * C];
+  __shared__ float s_grad[8][GSZ];
   __shared__ float s_loss[8];
   const int tiles_x = (a.w + TILE - 1) / TILE, tiles_y = (a.h + TILE - 1) / TILE;
   const int tile = blockIdx.x % (tiles_x * tiles_y);
@@ -116,8 +123,8 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
     const int c = i % C, cell = i / C;
     const int cy = min(ty0 + cell / TP, a.h - 1), cx = min(tx0 + cell % TP, a.w - 1);
     s_log[i] = a.logits[((static_cast<size_t>(b) * a.h + cy) * a.w + cx) * a.ldl + c];
-    s_grad[i] = 0.f;
   }
+  for (int i = tid; i < 8 * GSZ; i += 256) (&s_grad[0][0])[i] = 0.f;
   __syncthreads();
   const float gs = *a.grad_scale;
   float loss_acc = 0.f;
@@ -186,8 +193,20 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
         }
       }
     }
-    // fold over the S lanes of the cell (same cx0 / cx1), split by the x weights
+    // fold over the S lanes of the cell (same cx0 / cx1), split by the x weights; the leaders of a warp own distinct
+    // cells, so their left-corner updates never collide, nor do their right-corner updates -- only a cell's right
+    // corner with its neighbour's left one, which the __syncwarp between the two halves orders
     const bool leader = (lane % S) == 0;
+    const int gx0 = cx0 - (((warp * 32) % PX) / S);    // corner column inside the warp's tile
+    // on the right image edge cx1 is clamped to cx0: that cell's right-corner share is folded into its left corner, or
+    // its right-corner update would land on the slot the neighbouring leader updates in the same instruction
+    const bool xclamp = cx1 == cx0;
+    const int gx1 = gx0 + 1;
+    const int r0 = 2 * ((cy0 - rg) / RG), r1 = r0 + (cy1 - cy0);      // corner rows inside the warp's tile
+    float* g00 = &s_grad[warp][(r0 * GC + gx0) * C];
+    float* g10 = &s_grad[warp][(r1 * GC + gx0) * C];
+    float* g01 = &s_grad[warp][(r0 * GC + gx1) * C];
+    float* g11 = &s_grad[warp][(r1 * GC + gx1) * C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       float v00 = acc0[c] * (1.f - fx), v01 = acc0[c] * fx, v10 = acc1[c] * (1.f - fx), v11 = acc1[c] * fx;
@@ -198,12 +217,11 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
         v10 += __shfl_xor_sync(0xffffffffu, v10, o);
         v11 += __shfl_xor_sync(0xffffffffu, v11, o);
       }
-      if (leader) {
-        if (v00 != 0.f) atomicAdd(&s_grad[(cy0 * TP + cx0) * C + c], v00);
-        if (v01 != 0.f) atomicAdd(&s_grad[(cy0 * TP + cx1) * C + c], v01);
-        if (v10 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx0) * C + c], v10);
-        if (v11 != 0.f) atomicAdd(&s_grad[(cy1 * TP + cx1) * C + c], v11);
-      }
+      if (xclamp) { v00 += v01; v10 += v11; v01 = 0.f; v11 = 0.f; }
+      if (leader) { g00[c] += v00; g10[c] += v10; }      // (r1 == r0 on the bottom edge: same thread, program order)
+      __syncwarp();
+      if (leader) { g01[c] += v01; g11[c] += v11; }
+      __syncwarp();
     }
   }
 #pragma unroll
@@ -215,11 +233,24 @@ __global__ void __launch_bounds__(256, 2) resize_softmax_ce_kernel(const CeArgs 
     for (int i = 0; i < 8; ++i) t += s_loss[i];
     atomicAdd(a.loss_sum, static_cast<double>(t));
   }
+  // sum the warp tiles: warp w covers corner columns [w0, w0 + CW] of the CTA tile (w0 = ((w * 32) % PX) / S) and the
+  // corner rows rg_w + it * RG + {0, 1} (rg_w = (w * 32) / PX)
   for (int i = tid; i < TP * TP * C; i += 256) {
-    const float v = s_grad[i];
-    if (v == 0.f) continue;
     const int c = i % C, cell = i / C;
-    const int cy = ty0 + cell / TP, cx = tx0 + cell % TP;
+    const int ry = cell / TP, rx = cell % TP;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int gx = rx - ((w * 32) % PX) / S;
+      if (gx < 0 || gx >= GC) continue;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int dy = ry - ((w * 32) / PX + it * RG);
+        if (dy == 0 || dy == 1) v += s_grad[w][((2 * it + dy) * GC + gx) * C + c];
+      }
+    }
+    if (v == 0.f) continue;
+    const int cy = ty0 + ry, cx = tx0 + rx;
     if (cy < a.h && cx < a.w) atomicAdd(&a.dlogits[((static_cast<size_t>(b) * a.h + cy) * a.w + cx) * a.ldl + c], v);
   }
 }

@@ -336,6 +336,19 @@ def test_small_gemm():
     out2 = torch.empty(320, 256, device="cuda")
     ops.small_gemm(A, out, out2, M=320, N=256, K=16, transA=True, alpha=2.0)
     assert rel_err(out2, 2 * A.t() @ out) < 1e-5
+    # both operands K-contiguous (the image-pooling dgrads): warp-per-column kernel, odd K, beta accumulation
+    for M, N, K in [(16, 320, 256), (16, 256, 256), (3, 21, 77), (64, 40, 512)]:
+        A2, B2 = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+        c0 = torch.randn(M, N, device="cuda")
+        o = c0.clone()
+        ops.small_gemm(A2, B2, o, M=M, N=N, K=K, transB=True, alpha=0.5, beta=2.0)
+        assert rel_err(o, 0.5 * A2 @ B2.t() + 2.0 * c0) < 1e-5
+        ops.small_gemm(A2, B2, o, M=M, N=N, K=K, transB=True)
+        assert rel_err(o, A2 @ B2.t()) < 1e-5
+    A3, B3 = torch.randn(8, 600, device="cuda"), torch.randn(24, 600, device="cuda")       # K > 512: the generic kernel
+    o3 = torch.empty(8, 24, device="cuda")
+    ops.small_gemm(A3, B3, o3, M=8, N=24, K=600, transB=True)
+    assert rel_err(o3, A3 @ B3.t()) < 1e-5
 
 
 @pytest.mark.parametrize("h,w,S,ldl", [(16, 16, 8, 32), (12, 20, 8, 32), (16, 24, 4, 32), (32, 32, 1, 21)])
